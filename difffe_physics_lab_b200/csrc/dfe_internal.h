@@ -1,0 +1,77 @@
+// Internal definitions shared by the translation units of libdfe_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "dfe.h"
+
+namespace dfe {
+
+void set_error(const char* fmt, ...);
+
+#define DFE_CUDA_OK(expr)                                                              \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      ::dfe::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                       __LINE__);                                                      \
+      return DFE_ERR_CUDA;                                                             \
+    }                                                                                  \
+  } while (0)
+
+#define DFE_REQUIRE(cond, ...)          \
+  do {                                  \
+    if (!(cond)) {                      \
+      ::dfe::set_error(__VA_ARGS__);    \
+      return DFE_ERR_INVALID;           \
+    }                                   \
+  } while (0)
+
+// Device-side view of a mesh (plain pointers; passed by value to kernels).
+struct MeshDev {
+  int dim, npe;
+  int n_nodes, n_el, n_dir, n_free;
+  int nnz_full, nnz_free, sell_nnz, n_slices;
+  const double* nodes;       // (n_nodes, dim)
+  const int* elems;          // (n_el, npe)
+  const int* adj_ptr;        // (n_nodes+1) node -> adjacent elements, ascending element id
+  const int* adj_elem;       // (nadj)
+  const int* adj_loc;        // (nadj) local index of the node inside the element
+  const int* adj_slot;       // (nadj*npe) index into vals_full of (node, elem[q])
+  const int* rowptr;         // (n_nodes+1) full CSR
+  const int* col;            // (nnz_full)
+  const int* free_nodes;     // (n_free) node id of free row r
+  const int* free_rank;      // (n_nodes) rank or -1
+  const int* dir_idx;        // (n_dir) dict order
+  const double* dir_val;     // (n_dir)
+  const int* rowptr_f;       // (n_free+1) K_free CSR
+  const int* col_f;          // (nnz_free)
+  const int* src_f;          // (nnz_free) index into vals_full
+  const int* diag_src;       // (n_free) index into vals_full of the diagonal
+  const int* lift_ptr;       // (n_free+1)
+  const int* lift_src;       // index into vals_full of K[free row, dirichlet col], dict order
+  const double* lift_g;      // Dirichlet value for that entry
+  const int* slice_ptr;      // (n_slices+1) SELL-32 offsets (elements)
+  const int* sell_col;       // (sell_nnz) column (free numbering); padding points at the row itself
+  const int* sell_src;       // (sell_nnz) index into vals_full, -1 for padding
+};
+
+}  // namespace dfe
+
+struct dfe_mesh {
+  dfe_mesh_info info{};
+  // ---- host-side symbolic data (int64 copies exposed through the ABI)
+  std::vector<int64_t> h_rowptr, h_col, h_rowptr_f, h_col_f, h_free;
+  // ---- 1-D chain description
+  bool chain = false;
+  bool bc_left = false, bc_right = false, lift_left_first = true;
+  double g_left = 0.0, g_right = 0.0;
+  // ---- device
+  dfe::MeshDev dev{};
+  std::vector<void*> allocs;  // every cudaMalloc owned by the handle
+  int sm_count = 0;
+};

@@ -1,0 +1,319 @@
+// Jacobi-preconditioned conjugate gradients on the SELL-32 copy of K_free, one cooperative
+// persistent kernel per solve (sm_100a).
+//
+// Replaces torch.linalg.solve(K_free, F_free) (diffhe/solver.py:174) and — called with gbar_free —
+// the adjoint solve inside LinalgSolveExBackward0 (K_free is symmetric).
+//
+// Layout: warp w owns SELL slices w, w+W, ...; lane l owns row 32*slice+l, so every load of
+// sell_val / sell_col is a fully coalesced 256 B / 128 B request.  Per iteration two phases, each
+// ended by one grid-wide barrier:
+//   A  p = z + beta p_old (recomputed on the fly for the gathered neighbours, ping-pong p buffers)
+//      q = K p ;  partial p.q
+//   B  x += alpha p ; r -= alpha q ; z = D^{-1} r ; partial r.z and r.r
+// Dot products are reduced in a fixed order (lane-strided sum + xor-shuffle tree over the per-CTA
+// partials), identically on every CTA: results are bit-reproducible and no float atomics are used.
+// Stops when the recursive residual satisfies ||r||_2 <= tol ||rhs||_2.
+#include <cooperative_groups.h>
+
+#include "dfe_internal.h"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int PT = 256;  // threads per CTA
+constexpr int PW = PT / 32;
+
+struct PcgArgs {
+  int n, n_slices;
+  const int* slice_ptr;
+  const int* col;
+  const double* val;
+  const double* dinv;
+  const double* b;
+  double* x;
+  double* r;
+  double* z;
+  double* p0;
+  double* p1;
+  double* q;
+  double* part;   // [3][gridDim.x]
+  double* out;    // [0]=iterations, [1]=relres, [2]=status (0 ok, 4 not converged, 5 breakdown)
+  double tol;
+  long long maxit;
+};
+
+// Sum of `v` over the whole grid; every thread of every CTA returns the same bits.
+__device__ __forceinline__ double grid_sum(cg::grid_group& grid, double v, double* part, double* sh) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0;
+    for (int w = 0; w < PW; ++w) a += sh[w];
+    part[blockIdx.x] = a;
+  }
+  grid.sync();
+  double a = 0.0;
+  for (int i = lane; i < static_cast<int>(gridDim.x); i += 32) a += __ldcg(part + i);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+  return a;
+}
+
+__global__ void __launch_bounds__(PT) k_pcg(const PcgArgs A) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double sh[3][PW];
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * PT + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * PT) >> 5;
+  const int G = gridDim.x;
+  double* partA = A.part;
+  double* partB = A.part + G;
+  double* partC = A.part + 2 * G;
+
+  // ---- init: x = 0, r = b, z = D^{-1} r, p buffers = 0
+  double bb = 0.0, rz = 0.0;
+  for (int s = gw; s < A.n_slices; s += nwarps) {
+    const int i = 32 * s + lane;
+    if (i < A.n) {
+      const double bi = A.b[i];
+      const double zi = A.dinv[i] * bi;
+      A.x[i] = 0.0;
+      A.r[i] = bi;
+      A.z[i] = zi;
+      A.p0[i] = 0.0;
+      A.p1[i] = 0.0;
+      bb = fma(bi, bi, bb);
+      rz = fma(bi, zi, rz);
+    }
+  }
+  bb = grid_sum(grid, bb, partA, sh[0]);
+  rz = grid_sum(grid, rz, partB, sh[1]);
+  const double bnorm = sqrt(bb);
+  double status = 0.0, relres = 0.0;
+  long long it = 0;
+  if (!(bb > 0.0)) {
+    // rhs == 0 -> x = 0 (or rhs non-finite -> breakdown)
+    if (bb != 0.0) status = 5.0;
+  } else {
+    double beta = 0.0;
+    double* pold = A.p0;
+    double* pnew = A.p1;
+    status = 4.0;
+    while (it < A.maxit) {
+      // ---- phase A
+      double pq = 0.0;
+      for (int s = gw; s < A.n_slices; s += nwarps) {
+        const int i = 32 * s + lane;
+        const int beg = A.slice_ptr[s], end = A.slice_ptr[s + 1];
+        double sum = 0.0;
+        for (int k = beg + lane; k < end; k += 32) {
+          const int j = A.col[k];
+          const double pj = fma(beta, pold[j], A.z[j]);
+          sum = fma(A.val[k], pj, sum);
+        }
+        if (i < A.n) {
+          const double pi = fma(beta, pold[i], A.z[i]);
+          pnew[i] = pi;
+          A.q[i] = sum;
+          pq = fma(pi, sum, pq);
+        }
+      }
+      pq = grid_sum(grid, pq, partA, sh[0]);
+      if (!(pq > 0.0) || !isfinite(pq)) {
+        status = 5.0;
+        break;
+      }
+      const double alpha = rz / pq;
+      // ---- phase B
+      double rz_new = 0.0, rr = 0.0;
+      for (int s = gw; s < A.n_slices; s += nwarps) {
+        const int i = 32 * s + lane;
+        if (i < A.n) {
+          A.x[i] = fma(alpha, pnew[i], A.x[i]);
+          const double ri = fma(-alpha, A.q[i], A.r[i]);
+          const double zi = A.dinv[i] * ri;
+          A.r[i] = ri;
+          A.z[i] = zi;
+          rz_new = fma(ri, zi, rz_new);
+          rr = fma(ri, ri, rr);
+        }
+      }
+      // two independent reductions share one grid barrier
+      {
+        const int warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+          rz_new += __shfl_xor_sync(0xffffffffu, rz_new, d);
+          rr += __shfl_xor_sync(0xffffffffu, rr, d);
+        }
+        if (lane == 0) {
+          sh[1][warp] = rz_new;
+          sh[2][warp] = rr;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          double a = 0.0, c = 0.0;
+          for (int w = 0; w < PW; ++w) {
+            a += sh[1][w];
+            c += sh[2][w];
+          }
+          partB[blockIdx.x] = a;
+          partC[blockIdx.x] = c;
+        }
+        grid.sync();
+        double a = 0.0, c = 0.0;
+        for (int i = lane; i < G; i += 32) {
+          a += __ldcg(partB + i);
+          c += __ldcg(partC + i);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, d);
+          c += __shfl_xor_sync(0xffffffffu, c, d);
+        }
+        rz_new = a;
+        rr = c;
+      }
+      ++it;
+      relres = sqrt(rr) / bnorm;
+      if (!isfinite(rr)) {
+        status = 5.0;
+        break;
+      }
+      if (sqrt(rr) <= A.tol * bnorm) {
+        status = 0.0;
+        break;
+      }
+      beta = rz_new / rz;
+      rz = rz_new;
+      double* t = pold;
+      pold = pnew;
+      pnew = t;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    A.out[0] = static_cast<double>(it);
+    A.out[1] = relres;
+    A.out[2] = status;
+  }
+}
+
+struct PcgPlan {
+  int grid;
+  size_t off_r, off_z, off_p0, off_p1, off_q, off_part, off_out, total;
+};
+
+int plan_pcg(const dfe_mesh* m, PcgPlan* pl, bool query_device) {
+  const size_t n = static_cast<size_t>(m->info.n_free);
+  const size_t vec = ((n * sizeof(double) + 255) / 256) * 256;
+  int max_grid = 148 * 8;  // upper bound used for workspace sizing
+  pl->grid = max_grid;
+  if (query_device) {
+    int per_sm = 0;
+    DFE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg, PT, 0));
+    long long resident = static_cast<long long>(per_sm) * m->sm_count;
+    long long want = (static_cast<long long>(m->dev.n_slices) + PW - 1) / PW;  // one slice per warp
+    long long g = want < resident ? want : resident;
+    if (g < 1) g = 1;
+    if (g > max_grid) g = max_grid;
+    pl->grid = static_cast<int>(g);
+  }
+  size_t off = 0;
+  pl->off_r = off; off += vec;
+  pl->off_z = off; off += vec;
+  pl->off_p0 = off; off += vec;
+  pl->off_p1 = off; off += vec;
+  pl->off_q = off; off += vec;
+  pl->off_part = off; off += 3 * static_cast<size_t>(max_grid) * sizeof(double);
+  pl->off_out = off; off += 256;
+  pl->total = off;
+  return DFE_OK;
+}
+
+}  // namespace
+
+extern "C" size_t dfe_pcg_workspace_bytes(const dfe_mesh* m) {
+  if (!m) return 0;
+  PcgPlan pl;
+  plan_pcg(m, &pl, false);
+  return pl.total;
+}
+
+extern "C" int dfe_pcg(const dfe_mesh* m, const double* sell_vals, const double* dinv, const double* rhs,
+                       double* x, double tol, int64_t maxit, int64_t* iters_host, double* relres_host, void* ws,
+                       size_t ws_bytes, void* stream) {
+  DFE_REQUIRE(m, "dfe_pcg: mesh is null");
+  if (m->info.device < 0) {
+    dfe::set_error("dfe_pcg: mesh handle is host-only; no CUDA device (this library has no CPU path)");
+    return DFE_ERR_CUDA;
+  }
+  DFE_REQUIRE(sell_vals && dinv && rhs && x && ws, "dfe_pcg: null argument");
+  DFE_REQUIRE(tol > 0.0 && maxit >= 1, "dfe_pcg: tol must be > 0 and maxit >= 1");
+  if (iters_host) *iters_host = 0;
+  if (relres_host) *relres_host = 0.0;
+  if (m->info.n_free == 0) return DFE_OK;
+  int prev = -1;
+  DFE_CUDA_OK(cudaGetDevice(&prev));
+  if (prev != m->info.device) DFE_CUDA_OK(cudaSetDevice(m->info.device));
+  PcgPlan pl;
+  int rc = plan_pcg(m, &pl, true);
+  if (rc == DFE_OK && ws_bytes < pl.total) {
+    dfe::set_error("dfe_pcg: workspace %zu bytes < required %zu", ws_bytes, pl.total);
+    rc = DFE_ERR_WORKSPACE;
+  }
+  if (rc == DFE_OK) {
+    unsigned char* w = static_cast<unsigned char*>(ws);
+    PcgArgs A{};
+    A.n = m->dev.n_free;
+    A.n_slices = m->dev.n_slices;
+    A.slice_ptr = m->dev.slice_ptr;
+    A.col = m->dev.sell_col;
+    A.val = sell_vals;
+    A.dinv = dinv;
+    A.b = rhs;
+    A.x = x;
+    A.r = reinterpret_cast<double*>(w + pl.off_r);
+    A.z = reinterpret_cast<double*>(w + pl.off_z);
+    A.p0 = reinterpret_cast<double*>(w + pl.off_p0);
+    A.p1 = reinterpret_cast<double*>(w + pl.off_p1);
+    A.q = reinterpret_cast<double*>(w + pl.off_q);
+    A.part = reinterpret_cast<double*>(w + pl.off_part);
+    A.out = reinterpret_cast<double*>(w + pl.off_out);
+    A.tol = tol;
+    A.maxit = maxit;
+    void* args[] = {&A};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_pcg), dim3(pl.grid), dim3(PT), args, 0, st);
+    if (e != cudaSuccess) {
+      dfe::set_error("dfe_pcg: cooperative launch failed: %s", cudaGetErrorString(e));
+      rc = DFE_ERR_CUDA;
+    } else {
+      double out[3] = {0, 0, 0};
+      e = cudaMemcpyAsync(out, A.out, sizeof out, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) {
+        dfe::set_error("dfe_pcg: %s", cudaGetErrorString(e));
+        rc = DFE_ERR_CUDA;
+      } else {
+        if (iters_host) *iters_host = static_cast<int64_t>(out[0]);
+        if (relres_host) *relres_host = out[1];
+        if (out[2] == 4.0) {
+          dfe::set_error("dfe_pcg: not converged after %lld iterations (relative residual %.3e, tol %.3e)",
+                         static_cast<long long>(out[0]), out[1], tol);
+          rc = DFE_ERR_NOT_CONVERGED;
+        } else if (out[2] == 5.0) {
+          dfe::set_error("dfe_pcg: breakdown at iteration %lld (p^T K p <= 0 or non-finite): K_free is not SPD — "
+                         "does the mesh have a Dirichlet node?",
+                         static_cast<long long>(out[0]));
+          rc = DFE_ERR_BREAKDOWN;
+        }
+      }
+    }
+  }
+  if (prev != m->info.device) cudaSetDevice(prev);
+  return rc;
+}

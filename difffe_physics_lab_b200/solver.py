@@ -1,0 +1,247 @@
+"""``DifferentiableFESolver`` — drop-in for reference ``diffhe/solver.py`` on B200.
+
+Same ``nn.Module`` surface as the reference (``diffhe/solver.py:21-67``): ``DifferentiableFESolver(mesh,
+kappa=1.0)``, ``.kappa``, ``solver(f) -> u`` for ``-div(kappa grad u) = f`` with P1 elements and
+Dirichlet elimination, differentiable w.r.t. ``kappa`` and ``f``.  The reference's Python element
+loop, dense ``K`` and ``torch.linalg.solve`` (solver.py:73-183) are replaced by ONE
+``torch.autograd.Function`` whose forward/backward call hand-written sm_100a kernels through the C
+ABI in ``include/dfe.h`` (``libdfe_b200.so``, loaded with ctypes).  No Triton, no dispatch, no CPU
+fallback: without a CUDA device the call raises.
+
+Extensions over the reference (semantics = a stack of independent reference calls):
+``f`` may be ``(B, n_nodes)``; ``kappa`` may be ``()``/``(1,)`` (shared scalar — the only form the
+reference accepts), ``(n_el,)`` (shared per-element field), ``(B, 1)`` (per-sample scalar) or
+``(B, n_el)``.  Un-batched calls keep returning ``(n_nodes,)``.
+
+Device policy: a CPU ``f`` is copied to the current CUDA device, solved there, and ``u`` is returned
+on ``f``'s device (``PhysicsLoss`` feeds CPU tensors, reference loss.py:78-83).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _native
+from .mesh import FEMesh
+
+
+# --------------------------------------------------------------------------- helpers
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _ws(nbytes: int, device: torch.device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def _kappa_mode(kappa: torch.Tensor, B: int, n_el: int, batched: bool) -> int:
+    """Resolve the kappa layout."""
+    if kappa.dim() <= 1 and kappa.numel() == 1:
+        return _native.KAPPA_SCALAR
+    if kappa.dim() == 1 and kappa.shape[0] == n_el:
+        return _native.KAPPA_PER_ELEMENT
+    if kappa.dim() == 2 and batched and kappa.shape[0] == B:
+        if kappa.shape[1] == 1:
+            return _native.KAPPA_PER_SAMPLE
+        if kappa.shape[1] == n_el:
+            return _native.KAPPA_PER_SAMPLE_ELEMENT
+    raise ValueError(
+        f"kappa of shape {tuple(kappa.shape)} is not one of (), (1,), (n_el={n_el},), (B={B}, 1), (B, n_el) "
+        "[per-sample forms need a batched f of shape (B, n_nodes)]")
+
+
+class _FESolve(torch.autograd.Function):
+    """u = K(kappa)^{-1}-solve of the assembled P1 system; backward = adjoint solve + dL/dkappa, dL/df."""
+
+    @staticmethod
+    def forward(ctx, f: torch.Tensor, kappa: torch.Tensor, mesh: FEMesh, mode: int, opts: dict):
+        # f: (B, n) float64 contiguous CUDA; kappa: float64 contiguous CUDA, layout `mode`
+        dev = f.device
+        nm = mesh._native(dev.index)
+        B, n = f.shape
+        L = _native.lib()
+        u = torch.empty_like(f)
+        fused = bool(nm.info.chain1d) and mode in (_native.KAPPA_SCALAR, _native.KAPPA_PER_SAMPLE)
+        saved_mats = None
+        with torch.cuda.device(dev):
+            if fused:
+                ws = _ws(L.dfe_solve1d_workspace_bytes(nm.handle, B), dev)
+                _native.check(L.dfe_solve1d_fwd(nm.handle, B, f.data_ptr(), f.stride(0), kappa.data_ptr(), mode,
+                                                int(opts["n_refine"]), u.data_ptr(), u.stride(0), ws.data_ptr(),
+                                                ws.numel(), _stream(dev)))
+            else:
+                saved_mats = _general_forward(L, nm, f, kappa, mode, u, opts)
+        ctx.mesh, ctx.mode, ctx.opts, ctx.fused = mesh, mode, opts, fused
+        ctx.mats = saved_mats
+        ctx.save_for_backward(u, kappa)
+        return u
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gbar: torch.Tensor):
+        u, kappa = ctx.saved_tensors
+        need_f, need_k = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dev = u.device
+        nm = ctx.mesh._native(dev.index)
+        L = _native.lib()
+        B, n = u.shape
+        gbar = gbar.contiguous()
+        gf = torch.empty_like(u) if need_f else None
+        gk = torch.empty_like(kappa)
+        with torch.cuda.device(dev):
+            if ctx.fused:
+                ws = _ws(L.dfe_solve1d_workspace_bytes(nm.handle, B), dev)
+                _native.check(L.dfe_solve1d_bwd(nm.handle, B, gbar.data_ptr(), gbar.stride(0), u.data_ptr(),
+                                                u.stride(0), kappa.data_ptr(), ctx.mode, int(ctx.opts["n_refine"]),
+                                                _ptr(gf), gf.stride(0) if gf is not None else n, gk.data_ptr(),
+                                                ws.data_ptr(), ws.numel(), _stream(dev)))
+            else:
+                _general_backward(L, nm, gbar, u, kappa, ctx.mode, ctx.mats, gf, gk, ctx.opts)
+        return gf, (gk if need_k else None), None, None, None
+
+
+def _general_forward(L, nm, f, kappa, mode, u, opts):
+    """assemble -> eliminate -> PCG -> scatter, per sample; the matrix is reused when kappa is shared."""
+    dev = f.device
+    I = nm.info
+    B = f.shape[0]
+    st = _stream(dev)
+    n_el = I.n_elements
+    shared = mode in (_native.KAPPA_SCALAR, _native.KAPPA_PER_ELEMENT)
+    amode = _native.KAPPA_SCALAR if mode in (_native.KAPPA_SCALAR, _native.KAPPA_PER_SAMPLE) else _native.KAPPA_PER_ELEMENT
+    kflat = kappa.reshape(-1)
+    ws = _ws(L.dfe_pcg_workspace_bytes(nm.handle), dev)
+    vals = torch.empty(max(I.nnz_full, 1), dtype=torch.float64, device=dev)
+    F = torch.empty(I.n_nodes, dtype=torch.float64, device=dev)
+    x = torch.empty(max(I.n_free, 1), dtype=torch.float64, device=dev)
+    mats = []
+    iters = []
+    for b in range(B):
+        sell = torch.empty(max(I.sell_nnz, 1), dtype=torch.float64, device=dev)
+        dinv = torch.empty(max(I.n_free, 1), dtype=torch.float64, device=dev)
+        Ff = torch.empty(max(I.n_free, 1), dtype=torch.float64, device=dev)
+        if mode == _native.KAPPA_PER_SAMPLE:
+            kb = kflat[b:b + 1]
+        elif mode == _native.KAPPA_PER_SAMPLE_ELEMENT:
+            kb = kflat[b * n_el:(b + 1) * n_el]
+        else:
+            kb = kflat
+        # assembly is repeated per sample even for shared kappa: F depends on f[b]; cheap next to PCG
+        _native.check(L.dfe_assemble(nm.handle, kb.data_ptr(), amode, f[b].data_ptr(), vals.data_ptr(), F.data_ptr(), st))
+        _native.check(L.dfe_eliminate(nm.handle, vals.data_ptr(), F.data_ptr(), None, sell.data_ptr(), Ff.data_ptr(),
+                                      dinv.data_ptr(), st))
+        it, rel = C.c_int64(0), C.c_double(0.0)
+        _native.check(L.dfe_pcg(nm.handle, sell.data_ptr(), dinv.data_ptr(), Ff.data_ptr(), x.data_ptr(),
+                                float(opts["pcg_tol"]), int(opts["pcg_maxit"] or max(10 * I.n_free, 1000)),
+                                C.byref(it), C.byref(rel), ws.data_ptr(), ws.numel(), st))
+        iters.append((it.value, rel.value))
+        _native.check(L.dfe_scatter(nm.handle, x.data_ptr(), 0, u[b].data_ptr(), st))
+        if not shared or b == 0:
+            mats.append((sell, dinv))
+    opts["last_pcg"] = iters
+    return mats
+
+
+def _general_backward(L, nm, gbar, u, kappa, mode, mats, gf, gk, opts):
+    dev = u.device
+    I = nm.info
+    B = u.shape[0]
+    st = _stream(dev)
+    shared = mode in (_native.KAPPA_SCALAR, _native.KAPPA_PER_ELEMENT)
+    gmode = _native.KAPPA_SCALAR if mode in (_native.KAPPA_SCALAR, _native.KAPPA_PER_SAMPLE) else _native.KAPPA_PER_ELEMENT
+    ws = _ws(L.dfe_pcg_workspace_bytes(nm.handle), dev)
+    gws = _ws(L.dfe_grad_workspace_bytes(nm.handle), dev)
+    gfree = torch.empty(max(I.n_free, 1), dtype=torch.float64, device=dev)
+    lam_free = torch.empty(max(I.n_free, 1), dtype=torch.float64, device=dev)
+    lam = torch.zeros(I.n_nodes, dtype=torch.float64, device=dev)
+    nk = 1 if gmode == _native.KAPPA_SCALAR else I.n_elements
+    gk_b = torch.empty((B, nk), dtype=torch.float64, device=dev)
+    iters = []
+    for b in range(B):
+        sell, dinv = mats[0] if shared else mats[b]
+        _native.check(L.dfe_gather_free(nm.handle, gbar[b].data_ptr(), gfree.data_ptr(), st))
+        it, rel = C.c_int64(0), C.c_double(0.0)
+        _native.check(L.dfe_pcg(nm.handle, sell.data_ptr(), dinv.data_ptr(), gfree.data_ptr(), lam_free.data_ptr(),
+                                float(opts["pcg_tol"]), int(opts["pcg_maxit"] or max(10 * I.n_free, 1000)),
+                                C.byref(it), C.byref(rel), ws.data_ptr(), ws.numel(), st))
+        iters.append((it.value, rel.value))
+        _native.check(L.dfe_scatter(nm.handle, lam_free.data_ptr(), 1, lam.data_ptr(), st))
+        _native.check(L.dfe_grad(nm.handle, lam.data_ptr(), u[b].data_ptr(), None, gmode, gk_b[b].data_ptr(),
+                                 gf[b].data_ptr() if gf is not None else None, gws.data_ptr(), gws.numel(), st))
+    opts["last_pcg_adjoint"] = iters
+    if shared:
+        gk.copy_(gk_b.sum(dim=0).reshape(gk.shape))   # torch.sum on CUDA is deterministic (no atomics)
+    else:
+        gk.copy_(gk_b.reshape(gk.shape))
+
+
+# ----------------------------------------------------------------------------- module
+class DifferentiableFESolver(nn.Module):
+    """Assemble and solve the P1 FEM system for ``mesh`` and a nodal forcing ``f``.
+
+    Parameters
+    ----------
+    mesh : FEMesh
+    kappa : float or torch.Tensor
+        Diffusion coefficient; see the module docstring for the accepted tensor shapes.
+    pcg_tol, pcg_maxit : keyword-only
+        2D / general path: Jacobi-PCG stops at recursive ``||r|| <= pcg_tol ||rhs||`` (default 1e-13,
+        which keeps ``u`` and the gradients within 1e-9 of the reference's dense solve).
+    n_refine : keyword-only
+        1D fused path: number of Neumann sweeps after the structured solve (-1 = automatic).
+    """
+
+    def __init__(self, mesh: FEMesh, kappa: float = 1.0, *, pcg_tol: float = 1e-13,
+                 pcg_maxit: Optional[int] = None, n_refine: int = -1):
+        super().__init__()
+        self.mesh = mesh
+        # Same rule as the reference (solver.py:35-39): numbers become 0-dim float64 tensors, tensors are
+        # converted with .to(float64) — which keeps the autograd graph and, for a float64 nn.Parameter,
+        # returns the same object so that nn.Module registers it (SURVEY §5 checkpoint quirk).
+        if isinstance(kappa, (int, float)):
+            self._kappa = torch.tensor(kappa, dtype=torch.float64)
+        else:
+            self._kappa = kappa.to(dtype=torch.float64)
+        self._opts = {"pcg_tol": pcg_tol, "pcg_maxit": pcg_maxit, "n_refine": n_refine}
+
+    @property
+    def kappa(self) -> torch.Tensor:
+        return self._kappa
+
+    @property
+    def last_pcg(self):
+        """[(iterations, relative residual)] of the most recent general-path forward (diagnostics)."""
+        return self._opts.get("last_pcg")
+
+    def forward(self, f: torch.Tensor) -> torch.Tensor:
+        """Solve ``-div(kappa grad u) = f``; ``f`` is ``(n_nodes,)`` or ``(B, n_nodes)``, any float dtype."""
+        mesh = self.mesh
+        if mesh.dim not in (1, 2):
+            raise NotImplementedError("Only 1D and 2D supported")
+        if not torch.cuda.is_available():
+            raise RuntimeError(
+                "DifferentiableFESolver (difffe_physics_lab_b200) runs on CUDA only and no device is visible; "
+                "there is deliberately no CPU fallback")
+        batched = f.dim() == 2
+        if f.dim() not in (1, 2) or f.shape[-1] != mesh.n_nodes:
+            raise ValueError(f"f must have shape (n_nodes,) or (B, n_nodes) with n_nodes={mesh.n_nodes}, got {tuple(f.shape)}")
+        dev = f.device if f.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        kappa = self.kappa
+        B = f.shape[0] if batched else 1
+        mode = _kappa_mode(kappa, B, mesh.n_elements, batched)
+        # dtype/device moves are ordinary differentiable torch ops; the Function sees f64 CUDA tensors
+        f_dev = f.to(device=dev, dtype=torch.float64).reshape(B, mesh.n_nodes).contiguous()
+        k_dev = kappa.to(device=dev).contiguous()
+        u = _FESolve.apply(f_dev, k_dev, mesh, mode, self._opts)
+        if not batched:
+            u = u.reshape(mesh.n_nodes)
+        return u if f.is_cuda else u.to(f.device)
