@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py — FEM fwd+adjoint solves/s on B200 (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c5a]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (N=1, default) = BASELINE.json configs[1]: 1-D Poisson, FEMesh.line(n_elements=100000), batch of
+4096 samples with random forcing f ~ U(0,1) and per-sample kappa ~ logU[0.5,2], forward + adjoint
+(upstream gradient gbar ~ N(0,1), dL/df and dL/dkappa both produced).  One "step" = one fwd+adjoint pass
+over the batch; with N GPUs every rank holds its own 4096 samples (weak scaling, no data-path collective:
+the samples are independent systems on a replicated mesh).
+
+  value      solves/s over all ranks, inputs resident in HBM, through the public API
+             (DifferentiableFESolver(...)(f); u.backward(gbar)), CUDA events, max over ranks
+  e2e        same metric with HOST inputs: every step copies f and kappa from pinned host memory and
+             reads dL/dkappa back (copies inside the timed region, sub-batches pipelined on two streams)
+  roofline   dominant kernel (k_solve1d<BWD>): algorithmic bytes per launch / its mean CUDA-event
+             duration inside the timed region, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  oracle/fem_port.c (C restatement, OpenMP over samples) on a bounded sample, rank 0, N=1
+  --impl reference  times that CPU port alone (the reference is pure Python and cannot run n=1e5:
+             dense K would be 80 GB — BASELINE.md §2)
+
+Inputs per array are 3.28 GB (>> 126 MB L2), so no L2 flush is needed between iterations.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import pathlib
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: (n_elements, batch per rank, kappa layout, scaling)
+    "c2": dict(n_elements=100000, batch=4096, kappa="per_sample", scaling="weak",
+               desc="1D Poisson batch of 4096 random forcing/kappa samples, n_elements=100000, fwd+adjoint"),
+    "c5a": dict(n_elements=16384, batch=65536, kappa="shared", scaling="strong",
+                desc="kappa inverse-problem sweep: 65536 1D solves (n_elements=16384), shared kappa, NCCL grad allreduce"),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None, help="override samples per rank (debugging; noted in config)")
+    ap.add_argument("--n-elements", type=int, default=None, help="override mesh size (debugging; noted in config)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------- CPU baseline (oracle port)
+def cpu_port_rate(n_elements, seconds_target, steps=1, warmup=0, seed=0):
+    """Time oracle/fem_port.c (fwd + adjoint, all host threads) on a bounded sample of the workload.
+    Returns (solves_per_s, cores, sample_description, ms_per_step)."""
+    from oracle import port as P
+    from oracle import oracle as O
+
+    cores = P.max_threads()
+    nodes, _, bc = O.line_mesh(n_elements)
+    x = nodes[:, 0]
+    nn = n_elements + 1
+    rng = np.random.default_rng(seed)
+    S = max(cores, 8)
+    f = rng.uniform(0, 1, (S, nn))
+    gbar = rng.standard_normal((S, nn))
+    kap = np.exp(rng.uniform(np.log(0.5), np.log(2.0), S))
+    t0 = time.perf_counter()
+    P.solve1d_batch(x, bc, f, kap, gbar)                       # calibration pass (also warms the pages)
+    t_cal = time.perf_counter() - t0
+    reps = max(1, int(seconds_target / max(t_cal, 1e-6)))
+    for _ in range(warmup):
+        P.solve1d_batch(x, bc, f, kap, gbar)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            P.solve1d_batch(x, bc, f, kap, gbar)
+        times.append(time.perf_counter() - t0)
+    per_step = float(np.mean(times))
+    rate = S * reps / per_step
+    sample = (f"{S * reps} fwd+adjoint solves per step ({S} distinct samples x {reps} passes) of the n_elements="
+              f"{n_elements} workload, OpenMP over samples, {cores} threads")
+    return rate, cores, sample, per_step * 1e3
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path on the host cores (oracle port)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = dict(WORKLOADS[args.workload])
+    n_el = args.n_elements or w["n_elements"]
+    subprocess.run(["make", "-s", "-C", str(ROOT / "oracle")], check=True)
+    rate, cores, sample, ms = cpu_port_rate(n_el, seconds_target=4.0, steps=args.steps, warmup=args.warmup)
+    line = {
+        "impl": "reference", "metric": "fem_fwd_adjoint_solves_per_s", "value": rate, "unit": "solves/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "dof_per_s": rate * (n_el - 1),
+        "config": {"workload": w["desc"], "n_elements": n_el, "note": "CPU port of the reference path (oracle/fem_port.c); "
+                   "the pure-Python reference cannot run this size (dense K = 80 GB, BASELINE.md §2)"},
+        "cpu_baseline": {"value": rate, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in open(self.tmp.name):
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 8 or not parts[0].isdigit() or int(parts[0]) != self.gpu_index:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[4:8]):
+                if v == "Active":
+                    reasons.add(nm)
+        os.unlink(self.tmp.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------- GPU arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from difffe_physics_lab_b200 import DifferentiableFESolver, FEMesh
+    from difffe_physics_lab_b200 import _native
+    from difffe_physics_lab_b200.solver import KernelTimer
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _native.build()
+
+    w = dict(WORKLOADS[args.workload])
+    n_el = args.n_elements or w["n_elements"]
+    if w["scaling"] == "weak":
+        B = args.batch or w["batch"]
+    else:
+        B = (args.batch or w["batch"]) // world
+    nn = n_el + 1
+    shared_kappa = w["kappa"] == "shared"
+
+    mesh = FEMesh.line(n_el)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    f = torch.rand((B, nn), dtype=torch.float64, device=dev, generator=gen)
+    if shared_kappa:
+        f = f + 0.5
+        kappa = torch.tensor(1.0, dtype=torch.float64, device=dev)
+    else:
+        kappa = torch.exp(torch.empty((B, 1), dtype=torch.float64, device=dev).uniform_(float(np.log(0.5)), float(np.log(2.0)), generator=gen))
+    gbar = torch.randn((B, nn), dtype=torch.float64, device=dev, generator=gen)
+    red = torch.zeros(2, dtype=torch.float64, device=dev)     # [sum dL/dkappa, loss] for the c5a all-reduce
+
+    def step_resident():
+        fr = f.requires_grad_(True)
+        fr.grad = None
+        kr = kappa.detach().requires_grad_(True)
+        u = DifferentiableFESolver(mesh, kappa=kr)(fr)
+        u.backward(gbar)
+        if shared_kappa and world > 1:
+            red[0] = kr.grad
+            dist.all_reduce(red)          # the only collective of the path: shared-parameter gradient (+loss)
+        return kr.grad
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with KernelTimer() as kt:
+        e0.record()
+        for _ in range(args.steps):
+            step_resident()
+        e1.record()
+        barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    ksum = kt.summary()
+    launches = kt.launches
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t[0])
+    ms_step = ms_total / args.steps
+    value = B * world * args.steps / (ms_total * 1e-3)
+
+    # ---------------- roofline of the dominant kernel (algorithmic bytes, SURVEY §8d: fwd 16N, adjoint 24N with gf)
+    peak, peak_src = measured_peak()
+    kern = {}
+    for name, bytes_per_node in (("solve1d_fwd", 16), ("solve1d_bwd", 24)):
+        if name in ksum:
+            calls, ms = ksum[name]
+            alg = bytes_per_node * nn * B
+            kern[name] = {"calls": calls, "ms_per_launch": ms / calls, "algorithmic_bytes": alg,
+                          "achieved_gbs": alg / (ms / calls * 1e-3) / 1e9}
+    dom = max(kern, key=lambda k: kern[k]["ms_per_launch"] * kern[k]["calls"]) if kern else None
+    roofline = None
+    if dom:
+        roofline = {"bound": "hbm", "kernel": "k_solve1d<BWD>" if dom == "solve1d_bwd" else "k_solve1d<FWD>",
+                    "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": kern[dom]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": kern[dom]["algorithmic_bytes"],
+                    "ms_per_launch": kern[dom]["ms_per_launch"], "kernels": kern,
+                    "step_frac_of_peak": (40 * nn * B) / (ms_step * 1e-3) / 1e9 / peak}
+
+    # ---------------- end to end: host f, kappa -> device -> fwd+adjoint -> dL/dkappa back to host
+    e2e = None
+    if not args.no_e2e:
+        nsub = 8 if B % 8 == 0 and B >= 64 else 1
+        bs = B // nsub
+        f_host = torch.empty((B, nn), dtype=torch.float64).pin_memory()
+        f_host.copy_(f.detach())
+        k_host = (kappa.detach().cpu() if not shared_kappa else kappa.detach().cpu().reshape(1)).pin_memory()
+        gk_host = torch.empty((B if not shared_kappa else nsub,), dtype=torch.float64).pin_memory()
+        f_dev = torch.empty((B, nn), dtype=torch.float64, device=dev)
+        k_dev = torch.empty_like(k_host, device=dev)
+        copy_stream = torch.cuda.Stream(device=dev)
+        ready = [torch.cuda.Event() for _ in range(nsub)]
+        done = [torch.cuda.Event() for _ in range(nsub)]
+
+        def step_e2e():
+            main = torch.cuda.current_stream()
+            with torch.cuda.stream(copy_stream):
+                k_dev.copy_(k_host, non_blocking=True)
+                for j in range(nsub):
+                    copy_stream.wait_event(done[j])                 # previous step finished reading this slice
+                    f_dev[j * bs:(j + 1) * bs].copy_(f_host[j * bs:(j + 1) * bs], non_blocking=True)
+                    ready[j].record(copy_stream)
+            for j in range(nsub):
+                main.wait_event(ready[j])
+                fj = f_dev[j * bs:(j + 1) * bs].requires_grad_(True)
+                kj = (k_dev if shared_kappa else k_dev[j * bs:(j + 1) * bs]).detach().requires_grad_(True)
+                kj = kj.reshape(()) if shared_kappa else kj
+                kj.retain_grad()
+                u = DifferentiableFESolver(mesh, kappa=kj)(fj)
+                u.backward(gbar[j * bs:(j + 1) * bs])
+                done[j].record(main)
+                if shared_kappa:
+                    gk_host[j:j + 1].copy_(kj.grad.reshape(1), non_blocking=True)
+                else:
+                    gk_host[j * bs:(j + 1) * bs].copy_(kj.grad.reshape(-1), non_blocking=True)
+
+        for _ in range(2):
+            step_e2e()
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_e2e = max(2, min(args.steps, 5))
+        a0.record()
+        for _ in range(n_e2e):
+            step_e2e()
+        a1.record()
+        barrier()
+        ms_e2e = a0.elapsed_time(a1)
+        if world > 1:
+            t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e2e = float(t[0])
+        e2e = {"value": B * world * n_e2e / (ms_e2e * 1e-3), "unit": "solves/s",
+               "h2d_bytes_per_step": int(f_host.numel() * 8 + k_host.numel() * 8),
+               "d2h_bytes_per_step": int(gk_host.numel() * 8), "steps": n_e2e, "ms_per_step": ms_e2e / n_e2e,
+               "pipeline": f"{nsub} sub-batches, copy stream + compute stream"}
+        del f_host, f_dev
+
+    # ---------------- CPU baseline (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            rate, cores, sample, _ = cpu_port_rate(n_el, seconds_target=12.0)
+            cpu = {"value": rate, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample}
+        except Exception as exc:  # the baseline must never sink the GPU number
+            cpu = {"value": None, "unit": "solves/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc}"}
+
+    if rank == 0:
+        line = {
+            "metric": "fem_fwd_adjoint_solves_per_s", "value": value, "unit": "solves/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": w["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "dof_per_s": value * (n_el - 1),
+            "config": {"workload": w["desc"], "n_elements": n_el, "batch_per_gpu": B, "global_batch": B * world,
+                       "kappa": w["kappa"], "grads": "dL/dkappa and dL/df", "l2": "inputs (3.28 GB/array) larger than L2; no flush",
+                       "parallelism": f"batch-sharded x{world}, mesh replicated" + (", NCCL allreduce of [dL/dkappa, loss]" if shared_kappa and world > 1 else ", no collective")},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -230,11 +230,24 @@ __global__ void __launch_bounds__(T, 2) k_solve1d(const P1D p) {
           if (!BWD) {
             // F_i = (0 + h_{i-1}/2*f_i) + h_i/2*f_i   (solver.py:95-96, element i-1 then element i)
             val = __dadd_rn(__dmul_rn(__dmul_rn(hp, 0.5), in), __dmul_rn(__dmul_rn(hi, 0.5), in));
-            // lifting F_free -= K[free, d]*g in dict order (solver.py:166-169); K[1,0] = -k_0 etc.
-            const bool liftL = p.bcL && i == 1, liftR = p.bcR && i == nn - 2;
-            if (liftL && p.lift_left_first) val = __dsub_rn(val, __dmul_rn(-__ddiv_rn(kap, hp), p.gL));
-            if (liftR) val = __dsub_rn(val, __dmul_rn(-__ddiv_rn(kap, hi), p.gR));
-            if (liftL && !p.lift_left_first) val = __dsub_rn(val, __dmul_rn(-__ddiv_rn(kap, hp), p.gL));
+            // Lifting F_free -= K[free, d]*g in dict order (solver.py:166-169); K[1,0] = -k_0 etc.
+            // The lifted load k*g is ~1/h times larger than F: pushing it through the prefix sums
+            // would cost 3-4 digits.  So the reference's lifted value is formed bit-exactly and the
+            // exact product k*g is then taken out again (TwoProduct / Sterbenz): the scans see only
+            // the small remainder, and the k*g part is solved in closed form (x_g below).
+            const bool liftL = p.bcL && i == 1 && p.gL != 0.0, liftR = p.bcR && i == nn - 2 && p.gR != 0.0;
+            if (liftL || liftR) {
+              const double kL = liftL ? __ddiv_rn(kap, hp) : 0.0, kR = liftR ? __ddiv_rn(kap, hi) : 0.0;
+              const double pL = __dmul_rn(kL, p.gL), pR = __dmul_rn(kR, p.gR);   // = -fl(K[f,d]*g)
+              if (liftL && p.lift_left_first) val = __dadd_rn(val, pL);
+              if (liftR) val = __dadd_rn(val, pR);
+              if (liftL && !p.lift_left_first) val = __dadd_rn(val, pL);
+              // val is now the reference's F_free entry; remainder = val - kL*gL - kR*gR
+              if (liftL && !p.lift_left_first) val = __dsub_rn(val, pL);
+              if (liftR) val = __dsub_rn(val, pR);
+              if (liftL && p.lift_left_first) val = __dsub_rn(val, pL);
+              val = __dsub_rn(val, __dadd_rn(__fma_rn(kL, p.gL, -pL), __fma_rn(kR, p.gR, -pR)));
+            }
           } else {
             val = in;  // gbar restricted to free rows (Dirichlet entries dropped)
           }
@@ -245,6 +258,7 @@ __global__ void __launch_bounds__(T, 2) k_solve1d(const P1D p) {
     }
 
     double gk = 0.0;
+    const bool has_g = (p.bcL && p.gL != 0.0) || (p.bcR && p.gR != 0.0);
     for (int st = 0; st <= nref; ++st) {
       // ---- local prefix of this thread's run
       Tri t = tri_id();
@@ -305,7 +319,11 @@ __global__ void __launch_bounds__(T, 2) k_solve1d(const P1D p) {
         const double hi = hs[tb + j + 1];
         const bool isfree = (li < len) && !(i == 0 && p.bcL) && !(i == nn - 1 && p.bcR);
         S += v[j];
-        const double xi = isfree ? (fma(C, X, x0c) - W) : 0.0;
+        double xi = isfree ? (fma(C, X, x0c) - W) : 0.0;
+        if (!BWD && st == 0 && isfree && has_g) {
+          // x_g = M^{-1}(lifted boundary loads): the discrete harmonic interpolant of the Dirichlet data
+          xi += (p.bcL && p.bcR) ? fma(p.gR - p.gL, X / total.x, p.gL) : (p.bcL ? p.gL : p.gR);
+        }
         if (BWD) {
           // dL/dkappa = -(1/kappa) sum_e q_e (u_{e+1}-u_e),  q_e = C - S_e the flux of lambda
           if (li < len && i < nn - 1) gk = fma(C - S, b1[q1.mis + li + 1] - b1[q1.mis + li], gk);

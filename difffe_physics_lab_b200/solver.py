@@ -28,6 +28,58 @@ from . import _native
 from .mesh import FEMesh
 
 
+# --------------------------------------------------------------------------- kernel timing hook
+class KernelTimer:
+    """Optional CUDA-event timer around the ABI calls (used by bench.py for the roofline numbers).
+
+    ``with KernelTimer() as t: ...`` records one (start, stop) event pair per ABI call on the stream the
+    kernels are launched on; ``t.summary()`` synchronises and returns {name: (calls, total_ms)}.
+    ``launches`` counts the kernels of libdfe_b200 launched while active."""
+
+    _active: Optional["KernelTimer"] = None
+    KERNELS_PER_CALL = {"solve1d_fwd": 1, "solve1d_bwd": 2, "assemble": 1, "eliminate": 2, "pcg": 1, "scatter": 1,
+                        "gather": 1, "grad": 3}
+
+    def __init__(self):
+        self.events = []
+        self.launches = 0
+
+    def __enter__(self):
+        KernelTimer._active = self
+        return self
+
+    def __exit__(self, *exc):
+        KernelTimer._active = None
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, a, b in self.events:
+            c, ms = out.get(name, (0, 0.0))
+            out[name] = (c + 1, ms + a.elapsed_time(b))
+        return out
+
+
+class _timed:
+    """Context manager: time one ABI call when a KernelTimer is active, else free."""
+
+    def __init__(self, name: str, device: torch.device):
+        self.t = KernelTimer._active
+        self.name, self.device = name, device
+
+    def __enter__(self):
+        if self.t is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record(torch.cuda.current_stream(self.device))
+
+    def __exit__(self, *exc):
+        if self.t is not None:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record(torch.cuda.current_stream(self.device))
+            self.t.events.append((self.name, self.a, b))
+            self.t.launches += KernelTimer.KERNELS_PER_CALL.get(self.name, 1)
+
+
 # --------------------------------------------------------------------------- helpers
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
@@ -73,9 +125,10 @@ class _FESolve(torch.autograd.Function):
         with torch.cuda.device(dev):
             if fused:
                 ws = _ws(L.dfe_solve1d_workspace_bytes(nm.handle, B), dev)
-                _native.check(L.dfe_solve1d_fwd(nm.handle, B, f.data_ptr(), f.stride(0), kappa.data_ptr(), mode,
-                                                int(opts["n_refine"]), u.data_ptr(), u.stride(0), ws.data_ptr(),
-                                                ws.numel(), _stream(dev)))
+                with _timed("solve1d_fwd", dev):
+                    _native.check(L.dfe_solve1d_fwd(nm.handle, B, f.data_ptr(), f.stride(0), kappa.data_ptr(), mode,
+                                                    int(opts["n_refine"]), u.data_ptr(), u.stride(0), ws.data_ptr(),
+                                                    ws.numel(), _stream(dev)))
             else:
                 saved_mats = _general_forward(L, nm, f, kappa, mode, u, opts)
         ctx.mesh, ctx.mode, ctx.opts, ctx.fused = mesh, mode, opts, fused
@@ -98,10 +151,11 @@ class _FESolve(torch.autograd.Function):
         with torch.cuda.device(dev):
             if ctx.fused:
                 ws = _ws(L.dfe_solve1d_workspace_bytes(nm.handle, B), dev)
-                _native.check(L.dfe_solve1d_bwd(nm.handle, B, gbar.data_ptr(), gbar.stride(0), u.data_ptr(),
-                                                u.stride(0), kappa.data_ptr(), ctx.mode, int(ctx.opts["n_refine"]),
-                                                _ptr(gf), gf.stride(0) if gf is not None else n, gk.data_ptr(),
-                                                ws.data_ptr(), ws.numel(), _stream(dev)))
+                with _timed("solve1d_bwd", dev):
+                    _native.check(L.dfe_solve1d_bwd(nm.handle, B, gbar.data_ptr(), gbar.stride(0), u.data_ptr(),
+                                                    u.stride(0), kappa.data_ptr(), ctx.mode, int(ctx.opts["n_refine"]),
+                                                    _ptr(gf), gf.stride(0) if gf is not None else n, gk.data_ptr(),
+                                                    ws.data_ptr(), ws.numel(), _stream(dev)))
             else:
                 _general_backward(L, nm, gbar, u, kappa, ctx.mode, ctx.mats, gf, gk, ctx.opts)
         return gf, (gk if need_k else None), None, None, None
@@ -134,13 +188,16 @@ def _general_forward(L, nm, f, kappa, mode, u, opts):
         else:
             kb = kflat
         # assembly is repeated per sample even for shared kappa: F depends on f[b]; cheap next to PCG
-        _native.check(L.dfe_assemble(nm.handle, kb.data_ptr(), amode, f[b].data_ptr(), vals.data_ptr(), F.data_ptr(), st))
-        _native.check(L.dfe_eliminate(nm.handle, vals.data_ptr(), F.data_ptr(), None, sell.data_ptr(), Ff.data_ptr(),
-                                      dinv.data_ptr(), st))
+        with _timed("assemble", dev):
+            _native.check(L.dfe_assemble(nm.handle, kb.data_ptr(), amode, f[b].data_ptr(), vals.data_ptr(), F.data_ptr(), st))
+        with _timed("eliminate", dev):
+            _native.check(L.dfe_eliminate(nm.handle, vals.data_ptr(), F.data_ptr(), None, sell.data_ptr(), Ff.data_ptr(),
+                                          dinv.data_ptr(), st))
         it, rel = C.c_int64(0), C.c_double(0.0)
-        _native.check(L.dfe_pcg(nm.handle, sell.data_ptr(), dinv.data_ptr(), Ff.data_ptr(), x.data_ptr(),
-                                float(opts["pcg_tol"]), int(opts["pcg_maxit"] or max(10 * I.n_free, 1000)),
-                                C.byref(it), C.byref(rel), ws.data_ptr(), ws.numel(), st))
+        with _timed("pcg", dev):
+            _native.check(L.dfe_pcg(nm.handle, sell.data_ptr(), dinv.data_ptr(), Ff.data_ptr(), x.data_ptr(),
+                                    float(opts["pcg_tol"]), int(opts["pcg_maxit"] or max(10 * I.n_free, 1000)),
+                                    C.byref(it), C.byref(rel), ws.data_ptr(), ws.numel(), st))
         iters.append((it.value, rel.value))
         _native.check(L.dfe_scatter(nm.handle, x.data_ptr(), 0, u[b].data_ptr(), st))
         if not shared or b == 0:
@@ -168,13 +225,15 @@ def _general_backward(L, nm, gbar, u, kappa, mode, mats, gf, gk, opts):
         sell, dinv = mats[0] if shared else mats[b]
         _native.check(L.dfe_gather_free(nm.handle, gbar[b].data_ptr(), gfree.data_ptr(), st))
         it, rel = C.c_int64(0), C.c_double(0.0)
-        _native.check(L.dfe_pcg(nm.handle, sell.data_ptr(), dinv.data_ptr(), gfree.data_ptr(), lam_free.data_ptr(),
-                                float(opts["pcg_tol"]), int(opts["pcg_maxit"] or max(10 * I.n_free, 1000)),
-                                C.byref(it), C.byref(rel), ws.data_ptr(), ws.numel(), st))
+        with _timed("pcg", dev):
+            _native.check(L.dfe_pcg(nm.handle, sell.data_ptr(), dinv.data_ptr(), gfree.data_ptr(), lam_free.data_ptr(),
+                                    float(opts["pcg_tol"]), int(opts["pcg_maxit"] or max(10 * I.n_free, 1000)),
+                                    C.byref(it), C.byref(rel), ws.data_ptr(), ws.numel(), st))
         iters.append((it.value, rel.value))
         _native.check(L.dfe_scatter(nm.handle, lam_free.data_ptr(), 1, lam.data_ptr(), st))
-        _native.check(L.dfe_grad(nm.handle, lam.data_ptr(), u[b].data_ptr(), None, gmode, gk_b[b].data_ptr(),
-                                 gf[b].data_ptr() if gf is not None else None, gws.data_ptr(), gws.numel(), st))
+        with _timed("grad", dev):
+            _native.check(L.dfe_grad(nm.handle, lam.data_ptr(), u[b].data_ptr(), None, gmode, gk_b[b].data_ptr(),
+                                     gf[b].data_ptr() if gf is not None else None, gws.data_ptr(), gws.numel(), st))
     opts["last_pcg_adjoint"] = iters
     if shared:
         gk.copy_(gk_b.sum(dim=0).reshape(gk.shape))   # torch.sum on CUDA is deterministic (no atomics)
