@@ -25,10 +25,10 @@
 
 namespace {
 
-constexpr int R = 17;           // nodes per thread (odd: stride-R shared-memory reads are conflict-free)
 constexpr int T = 256;          // threads per CTA
-constexpr int CHP = R * T;      // chunk capacity in nodes (4352)
 constexpr int NW = T / 32;
+constexpr int R_FWD = 17;       // nodes per thread, forward  (odd: stride-R LDS.64 is conflict-free)
+constexpr int R_BWD = 13;       // nodes per thread, backward (4 chunk arrays must fit twice per SM)
 constexpr int MAX_STAGES = 4;   // structured solve + up to 3 Neumann sweeps
 
 struct Tri { double s, x, w; };  // (sum rhs, sum w, sum w*S) of a block of nodes
@@ -102,10 +102,14 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t 
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ int ld_acquire(const int* p) {
+__device__ __forceinline__ int ld_relaxed(const int* p) {
   int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
+}
+// release-increment: orders this thread's earlier global stores before the counter update
+__device__ __forceinline__ void red_release_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // A row segment [g, g+len) of doubles is moved as: head (0/1 element, when g is only 8-byte
@@ -135,7 +139,7 @@ struct P1D {
   long long ldo;
   const double* kappa;
   int per_sample;        // kappa index = per_sample ? s : 0
-  int bcL, bcR, lift_left_first;
+  int bcL, bcR;
   double gL, gR;
   int* cnt;              // [B] arrival counters (zeroed per call)
   double* summ;          // [B][MAX_STAGES][G][4] chunk summaries
@@ -164,15 +168,145 @@ __device__ __forceinline__ void fold_chunks(const double* summ, int G, int c, in
   total = base;
 }
 
-template <bool BWD>
+// Per-CTA / per-sample state shared by the stages of one solve.
+struct Ctx {
+  int tid, lane, warp, c, G, tb;
+  long long s;
+  const double* hs;     // hs[j] = h_{n0-1+j}/2 (0 where there is no element)
+  const double* rh;     // rh[j] = RN(1/hs[j])  (0 where there is no element)
+  const double* ub;     // backward: u chunk in shared memory, element li at ub[li]
+  Tri* wtot;            // [2][NW]
+  double* bc;           // [2][8]
+  int nst;              // nodes of this thread inside the chunk
+  bool bcL, bcR, boundary_cta;
+  double kaph, invk2;   // kappa/2 and 2/kappa:  k_e = kaph/hs_e,  w_e = hs_e*invk2
+  double ga, gb;        // forward, stage 0: x_g = ga*X + gb (harmonic interpolant of the Dirichlet data)
+  double uL, uR;        // backward: u at the two end nodes
+};
+
+// One stage: e = M^{-1} v (flux-form prefix sums over the whole sample), xa (+)= e, and, if MORE,
+// v <- -delta*e for the next Neumann sweep.  FIRST: xa = e (+ x_g in the forward solve).
+template <bool BWD, int R, bool FIRST, bool MORE>
+__device__ __forceinline__ void run_stage(const P1D& p, const Ctx& cx, int st, double (&v)[R], double (&xa)[R],
+                                          double& gk) {
+  const double* hs = cx.hs + cx.tb;
+  // ---- local prefix of this thread's run
+  Tri t = tri_id();
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    const double w = hs[j + 1] * cx.invk2;
+    t.s += v[j];
+    t.w = fma(w, t.s, t.w);
+    t.x += w;
+  }
+  // ---- CTA scan
+  const Tri inc = warp_incl_scan(t, cx.lane);
+  const int par = st & 1;
+  if (cx.lane == 31) cx.wtot[par * NW + cx.warp] = inc;
+  __syncthreads();
+  Tri wc = tri_id();
+  for (int w = 0; w < cx.warp; ++w) wc = combine(wc, cx.wtot[par * NW + w]);
+  Tri ex = shfl_up_tri(inc, 1);
+  if (cx.lane == 0) ex = tri_id();
+  const Tri texcl = combine(wc, ex);
+  // ---- publish the chunk summary; warp 0 waits for the G chunks of this sample and folds them
+  double* stage_summ = p.summ + ((cx.s * MAX_STAGES + st) * cx.G) * 4;
+  if (cx.tid == T - 1) {
+    const Tri tot = combine(wc, inc);
+    double* slot = stage_summ + 4 * cx.c;
+    slot[0] = tot.s;
+    slot[1] = tot.x;
+    slot[2] = tot.w;
+    red_release_add(p.cnt + cx.s, 1);
+  }
+  if (cx.warp == 0) {
+    if (cx.lane == 0) {
+      const int target = (st + 1) * cx.G;
+      while (ld_relaxed(p.cnt + cx.s) < target) __nanosleep(20);
+    }
+    __syncwarp();
+    Tri carry, total;
+    fold_chunks(stage_summ, cx.G, cx.c, cx.lane, carry, total);
+    if (cx.lane == 0) {
+      double* o = cx.bc + par * 8;
+      o[0] = carry.s; o[1] = carry.x; o[2] = carry.w;
+      o[3] = total.s; o[4] = total.x; o[5] = total.w;
+    }
+  }
+  __syncthreads();
+  Tri carry, total;
+  {
+    const double* o = cx.bc + par * 8;
+    carry.s = o[0]; carry.x = o[1]; carry.w = o[2];
+    total.s = o[3]; total.x = o[4]; total.w = o[5];
+  }
+  double C, x0c;
+  if (cx.bcL && cx.bcR) {
+    x0c = 0.0;
+    C = total.w / total.x;
+  } else if (cx.bcL) {
+    x0c = 0.0;
+    C = total.s;
+  } else {
+    C = 0.0;
+    x0c = total.w;
+  }
+  if (BWD && cx.boundary_cta && cx.tid == 0) {
+    // boundary terms of  sum_e q_e (u_{e+1}-u_e) = C (u_R-u_L) - S_tot u_R + sum_i rhs_i u_i
+    gk += C * (cx.uR - cx.uL) - total.s * cx.uR;
+  }
+  const Tri tc = combine(carry, texcl);
+  // x_g = M^{-1}(lifted boundary loads): the harmonic interpolant of the Dirichlet data
+  const double ga = (!BWD && FIRST) ? ((cx.bcL && cx.bcR) ? cx.ga / total.x : 0.0) : 0.0;
+  // ---- apply on this run
+  double S = tc.s, X = tc.x, W = tc.w;
+  const double* rh = cx.rh + cx.tb;
+  double kp = 0.0;
+  if (MORE) {
+    const double y = rh[0], h = hs[0];
+    const double q0 = cx.kaph * y;
+    kp = fma(fma(-h, q0, cx.kaph), y, q0);
+  }
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    const double hi = hs[j + 1];
+    S += v[j];
+    double xi = fma(C, X, x0c) - W;
+    if (!BWD && FIRST) xi += fma(ga, X, cx.gb);
+    const double w = hi * cx.invk2;
+    W = fma(w, S, W);
+    X += w;
+    xa[j] = FIRST ? xi : xa[j] + xi;
+    if (MORE) {
+      // k_i = fl(kappa/h_i) by one correction step on the stored reciprocal (correctly rounded,
+      // Markstein); d_i = fl(k_{i-1}+k_i) is the reference's diagonal (solver.py:89-92) and
+      // err = (k_{i-1}+k_i) - d_i exactly (TwoSum).  err == 0 on Dirichlet and padding rows (one of the
+      // two k's is 0), so those rows stay masked without a branch.
+      const double y = rh[j + 1];
+      const double q0 = cx.kaph * y;
+      const double ki = fma(fma(-hi, q0, cx.kaph), y, q0);
+      const double d = __dadd_rn(kp, ki);
+      const double bb = __dsub_rn(d, kp);
+      const double err = __dadd_rn(__dsub_rn(kp, __dsub_rn(d, bb)), __dsub_rn(ki, bb));
+      v[j] = __dmul_rn(err, xi);
+      if (BWD) gk = fma(v[j], (j < cx.nst) ? cx.ub[cx.tb + j] : 0.0, gk);
+      kp = ki;
+    }
+  }
+}
+
+template <bool BWD, int R>
 __global__ void __launch_bounds__(T, 2) k_solve1d(const P1D p) {
+  constexpr int CHP = R * T;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-  Tri* wtot = reinterpret_cast<Tri*>(smem_raw + 16);                 // [2][NW]
+  Tri* wtot = reinterpret_cast<Tri*>(smem_raw + 16);                              // [2][NW]
   double* red = reinterpret_cast<double*>(smem_raw + 16 + 2 * NW * sizeof(Tri));  // [NW]
-  double* hs = reinterpret_cast<double*>(smem_raw + 512);            // hs[j] = h_{n0-1+j}, j = 0..CHP
-  double* b0 = hs + (CHP + 2);                                       // f / gbar row chunk, later output staging
-  double* b1 = b0 + (CHP + 4);                                       // backward: u row chunk (+1 halo)
+  double* bc = red + NW;                                                          // [2][8]
+  double* hs = reinterpret_cast<double*>(smem_raw + 1024);
+  double* rh = hs + (CHP + 2);
+  double* b0 = rh + (CHP + 2);   // f / gbar row chunk, later output staging
+  double* b1 = b0 + (CHP + 4);   // backward: u row chunk
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = p.G, nn = p.nn;
@@ -182,167 +316,96 @@ __global__ void __launch_bounds__(T, 2) k_solve1d(const P1D p) {
   const int len = n1 - n0;
   const int tb = tid * R;
   const int nref = p.n_refine;
+  const bool bcL = p.bcL, bcR = p.bcR;
+  // Static per-thread bookkeeping (the chunk is fixed for the whole batch): nin = nodes whose input is
+  // read (a right Dirichlet node is treated like padding), nst = nodes stored.
+  const int nin = max(0, min(R, min(len, nn - (bcR ? 1 : 0) - n0) - tb));
+  const int nst = max(0, min(R, len - tb));
+  const bool ownsL = bcL && c == 0 && tid == 0;                  // node 0 is v[0] of this thread
+  const bool ownsR = bcR && c == G - 1 && tid == (len - 1) / R;  // node nn-1
 
-  // element lengths of this chunk, bit-identical to the reference's h_e = x_j - x_i (solver.py:84-85)
+  // Half element lengths of this chunk: h_e = x_j - x_i exactly as the reference (solver.py:84-85); the
+  // halving is exact, and kappa/h == (kappa/2)/(h/2) bit for bit.  rh = correctly rounded reciprocal.
   for (int j = tid; j <= CHP; j += T) {
     const int e = n0 - 1 + j;
-    hs[j] = (e >= 0 && e < nn - 1 && j <= len) ? __dsub_rn(p.x[e + 1], p.x[e]) : 0.0;
+    const bool ex = (e >= 0 && e < nn - 1 && j <= len);
+    const double h = ex ? 0.5 * __dsub_rn(p.x[e + 1], p.x[e]) : 0.0;
+    hs[j] = h;
+    rh[j] = ex ? __ddiv_rn(1.0, h) : 0.0;
   }
   if (tid == 0) mbar_init(bar, 1);
   __syncthreads();
+
+  Ctx cx;
+  cx.tid = tid; cx.lane = lane; cx.warp = warp; cx.c = c; cx.G = G; cx.tb = tb;
+  cx.hs = hs; cx.rh = rh; cx.wtot = wtot; cx.bc = bc; cx.nst = nst;
+  cx.bcL = bcL; cx.bcR = bcR; cx.boundary_cta = (c == 0);
+  cx.ga = bcL && bcR ? p.gR - p.gL : 0.0;
+  cx.gb = bcL ? p.gL : p.gR;
+  cx.uL = cx.uR = 0.0;
+  cx.ub = b1;
 
   uint32_t phase = 0;
   for (long long s = grp; s < p.B; s += p.NG) {
     const double* g0 = p.in0 + s * p.ld0 + n0;
     const Seg q0 = make_seg(g0, len);
-    const int len1 = BWD ? len + (n1 < nn ? 1 : 0) : 0;
     const double* g1 = BWD ? p.in1 + s * p.ld1 + n0 : nullptr;
-    const Seg q1 = BWD ? make_seg(g1, len1) : Seg{0, 0, 0, 0};
+    const Seg q1 = BWD ? make_seg(g1, len) : Seg{0, 0, 0, 0};
     if (tid == 0) {
       bulk_wait_read0();  // the previous sample's bulk store has finished reading b0
       if (q0.head) b0[q0.mis] = g0[0];
       if (q0.tail) b0[q0.mis + len - 1] = g0[len - 1];
       if (BWD) {
         if (q1.head) b1[q1.mis] = g1[0];
-        if (q1.tail) b1[q1.mis + len1 - 1] = g1[len1 - 1];
+        if (q1.tail) b1[q1.mis + len - 1] = g1[len - 1];
       }
       mbar_arrive_expect_tx(bar, 8u * static_cast<uint32_t>(q0.body + q1.body));
       if (q0.body) bulk_g2s(b0 + q0.mis + q0.head, g0 + q0.head, 8u * q0.body, bar);
       if (BWD && q1.body) bulk_g2s(b1 + q1.mis + q1.head, g1 + q1.head, 8u * q1.body, bar);
+      if (BWD && c == 0) {
+        cx.uL = p.in1[s * p.ld1];
+        cx.uR = p.in1[s * p.ld1 + nn - 1];
+      }
     }
     const double kap = p.kappa[p.per_sample ? s : 0];
-    const double invk = 1.0 / kap;
+    cx.s = s;
+    cx.kaph = 0.5 * kap;
+    cx.invk2 = 2.0 / kap;
+    cx.ub = b1 + q1.mis;
     mbar_wait(bar, phase);
     phase ^= 1u;
 
     double v[R], xa[R];
-    // ---- right-hand side of the free rows
+    double gk = 0.0;
+    // ---- right-hand side: forward F_i = (0 + h_{i-1}/2 f_i) + h_i/2 f_i (solver.py:95-96, element i-1
+    // then element i); backward gbar restricted to the free rows.  The Dirichlet lifting
+    // k*g (solver.py:166-169) is NOT pushed through the prefix sums (it is ~1/h larger than F): its
+    // solution is the harmonic interpolant x_g, added in closed form in stage 0.  What is dropped is the
+    // rounding of fl(F_1 + k_0 g): a load error <= ulp(k_0 g) on the row next to the boundary, whose
+    // effect on u is <= ulp(g) (|K^-1_{1,.}| <= 1/k_0) — four orders below the parity bound.
     {
       double hp = hs[tb];
 #pragma unroll
       for (int j = 0; j < R; ++j) {
-        const int li = tb + j, i = n0 + li;
         const double hi = hs[tb + j + 1];
-        const bool isfree = (li < len) && !(i == 0 && p.bcL) && !(i == nn - 1 && p.bcR);
-        double val = 0.0;
-        if (isfree) {
-          const double in = b0[q0.mis + li];
-          if (!BWD) {
-            // F_i = (0 + h_{i-1}/2*f_i) + h_i/2*f_i   (solver.py:95-96, element i-1 then element i)
-            val = __dadd_rn(__dmul_rn(__dmul_rn(hp, 0.5), in), __dmul_rn(__dmul_rn(hi, 0.5), in));
-            // Lifting F_free -= K[free, d]*g in dict order (solver.py:166-169); K[1,0] = -k_0 etc.
-            // The lifted load k*g is ~1/h times larger than F: pushing it through the prefix sums
-            // would cost 3-4 digits.  So the reference's lifted value is formed bit-exactly and the
-            // exact product k*g is then taken out again (TwoProduct / Sterbenz): the scans see only
-            // the small remainder, and the k*g part is solved in closed form (x_g below).
-            const bool liftL = p.bcL && i == 1 && p.gL != 0.0, liftR = p.bcR && i == nn - 2 && p.gR != 0.0;
-            if (liftL || liftR) {
-              const double kL = liftL ? __ddiv_rn(kap, hp) : 0.0, kR = liftR ? __ddiv_rn(kap, hi) : 0.0;
-              const double pL = __dmul_rn(kL, p.gL), pR = __dmul_rn(kR, p.gR);   // = -fl(K[f,d]*g)
-              if (liftL && p.lift_left_first) val = __dadd_rn(val, pL);
-              if (liftR) val = __dadd_rn(val, pR);
-              if (liftL && !p.lift_left_first) val = __dadd_rn(val, pL);
-              // val is now the reference's F_free entry; remainder = val - kL*gL - kR*gR
-              if (liftL && !p.lift_left_first) val = __dsub_rn(val, pL);
-              if (liftR) val = __dsub_rn(val, pR);
-              if (liftL && p.lift_left_first) val = __dsub_rn(val, pL);
-              val = __dsub_rn(val, __dadd_rn(__fma_rn(kL, p.gL, -pL), __fma_rn(kR, p.gR, -pR)));
-            }
-          } else {
-            val = in;  // gbar restricted to free rows (Dirichlet entries dropped)
-          }
-        }
-        v[j] = val;
+        const double in = (j < nin) ? b0[q0.mis + tb + j] : 0.0;
+        v[j] = BWD ? in : __dadd_rn(__dmul_rn(hp, in), __dmul_rn(hi, in));
         hp = hi;
+      }
+      if (ownsL) v[0] = 0.0;
+      if (BWD) {
+#pragma unroll
+        for (int j = 0; j < R; ++j) gk = fma(v[j], (j < nst) ? cx.ub[tb + j] : 0.0, gk);
       }
     }
 
-    double gk = 0.0;
-    const bool has_g = (p.bcL && p.gL != 0.0) || (p.bcR && p.gR != 0.0);
-    for (int st = 0; st <= nref; ++st) {
-      // ---- local prefix of this thread's run
-      Tri t = tri_id();
-#pragma unroll
-      for (int j = 0; j < R; ++j) {
-        const double w = hs[tb + j + 1] * invk;
-        t.s += v[j];
-        t.w = fma(w, t.s, t.w);
-        t.x += w;
-      }
-      // ---- CTA scan
-      const Tri inc = warp_incl_scan(t, lane);
-      const int par = (st & 1) * NW;
-      if (lane == 31) wtot[par + warp] = inc;
-      __syncthreads();
-      Tri wc = tri_id();
-      for (int w = 0; w < warp; ++w) wc = combine(wc, wtot[par + w]);
-      Tri ex = shfl_up_tri(inc, 1);
-      if (lane == 0) ex = tri_id();
-      const Tri texcl = combine(wc, ex);
-      // ---- publish chunk summary, wait for the G chunks of this sample, fold
-      double* stage_summ = p.summ + ((s * MAX_STAGES + st) * G) * 4;
-      if (tid == T - 1) {
-        const Tri tot = combine(wc, inc);
-        double* slot = stage_summ + 4 * c;
-        slot[0] = tot.s;
-        slot[1] = tot.x;
-        slot[2] = tot.w;
-        __threadfence();
-        atomicAdd(p.cnt + s, 1);
-      }
-      if (lane == 0) {
-        const int target = (st + 1) * G;
-        while (ld_acquire(p.cnt + s) < target) __nanosleep(40);
-      }
-      __syncwarp();
-      Tri carry, total;
-      fold_chunks(stage_summ, G, c, lane, carry, total);
-      double C, x0c;
-      if (p.bcL && p.bcR) {
-        x0c = 0.0;
-        C = total.w / total.x;
-      } else if (p.bcL) {
-        x0c = 0.0;
-        C = total.s;
-      } else {
-        C = 0.0;
-        x0c = total.w;
-      }
-      const Tri tc = combine(carry, texcl);
-      // ---- apply: e = M^{-1} rhs on this run; accumulate; next rhs = -delta*e
-      double S = tc.s, X = tc.x, W = tc.w;
-      double hp = hs[tb];
-      double kp = (st < nref && hp > 0.0) ? __ddiv_rn(kap, hp) : 0.0;
-#pragma unroll
-      for (int j = 0; j < R; ++j) {
-        const int li = tb + j, i = n0 + li;
-        const double hi = hs[tb + j + 1];
-        const bool isfree = (li < len) && !(i == 0 && p.bcL) && !(i == nn - 1 && p.bcR);
-        S += v[j];
-        double xi = isfree ? (fma(C, X, x0c) - W) : 0.0;
-        if (!BWD && st == 0 && isfree && has_g) {
-          // x_g = M^{-1}(lifted boundary loads): the discrete harmonic interpolant of the Dirichlet data
-          xi += (p.bcL && p.bcR) ? fma(p.gR - p.gL, X / total.x, p.gL) : (p.bcL ? p.gL : p.gR);
-        }
-        if (BWD) {
-          // dL/dkappa = -(1/kappa) sum_e q_e (u_{e+1}-u_e),  q_e = C - S_e the flux of lambda
-          if (li < len && i < nn - 1) gk = fma(C - S, b1[q1.mis + li + 1] - b1[q1.mis + li], gk);
-        }
-        const double w = hi * invk;
-        W = fma(w, S, W);
-        X += w;
-        xa[j] = (st == 0) ? xi : xa[j] + xi;
-        if (st < nref) {
-          const double ki = (hi > 0.0) ? __ddiv_rn(kap, hi) : 0.0;
-          // d_i = fl(k_{i-1}+k_i) (solver.py:89-92 accumulation); err = (k_{i-1}+k_i) - d_i exactly
-          const double d = __dadd_rn(kp, ki);
-          const double bb = __dsub_rn(d, kp);
-          const double err = __dadd_rn(__dsub_rn(kp, __dsub_rn(d, bb)), __dsub_rn(ki, bb));
-          v[j] = isfree ? __dmul_rn(err, xi) : 0.0;
-          kp = ki;
-        }
-        hp = hi;
-      }
+    // ---- structured solve + Neumann sweeps:  x = sum_s (-M^{-1}E)^s M^{-1} rhs
+    if (nref == 0) {
+      run_stage<BWD, R, true, false>(p, cx, 0, v, xa, gk);
+    } else {
+      run_stage<BWD, R, true, true>(p, cx, 0, v, xa, gk);
+      for (int st = 1; st < nref; ++st) run_stage<BWD, R, false, true>(p, cx, st, v, xa, gk);
+      run_stage<BWD, R, false, false>(p, cx, nref, v, xa, gk);
     }
 
     // ---- epilogue
@@ -353,21 +416,14 @@ __global__ void __launch_bounds__(T, 2) k_solve1d(const P1D p) {
       double hp = hs[tb];
 #pragma unroll
       for (int j = 0; j < R; ++j) {
-        const int li = tb + j, i = n0 + li;
         const double hi = hs[tb + j + 1];
-        if (li < len) {
-          double o;
-          if (!BWD) {
-            // u[d] = g ; u[free] = x   (solver.py:177-181)
-            o = (i == 0 && p.bcL) ? p.gL : ((i == nn - 1 && p.bcR) ? p.gR : xa[j]);
-          } else {
-            // dL/df_i = lambda_i (h_{i-1}/2 + h_i/2)   (autograd of solver.py:95-96)
-            o = fma(xa[j], hp * 0.5, xa[j] * (hi * 0.5));
-          }
-          b0[qo.mis + li] = o;
-        }
+        // forward: u[free] = x (solver.py:180-181); backward: dL/df_i = lambda_i (h_{i-1}/2 + h_i/2)
+        if (j < nst) b0[qo.mis + tb + j] = BWD ? fma(xa[j], hp, xa[j] * hi) : xa[j];
         hp = hi;
       }
+      // Dirichlet nodes: u[d] = g (solver.py:177-179); dL/df = 0 there in 1-D
+      if (ownsL) b0[qo.mis] = BWD ? 0.0 : p.gL;
+      if (ownsR) b0[qo.mis + len - 1] = BWD ? 0.0 : p.gR;
       fence_async_smem();
     }
     if (BWD) {
@@ -380,7 +436,7 @@ __global__ void __launch_bounds__(T, 2) k_solve1d(const P1D p) {
       if (BWD) {
         double a = 0.0;
         for (int w = 0; w < NW; ++w) a += red[w];
-        p.gkpart[s * G + c] = -invk * a;
+        p.gkpart[s * G + c] = -(1.0 / kap) * a;
       }
       if (have_out) {
         if (qo.head) go[0] = b0[qo.mis];
@@ -418,35 +474,38 @@ __global__ void k_reduce_gk(const double* part, long long B, int G, int per_samp
   }
 }
 
-constexpr size_t SMEM_FWD = 512 + sizeof(double) * ((CHP + 2) + (CHP + 4));
-constexpr size_t SMEM_BWD = 512 + sizeof(double) * ((CHP + 2) + 2 * (CHP + 4));
+template <int R>
+constexpr size_t smem_bytes(bool bwd) {
+  return 1024 + sizeof(double) * (2 * (R * T + 2) + (bwd ? 2 : 1) * (R * T + 4));
+}
 
 struct Plan {
-  int G, chg, NG;
+  int G, chg;
   size_t off_cnt, off_summ, off_gk, total;
 };
 
-int make_plan(const dfe_mesh* m, long long B, bool bwd, Plan* pl) {
+// Chunking for a kernel with R nodes per thread.  The workspace is sized for the backward kernel
+// (smaller R -> more chunks) so that one allocation serves both directions.
+void make_plan(const dfe_mesh* m, long long B, int R, Plan* pl) {
   const int nn = static_cast<int>(m->info.n_nodes);
-  pl->G = (nn + CHP - 1) / CHP;
+  const int chp = R * T;
+  pl->G = (nn + chp - 1) / chp;
   pl->chg = (nn + pl->G - 1) / pl->G;
-  pl->NG = 0;
+  const int gmax = (nn + R_BWD * T - 1) / (R_BWD * T);
   size_t off = 0;
   pl->off_cnt = off;
   off += ((static_cast<size_t>(B) * sizeof(int) + 255) / 256) * 256;
   pl->off_summ = off;
-  off += static_cast<size_t>(B) * MAX_STAGES * pl->G * 4 * sizeof(double);
+  off += static_cast<size_t>(B) * MAX_STAGES * gmax * 4 * sizeof(double);
   pl->off_gk = off;
-  off += static_cast<size_t>(B) * pl->G * sizeof(double);
+  off += static_cast<size_t>(B) * gmax * sizeof(double);
   pl->total = off + 256;
-  (void)bwd;
-  return DFE_OK;
 }
 
-template <bool BWD>
+template <bool BWD, int R>
 int launch(const dfe_mesh* m, long long B, P1D p, const Plan& pl, cudaStream_t st) {
-  auto kern = k_solve1d<BWD>;
-  const size_t smem = BWD ? SMEM_BWD : SMEM_FWD;
+  auto kern = k_solve1d<BWD, R>;
+  const size_t smem = smem_bytes<R>(BWD);
   DFE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int per_sm = 0;
   DFE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
@@ -459,7 +518,7 @@ int launch(const dfe_mesh* m, long long B, P1D p, const Plan& pl, cudaStream_t s
   long long NG = resident / pl.G;
   if (NG > B) NG = B;
   p.NG = static_cast<int>(NG);
-  k_solve1d<BWD><<<static_cast<unsigned>(NG * pl.G), T, smem, st>>>(p);
+  kern<<<static_cast<unsigned>(NG * pl.G), T, smem, st>>>(p);
   DFE_CUDA_OK(cudaGetLastError());
   return DFE_OK;
 }
@@ -505,7 +564,6 @@ P1D base_params(const dfe_mesh* m, long long B, const Plan& pl, const double* ka
   p.per_sample = kappa_mode == DFE_KAPPA_PER_SAMPLE;
   p.bcL = m->bc_left;
   p.bcR = m->bc_right;
-  p.lift_left_first = m->lift_left_first;
   p.gL = m->g_left;
   p.gR = m->g_right;
   unsigned char* w = static_cast<unsigned char*>(ws);
@@ -520,7 +578,7 @@ P1D base_params(const dfe_mesh* m, long long B, const Plan& pl, const double* ka
 extern "C" size_t dfe_solve1d_workspace_bytes(const dfe_mesh* m, int64_t B) {
   if (!m || B < 1) return 0;
   Plan pl;
-  make_plan(m, B, true, &pl);
+  make_plan(m, B, R_BWD, &pl);
   return pl.total;
 }
 
@@ -528,7 +586,7 @@ extern "C" int dfe_solve1d_fwd(const dfe_mesh* m, int64_t B, const double* f, in
                                int kappa_mode, int n_refine, double* u, int64_t ldu, void* ws, size_t ws_bytes,
                                void* stream) {
   Plan pl{};
-  if (m) make_plan(m, B, false, &pl);
+  if (m) make_plan(m, B, R_FWD, &pl);
   int rc = common_checks(m, B, f, kappa, kappa_mode, ws, ws_bytes, pl, "dfe_solve1d_fwd");
   if (rc != DFE_OK) return rc;
   DFE_REQUIRE(u && ldf >= m->info.n_nodes && ldu >= m->info.n_nodes, "dfe_solve1d_fwd: bad u / leading dimension");
@@ -542,7 +600,7 @@ extern "C" int dfe_solve1d_fwd(const dfe_mesh* m, int64_t B, const double* f, in
   p.out = u;
   p.ldo = ldu;
   DFE_CUDA_OK(cudaMemsetAsync(p.cnt, 0, static_cast<size_t>(B) * sizeof(int), st));
-  rc = launch<false>(m, B, p, pl, st);
+  rc = launch<false, R_FWD>(m, B, p, pl, st);
   if (cur != m->info.device) cudaSetDevice(cur);
   return rc;
 }
@@ -551,7 +609,7 @@ extern "C" int dfe_solve1d_bwd(const dfe_mesh* m, int64_t B, const double* gbar,
                                int64_t ldu, const double* kappa, int kappa_mode, int n_refine, double* gf,
                                int64_t ldgf, double* gkappa, void* ws, size_t ws_bytes, void* stream) {
   Plan pl{};
-  if (m) make_plan(m, B, true, &pl);
+  if (m) make_plan(m, B, R_BWD, &pl);
   int rc = common_checks(m, B, gbar, kappa, kappa_mode, ws, ws_bytes, pl, "dfe_solve1d_bwd");
   if (rc != DFE_OK) return rc;
   DFE_REQUIRE(u && gkappa, "dfe_solve1d_bwd: null u / gkappa");
@@ -569,7 +627,7 @@ extern "C" int dfe_solve1d_bwd(const dfe_mesh* m, int64_t B, const double* gbar,
   p.out = gf;
   p.ldo = ldgf;
   DFE_CUDA_OK(cudaMemsetAsync(p.cnt, 0, static_cast<size_t>(B) * sizeof(int), st));
-  rc = launch<true>(m, B, p, pl, st);
+  rc = launch<true, R_BWD>(m, B, p, pl, st);
   if (rc == DFE_OK) {
     if (p.per_sample) {
       k_reduce_gk<<<static_cast<unsigned>((B + 255) / 256), 256, 0, st>>>(p.gkpart, B, pl.G, 1, gkappa);
