@@ -19,8 +19,8 @@ import subprocess
 PKG = pathlib.Path(__file__).resolve().parent
 ROOT = PKG.parent
 LIB_PATH = PKG / "libdfe_b200.so"
-SOURCES = ["dfe_mesh.cu", "dfe_1d.cu", "dfe_general.cu", "dfe_pcg.cu"]
-HEADERS = [PKG / "csrc" / "dfe_internal.h", ROOT / "include" / "dfe.h"]
+SOURCES = ["dfe_mesh.cu", "dfe_1d.cu", "dfe_1d_split.cu", "dfe_general.cu", "dfe_pcg.cu"]
+HEADERS = [PKG / "csrc" / "dfe_internal.h", PKG / "csrc" / "dfe_1d_common.cuh", ROOT / "include" / "dfe.h"]
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOT_CONVERGED, ERR_BREAKDOWN, ERR_WORKSPACE = range(7)
 KAPPA_SCALAR, KAPPA_PER_SAMPLE, KAPPA_PER_ELEMENT, KAPPA_PER_SAMPLE_ELEMENT = range(4)

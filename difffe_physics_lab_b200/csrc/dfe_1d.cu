@@ -20,8 +20,16 @@
 // walks samples s = group, group+NG, ...  Rows move global<->shared with 1-D TMA bulk copies
 // (cp.async.bulk + mbarrier); thread t owns R consecutive nodes (R odd -> conflict-free LDS.64).
 #include <cstdint>
+#include <cstdlib>
 
 #include "dfe_internal.h"
+
+namespace dfe {
+size_t split1d_workspace_bytes(const dfe_mesh* m, long long B);
+int split1d_run(const dfe_mesh* m, long long B, bool bwd, const double* in0, long long ld0, const double* in1,
+                long long ld1, const double* kappa, int per_sample, double* out, long long ldo, double* gkappa,
+                void* ws, cudaStream_t st);
+}  // namespace dfe
 
 namespace {
 
@@ -31,101 +39,7 @@ constexpr int R_FWD = 17;       // nodes per thread, forward  (odd: stride-R LDS
 constexpr int R_BWD = 13;       // nodes per thread, backward (4 chunk arrays must fit twice per SM)
 constexpr int MAX_STAGES = 4;   // structured solve + up to 3 Neumann sweeps
 
-struct Tri { double s, x, w; };  // (sum rhs, sum w, sum w*S) of a block of nodes
-
-__device__ __forceinline__ Tri tri_id() { return Tri{0.0, 0.0, 0.0}; }
-// a block followed by b block
-__device__ __forceinline__ Tri combine(const Tri& a, const Tri& b) {
-  Tri r;
-  r.s = a.s + b.s;
-  r.x = a.x + b.x;
-  r.w = fma(a.s, b.x, a.w + b.w);
-  return r;
-}
-__device__ __forceinline__ Tri shfl_up_tri(const Tri& t, int d) {
-  Tri r;
-  r.s = __shfl_up_sync(0xffffffffu, t.s, d);
-  r.x = __shfl_up_sync(0xffffffffu, t.x, d);
-  r.w = __shfl_up_sync(0xffffffffu, t.w, d);
-  return r;
-}
-__device__ __forceinline__ Tri shfl_tri(const Tri& t, int src) {
-  Tri r;
-  r.s = __shfl_sync(0xffffffffu, t.s, src);
-  r.x = __shfl_sync(0xffffffffu, t.x, src);
-  r.w = __shfl_sync(0xffffffffu, t.w, src);
-  return r;
-}
-__device__ __forceinline__ Tri warp_incl_scan(Tri t, int lane) {
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    Tri o = shfl_up_tri(t, d);
-    if (lane >= d) t = combine(o, t);
-  }
-  return t;
-}
-
-// ---- PTX helpers: mbarrier + 1-D TMA bulk copies -------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void bulk_g2s(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(sdst)),
-               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ int ld_relaxed(const int* p) {
-  int v;
-  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-// release-increment: orders this thread's earlier global stores before the counter update
-__device__ __forceinline__ void red_release_add(int* p, int v) {
-  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-// A row segment [g, g+len) of doubles is moved as: head (0/1 element, when g is only 8-byte
-// aligned) + 16-byte aligned body (TMA bulk) + tail (0/1 element).  Element j lives at sbuf[mis+j]
-// so that global and shared addresses share their 16-byte phase.
-struct Seg {
-  int mis, head, body, tail;
-};
-__device__ __forceinline__ Seg make_seg(const double* g, int len) {
-  Seg q;
-  q.mis = static_cast<int>((reinterpret_cast<uintptr_t>(g) >> 3) & 1);
-  q.head = (len > 0) ? q.mis : 0;
-  q.body = (len - q.head) & ~1;
-  q.tail = len - q.head - q.body;
-  return q;
-}
+#include "dfe_1d_common.cuh"
 
 struct P1D {
   int nn, G, chg, NG, n_refine;
@@ -523,6 +437,24 @@ int launch(const dfe_mesh* m, long long B, P1D p, const Plan& pl, cudaStream_t s
   return DFE_OK;
 }
 
+int auto_refine(int n_refine, long long nn) {
+  if (n_refine < 0) n_refine = nn <= 200000 ? 1 : (nn <= 2000000 ? 2 : 3);
+  return n_refine > MAX_STAGES - 1 ? MAX_STAGES - 1 : n_refine;
+}
+
+// Kernel variant for n_refine == 1 (the common case): DFE_1D_MODE = split (default) | seq.
+//   split : two streaming passes + fold kernel (dfe_1d_split.cu) — no cross-CTA waits, any mesh size
+//   seq   : single persistent kernel with an on-chip exchange per sweep (k_solve1d)
+// n_refine != 1 always uses seq.
+enum Mode1D { MODE_SEQ = 0, MODE_SPLIT = 2 };
+Mode1D mode_1d(int n_refine) {
+  static const Mode1D pref = [] {
+    const char* e = getenv("DFE_1D_MODE");
+    return (e && e[0] == 's' && e[1] == 'e') ? MODE_SEQ : MODE_SPLIT;
+  }();
+  return n_refine == 1 ? pref : MODE_SEQ;
+}
+
 int common_checks(const dfe_mesh* m, long long B, const void* a, const void* kappa, int kappa_mode, void* ws,
                   size_t ws_bytes, const Plan& pl, const char* who) {
   DFE_REQUIRE(m && a && kappa && ws, "%s: null argument", who);
@@ -539,16 +471,12 @@ int common_checks(const dfe_mesh* m, long long B, const void* a, const void* kap
     dfe::set_error("%s: per-element kappa is not implemented in the fused 1-D path yet", who);
     return DFE_ERR_UNSUPPORTED;
   }
-  if (ws_bytes < pl.total) {
-    dfe::set_error("%s: workspace %zu bytes < required %zu", who, ws_bytes, pl.total);
+  const size_t need = pl.total > dfe::split1d_workspace_bytes(m, B) ? pl.total : dfe::split1d_workspace_bytes(m, B);
+  if (ws_bytes < need) {
+    dfe::set_error("%s: workspace %zu bytes < required %zu", who, ws_bytes, need);
     return DFE_ERR_WORKSPACE;
   }
   return DFE_OK;
-}
-
-int auto_refine(int n_refine, long long nn) {
-  if (n_refine < 0) n_refine = nn <= 200000 ? 1 : (nn <= 2000000 ? 2 : 3);
-  return n_refine > MAX_STAGES - 1 ? MAX_STAGES - 1 : n_refine;
 }
 
 P1D base_params(const dfe_mesh* m, long long B, const Plan& pl, const double* kappa, int kappa_mode, int n_refine,
@@ -579,13 +507,15 @@ extern "C" size_t dfe_solve1d_workspace_bytes(const dfe_mesh* m, int64_t B) {
   if (!m || B < 1) return 0;
   Plan pl;
   make_plan(m, B, R_BWD, &pl);
-  return pl.total;
+  const size_t sp = m->chain ? dfe::split1d_workspace_bytes(m, B) : 0;
+  return pl.total > sp ? pl.total : sp;
 }
 
 extern "C" int dfe_solve1d_fwd(const dfe_mesh* m, int64_t B, const double* f, int64_t ldf, const double* kappa,
                                int kappa_mode, int n_refine, double* u, int64_t ldu, void* ws, size_t ws_bytes,
                                void* stream) {
   Plan pl{};
+  const Mode1D mode = m ? mode_1d(auto_refine(n_refine, m->info.n_nodes)) : MODE_SEQ;
   if (m) make_plan(m, B, R_FWD, &pl);
   int rc = common_checks(m, B, f, kappa, kappa_mode, ws, ws_bytes, pl, "dfe_solve1d_fwd");
   if (rc != DFE_OK) return rc;
@@ -599,8 +529,12 @@ extern "C" int dfe_solve1d_fwd(const dfe_mesh* m, int64_t B, const double* f, in
   p.ld0 = ldf;
   p.out = u;
   p.ldo = ldu;
-  DFE_CUDA_OK(cudaMemsetAsync(p.cnt, 0, static_cast<size_t>(B) * sizeof(int), st));
-  rc = launch<false, R_FWD>(m, B, p, pl, st);
+  if (mode == MODE_SPLIT) {
+    rc = dfe::split1d_run(m, B, false, f, ldf, nullptr, 0, kappa, p.per_sample, u, ldu, nullptr, ws, st);
+  } else {
+    DFE_CUDA_OK(cudaMemsetAsync(p.cnt, 0, static_cast<size_t>(B) * sizeof(int), st));
+    rc = launch<false, R_FWD>(m, B, p, pl, st);
+  }
   if (cur != m->info.device) cudaSetDevice(cur);
   return rc;
 }
@@ -609,6 +543,7 @@ extern "C" int dfe_solve1d_bwd(const dfe_mesh* m, int64_t B, const double* gbar,
                                int64_t ldu, const double* kappa, int kappa_mode, int n_refine, double* gf,
                                int64_t ldgf, double* gkappa, void* ws, size_t ws_bytes, void* stream) {
   Plan pl{};
+  const Mode1D mode = m ? mode_1d(auto_refine(n_refine, m->info.n_nodes)) : MODE_SEQ;
   if (m) make_plan(m, B, R_BWD, &pl);
   int rc = common_checks(m, B, gbar, kappa, kappa_mode, ws, ws_bytes, pl, "dfe_solve1d_bwd");
   if (rc != DFE_OK) return rc;
@@ -626,13 +561,19 @@ extern "C" int dfe_solve1d_bwd(const dfe_mesh* m, int64_t B, const double* gbar,
   p.ld1 = ldu;
   p.out = gf;
   p.ldo = ldgf;
+  if (mode == MODE_SPLIT) {
+    rc = dfe::split1d_run(m, B, true, gbar, ldg, u, ldu, kappa, p.per_sample, gf, ldgf, gkappa, ws, st);
+    if (cur != m->info.device) cudaSetDevice(cur);
+    return rc;
+  }
   DFE_CUDA_OK(cudaMemsetAsync(p.cnt, 0, static_cast<size_t>(B) * sizeof(int), st));
+  const int G_used = pl.G;
   rc = launch<true, R_BWD>(m, B, p, pl, st);
   if (rc == DFE_OK) {
     if (p.per_sample) {
-      k_reduce_gk<<<static_cast<unsigned>((B + 255) / 256), 256, 0, st>>>(p.gkpart, B, pl.G, 1, gkappa);
+      k_reduce_gk<<<static_cast<unsigned>((B + 255) / 256), 256, 0, st>>>(p.gkpart, B, G_used, 1, gkappa);
     } else {
-      k_reduce_gk<<<1, 1024, 0, st>>>(p.gkpart, B, pl.G, 0, gkappa);
+      k_reduce_gk<<<1, 1024, 0, st>>>(p.gkpart, B, G_used, 0, gkappa);
     }
     if (cudaGetLastError() != cudaSuccess) {
       dfe::set_error("dfe_solve1d_bwd: reduce kernel launch failed");

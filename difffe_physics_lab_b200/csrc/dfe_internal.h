@@ -70,6 +70,8 @@ struct dfe_mesh {
   bool chain = false;
   bool bc_left = false, bc_right = false, lift_left_first = true;
   double g_left = 0.0, g_right = 0.0;
+  const double* d_hs = nullptr;  // chain: h_e/2 (h_e = x_{e+1}-x_e as the reference computes it), device, n_el
+  const double* d_rh = nullptr;  // chain: correctly rounded 1/(h_e/2), device, n_el
   // ---- device
   dfe::MeshDev dev{};
   std::vector<void*> allocs;  // every cudaMalloc owned by the handle

@@ -297,6 +297,17 @@ extern "C" int dfe_mesh_create(int dim, int64_t n_nodes, int64_t n_el, const dou
     UP(lift_ptr, lift_ptr); UP(lift_src, lift_src); UP(lift_g, lift_g); UP(slice_ptr, slice_ptr);
     UP(sell_col, sell_col); UP(sell_src, sell_src);
 #undef UP
+    if (rc == DFE_OK && chain) {
+      // half element lengths and their reciprocals for the fused 1-D kernels (IEEE double on the host)
+      std::vector<double> hsv(ne), rhv(ne);
+      for (int e = 0; e < ne; ++e) {
+        const volatile double h = nodes[e + 1] - nodes[e];   // solver.py:84-85
+        hsv[e] = 0.5 * h;
+        rhv[e] = 1.0 / hsv[e];
+      }
+      rc = upload(m, hsv, &m->d_hs);
+      if (rc == DFE_OK) rc = upload(m, rhv, &m->d_rh);
+    }
     cudaDeviceProp prop;
     if (rc == DFE_OK && cudaGetDeviceProperties(&prop, device) == cudaSuccess) m->sm_count = prop.multiProcessorCount;
     cudaSetDevice(cur);
