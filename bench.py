@@ -44,6 +44,11 @@ WORKLOADS = {
                desc="1D Poisson batch of 4096 random forcing/kappa samples, n_elements=100000, fwd+adjoint"),
     "c5a": dict(n_elements=16384, batch=65536, kappa="shared", scaling="strong",
                 desc="kappa inverse-problem sweep: 65536 1D solves (n_elements=16384), shared kappa, NCCL grad allreduce"),
+    # 2-D configs (one mesh per GPU; N > 1 = replicas only).  Not the default bench line.
+    "c3": dict(nx=128, kappa="scalar", scaling="weak",
+               desc="2D unit-square P1 triangles 128x128 (16641 nodes), f=1, kappa=1, fwd+adjoint"),
+    "c4": dict(nx=1024, kappa="per_element", scaling="weak",
+               desc="2D heterogeneous per-element kappa 1024x1024 mesh, kappa_e ~ logU[1e-3,1], f=1, fwd+adjoint of sum(u)"),
 }
 
 
@@ -131,7 +136,7 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    FIELDS = ("index,clocks.sm,clocks.max.sm,utilization.gpu,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
@@ -157,23 +162,31 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         self.tmp.flush()
-        sm, mx, reasons = [], [], set()
+        sm, sm_load, mx, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in open(self.tmp.name):
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 8 or not parts[0].isdigit() or int(parts[0]) != self.gpu_index:
                 continue
             try:
-                sm.append(float(parts[1]))
-                mx.append(float(parts[2]))
+                clk, cmax = float(parts[1]), float(parts[2])
             except ValueError:
                 continue
+            sm.append(clk)
+            mx.append(cmax)
+            try:
+                if float(parts[3]) >= 50.0:
+                    sm_load.append(clk)
+            except ValueError:
+                pass
             for nm, v in zip(names, parts[4:8]):
                 if v == "Active":
                     reasons.add(nm)
         os.unlink(self.tmp.name)
         if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+            use = sm_load or sm
+            out.update(sm_mhz=float(np.median(use)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm), samples_under_load=len(sm_load))
         return out
 
 
@@ -199,6 +212,8 @@ def run_b200(args):
     _native.build()
 
     w = dict(WORKLOADS[args.workload])
+    if "nx" in w:
+        return run_b200_2d(args, w, rank, local_rank, world, dev)
     n_el = args.n_elements or w["n_elements"]
     if w["scaling"] == "weak":
         B = args.batch or w["batch"]
@@ -234,12 +249,13 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident timing
+    # ---------------- device-resident timing (the clock sampler runs from the warm-up to the end of the e2e
+    # region: all of it is under load, and nvidia-smi needs a few hundred ms to deliver its first sample)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_resident()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with KernelTimer() as kt:
         e0.record()
@@ -247,7 +263,6 @@ def run_b200(args):
             step_resident()
         e1.record()
         barrier()
-    clocks = sampler.stop()
     ms_total = e0.elapsed_time(e1)
     ksum = kt.summary()
     launches = kt.launches
@@ -270,7 +285,9 @@ def run_b200(args):
     dom = max(kern, key=lambda k: kern[k]["ms_per_launch"] * kern[k]["calls"]) if kern else None
     roofline = None
     if dom:
-        roofline = {"bound": "hbm", "kernel": "k_solve1d<BWD>" if dom == "solve1d_bwd" else "k_solve1d<FWD>",
+        knames = {"solve1d_fwd": "dfe_solve1d_fwd = k1d_pass1<0> + k1d_fold<0> + k1d_pass2<0>",
+                  "solve1d_bwd": "dfe_solve1d_bwd = k1d_pass1<1> + k1d_fold<1> + k1d_pass2<1> + k1d_gk_out"}
+        roofline = {"bound": "hbm", "kernel": knames[dom],
                     "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                     "frac": kern[dom]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": kern[dom]["algorithmic_bytes"],
@@ -335,6 +352,8 @@ def run_b200(args):
                "pipeline": f"{nsub} sub-batches, copy stream + compute stream"}
         del f_host, f_dev
 
+    clocks = sampler.stop()
+
     # ---------------- CPU baseline (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -355,6 +374,90 @@ def run_b200(args):
                        "parallelism": f"batch-sharded x{world}, mesh replicated" + (", NCCL allreduce of [dL/dkappa, loss]" if shared_kappa and world > 1 else ", no collective")},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_b200_2d(args, w, rank, local_rank, world, dev):
+    """Configs 3 / 4: one 2-D mesh per GPU (replicas only across GPUs), step = forward + adjoint of one solve."""
+    import torch
+    import torch.distributed as dist
+
+    from difffe_physics_lab_b200 import DifferentiableFESolver, FEMesh
+    from difffe_physics_lab_b200.solver import KernelTimer
+
+    nx = args.n_elements or w["nx"]
+    t0 = time.perf_counter()
+    mesh = FEMesh.rectangle(nx, nx)
+    gen = torch.Generator(device=dev).manual_seed(rank)
+    if w["kappa"] == "per_element":
+        kappa = torch.exp(torch.empty(mesh.n_elements, dtype=torch.float64, device=dev).uniform_(float(np.log(1e-3)), 0.0, generator=gen))
+    else:
+        kappa = torch.tensor(1.0, dtype=torch.float64, device=dev)
+    f = torch.ones(mesh.n_nodes, dtype=torch.float64, device=dev)
+    nm = mesh._native(dev.index)
+    t_setup = time.perf_counter() - t0
+    I = nm.info
+    its = {}
+
+    def step():
+        kr = kappa.detach().requires_grad_(True)
+        s = DifferentiableFESolver(mesh, kappa=kr)
+        u = s(f)
+        u.sum().backward()
+        its["fwd"] = s.last_pcg[0][0]
+        its["adj"] = s._opts["last_pcg_adjoint"][0][0]
+        return kr.grad
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with KernelTimer() as kt:
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    ksum = kt.summary()
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t[0])
+    ms_step = ms_total / args.steps
+    peak, peak_src = measured_peak()
+    N, nnz = I.n_free, I.nnz_free
+    bytes_iter = 12 * nnz + 104 * N + 4 * (N + 1)              # SURVEY §8d accounting convention
+    calls, ms_pcg = ksum.get("pcg", (0, 0.0))
+    iters_step = its.get("fwd", 0) + its.get("adj", 0)
+    roofline = None
+    if calls:
+        ms_launch = ms_pcg / calls
+        alg = bytes_iter * iters_step / 2.0                     # per PCG launch (forward and adjoint solves average)
+        roofline = {"bound": "hbm", "kernel": "k_pcg (cooperative Jacobi-PCG)", "achieved": alg / (ms_launch * 1e-3) / 1e9,
+                    "peak": peak, "unit": "GB/s", "frac": alg / (ms_launch * 1e-3) / 1e9 / peak, "traffic": None,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "ms_per_launch": ms_launch,
+                    "bytes_per_iteration": bytes_iter, "iterations": its, "us_per_iteration": 1e3 * ms_pcg / calls / (iters_step / 2.0),
+                    "kernels": {k: {"calls": c, "ms_per_launch": m / c} for k, (c, m) in ksum.items()}}
+    if rank == 0:
+        line = {"metric": "fem_fwd_adjoint_solves_per_s", "value": world * args.steps / (ms_total * 1e-3), "unit": "solves/s",
+                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "dof_per_s": world * args.steps / (ms_total * 1e-3) * N,
+                "config": {"workload": w["desc"], "nx": nx, "n_free": int(N), "nnz_free": int(nnz), "pcg_tol": 1e-13,
+                           "l2": "config 4 working set ~0.2 GB > L2; config 3 (3 MB) is L2/latency-bound by construction",
+                           "mesh_setup_s": t_setup, "parallelism": f"replicas only x{world} (a single mesh stays on one GPU)"},
+                "roofline": roofline, "cpu_baseline": None, "e2e": None, "gpu_launches": kt.launches, "clocks": clocks}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

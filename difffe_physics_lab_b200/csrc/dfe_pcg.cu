@@ -6,20 +6,33 @@
 //
 // Layout: warp w owns SELL slices w, w+W, ...; lane l owns row 32*slice+l, so every load of
 // sell_val / sell_col is a fully coalesced 256 B / 128 B request.  Per iteration two phases, each
-// ended by one grid-wide barrier:
+// ended by one grid-wide barrier (hand-rolled: release-increment + acquire-poll, see grid_barrier):
 //   A  p = z + beta p_old (recomputed on the fly for the gathered neighbours, ping-pong p buffers)
 //      q = K p ;  partial p.q
 //   B  x += alpha p ; r -= alpha q ; z = D^{-1} r ; partial r.z and r.r
 // Dot products are reduced in a fixed order (lane-strided sum + xor-shuffle tree over the per-CTA
 // partials), identically on every CTA: results are bit-reproducible and no float atomics are used.
 // Stops when the recursive residual satisfies ||r||_2 <= tol ||rhs||_2.
-#include <cooperative_groups.h>
-
 #include "dfe_internal.h"
 
-namespace cg = cooperative_groups;
-
 namespace {
+
+// Grid-wide barrier for a cooperative (co-resident) launch: one release-increment per CTA on a monotonically
+// increasing counter, acquire-polling by one thread per CTA.  `epoch` counts the barriers this CTA has passed.
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& epoch) {
+  __syncthreads();
+  ++epoch;
+  if (threadIdx.x == 0) {
+    const unsigned int target = epoch * gridDim.x;
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    unsigned int v;
+    do {   // relaxed polling (no L1 invalidation per poll), one acquire fence once the count is reached
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while (v < target);
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+  }
+  __syncthreads();
+}
 
 constexpr int PT = 256;  // threads per CTA
 constexpr int PW = PT / 32;
@@ -37,6 +50,7 @@ struct PcgArgs {
   double* p0;
   double* p1;
   double* q;
+  unsigned int* barrier;  // grid barrier counter (zeroed before launch)
   double* part;   // [3][gridDim.x]
   double* out;    // [0]=iterations, [1]=relres, [2]=status (0 ok, 4 not converged, 5 breakdown)
   double tol;
@@ -44,7 +58,7 @@ struct PcgArgs {
 };
 
 // Sum of `v` over the whole grid; every thread of every CTA returns the same bits.
-__device__ __forceinline__ double grid_sum(cg::grid_group& grid, double v, double* part, double* sh) {
+__device__ __forceinline__ double grid_sum(unsigned int* bar, unsigned int& epoch, double v, double* part, double* sh) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
@@ -55,7 +69,7 @@ __device__ __forceinline__ double grid_sum(cg::grid_group& grid, double v, doubl
     for (int w = 0; w < PW; ++w) a += sh[w];
     part[blockIdx.x] = a;
   }
-  grid.sync();
+  grid_barrier(bar, epoch);
   double a = 0.0;
   for (int i = lane; i < static_cast<int>(gridDim.x); i += 32) a += __ldcg(part + i);
 #pragma unroll
@@ -63,8 +77,8 @@ __device__ __forceinline__ double grid_sum(cg::grid_group& grid, double v, doubl
   return a;
 }
 
-__global__ void __launch_bounds__(PT) k_pcg(const PcgArgs A) {
-  cg::grid_group grid = cg::this_grid();
+__global__ void __launch_bounds__(PT, 4) k_pcg(const PcgArgs A) {
+  unsigned int epoch = 0;
   __shared__ double sh[3][PW];
   const int lane = threadIdx.x & 31;
   const int gw = (blockIdx.x * PT + threadIdx.x) >> 5;
@@ -90,8 +104,8 @@ __global__ void __launch_bounds__(PT) k_pcg(const PcgArgs A) {
       rz = fma(bi, zi, rz);
     }
   }
-  bb = grid_sum(grid, bb, partA, sh[0]);
-  rz = grid_sum(grid, rz, partB, sh[1]);
+  bb = grid_sum(A.barrier, epoch, bb, partA, sh[0]);
+  rz = grid_sum(A.barrier, epoch, rz, partB, sh[1]);
   const double bnorm = sqrt(bb);
   double status = 0.0, relres = 0.0;
   long long it = 0;
@@ -106,14 +120,26 @@ __global__ void __launch_bounds__(PT) k_pcg(const PcgArgs A) {
     while (it < A.maxit) {
       // ---- phase A
       double pq = 0.0;
-      for (int s = gw; s < A.n_slices; s += nwarps) {
-        const int i = 32 * s + lane;
+      for (int s = gw; s < A.n_slices; s += 2 * nwarps) {
+        // two slices per trip: their column / value / gather loads are independent and overlap
+        const int s2 = s + nwarps;
+        const bool has2 = s2 < A.n_slices;
+        const int i = 32 * s + lane, i2 = 32 * s2 + lane;
         const int beg = A.slice_ptr[s], end = A.slice_ptr[s + 1];
-        double sum = 0.0;
-        for (int k = beg + lane; k < end; k += 32) {
-          const int j = A.col[k];
-          const double pj = fma(beta, pold[j], A.z[j]);
-          sum = fma(A.val[k], pj, sum);
+        const int beg2 = has2 ? A.slice_ptr[s2] : 0, end2 = has2 ? A.slice_ptr[s2 + 1] : 0;
+        double sum = 0.0, sum2 = 0.0;
+        int k = beg + lane, k2 = beg2 + lane;
+        while (k < end || k2 < end2) {
+          if (k < end) {
+            const int j = A.col[k];
+            sum = fma(A.val[k], fma(beta, pold[j], A.z[j]), sum);
+            k += 32;
+          }
+          if (k2 < end2) {
+            const int j = A.col[k2];
+            sum2 = fma(A.val[k2], fma(beta, pold[j], A.z[j]), sum2);
+            k2 += 32;
+          }
         }
         if (i < A.n) {
           const double pi = fma(beta, pold[i], A.z[i]);
@@ -121,8 +147,14 @@ __global__ void __launch_bounds__(PT) k_pcg(const PcgArgs A) {
           A.q[i] = sum;
           pq = fma(pi, sum, pq);
         }
+        if (has2 && i2 < A.n) {
+          const double pi = fma(beta, pold[i2], A.z[i2]);
+          pnew[i2] = pi;
+          A.q[i2] = sum2;
+          pq = fma(pi, sum2, pq);
+        }
       }
-      pq = grid_sum(grid, pq, partA, sh[0]);
+      pq = grid_sum(A.barrier, epoch, pq, partA, sh[0]);
       if (!(pq > 0.0) || !isfinite(pq)) {
         status = 5.0;
         break;
@@ -164,7 +196,7 @@ __global__ void __launch_bounds__(PT) k_pcg(const PcgArgs A) {
           partB[blockIdx.x] = a;
           partC[blockIdx.x] = c;
         }
-        grid.sync();
+        grid_barrier(A.barrier, epoch);
         double a = 0.0, c = 0.0;
         for (int i = lane; i < G; i += 32) {
           a += __ldcg(partB + i);
@@ -204,7 +236,7 @@ __global__ void __launch_bounds__(PT) k_pcg(const PcgArgs A) {
 
 struct PcgPlan {
   int grid;
-  size_t off_r, off_z, off_p0, off_p1, off_q, off_part, off_out, total;
+  size_t off_r, off_z, off_p0, off_p1, off_q, off_part, off_out, off_bar, total;
 };
 
 int plan_pcg(const dfe_mesh* m, PcgPlan* pl, bool query_device) {
@@ -230,6 +262,7 @@ int plan_pcg(const dfe_mesh* m, PcgPlan* pl, bool query_device) {
   pl->off_q = off; off += vec;
   pl->off_part = off; off += 3 * static_cast<size_t>(max_grid) * sizeof(double);
   pl->off_out = off; off += 256;
+  pl->off_bar = off; off += 256;
   pl->total = off;
   return DFE_OK;
 }
@@ -283,11 +316,13 @@ extern "C" int dfe_pcg(const dfe_mesh* m, const double* sell_vals, const double*
     A.q = reinterpret_cast<double*>(w + pl.off_q);
     A.part = reinterpret_cast<double*>(w + pl.off_part);
     A.out = reinterpret_cast<double*>(w + pl.off_out);
+    A.barrier = reinterpret_cast<unsigned int*>(w + pl.off_bar);
     A.tol = tol;
     A.maxit = maxit;
     void* args[] = {&A};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_pcg), dim3(pl.grid), dim3(PT), args, 0, st);
+    cudaError_t e = cudaMemsetAsync(A.barrier, 0, sizeof(unsigned int), st);
+    if (e == cudaSuccess) e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_pcg), dim3(pl.grid), dim3(PT), args, 0, st);
     if (e != cudaSuccess) {
       dfe::set_error("dfe_pcg: cooperative launch failed: %s", cudaGetErrorString(e));
       rc = DFE_ERR_CUDA;
