@@ -27,7 +27,7 @@
 namespace dfe {
 size_t split1d_workspace_bytes(const dfe_mesh* m, long long B);
 int split1d_run(const dfe_mesh* m, long long B, bool bwd, const double* in0, long long ld0, const double* in1,
-                long long ld1, const double* kappa, int per_sample, double* out, long long ldo, double* gkappa,
+                long long ld1, const double* kappa, int kappa_mode, double* out, long long ldo, double* gkappa,
                 void* ws, cudaStream_t st);
 }  // namespace dfe
 
@@ -467,10 +467,8 @@ int common_checks(const dfe_mesh* m, long long B, const void* a, const void* kap
     dfe::set_error("%s: mesh is not a 1-D chain with Dirichlet nodes at its ends; use the general path", who);
     return DFE_ERR_UNSUPPORTED;
   }
-  if (kappa_mode != DFE_KAPPA_SCALAR && kappa_mode != DFE_KAPPA_PER_SAMPLE) {
-    dfe::set_error("%s: per-element kappa is not implemented in the fused 1-D path yet", who);
-    return DFE_ERR_UNSUPPORTED;
-  }
+  DFE_REQUIRE(kappa_mode >= DFE_KAPPA_SCALAR && kappa_mode <= DFE_KAPPA_PER_SAMPLE_ELEMENT, "%s: bad kappa_mode %d", who,
+              kappa_mode);
   const size_t need = pl.total > dfe::split1d_workspace_bytes(m, B) ? pl.total : dfe::split1d_workspace_bytes(m, B);
   if (ws_bytes < need) {
     dfe::set_error("%s: workspace %zu bytes < required %zu", who, ws_bytes, need);
@@ -519,6 +517,10 @@ extern "C" int dfe_solve1d_fwd(const dfe_mesh* m, int64_t B, const double* f, in
   if (m) make_plan(m, B, R_FWD, &pl);
   int rc = common_checks(m, B, f, kappa, kappa_mode, ws, ws_bytes, pl, "dfe_solve1d_fwd");
   if (rc != DFE_OK) return rc;
+  if (kappa_mode >= DFE_KAPPA_PER_ELEMENT && mode != MODE_SPLIT) {
+    dfe::set_error("dfe_solve1d_fwd: per-element kappa needs the split path (n_refine == 1, i.e. meshes up to 2e5 nodes)");
+    return DFE_ERR_UNSUPPORTED;
+  }
   DFE_REQUIRE(u && ldf >= m->info.n_nodes && ldu >= m->info.n_nodes, "dfe_solve1d_fwd: bad u / leading dimension");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int cur = -1;
@@ -530,7 +532,7 @@ extern "C" int dfe_solve1d_fwd(const dfe_mesh* m, int64_t B, const double* f, in
   p.out = u;
   p.ldo = ldu;
   if (mode == MODE_SPLIT) {
-    rc = dfe::split1d_run(m, B, false, f, ldf, nullptr, 0, kappa, p.per_sample, u, ldu, nullptr, ws, st);
+    rc = dfe::split1d_run(m, B, false, f, ldf, nullptr, 0, kappa, kappa_mode, u, ldu, nullptr, ws, st);
   } else {
     DFE_CUDA_OK(cudaMemsetAsync(p.cnt, 0, static_cast<size_t>(B) * sizeof(int), st));
     rc = launch<false, R_FWD>(m, B, p, pl, st);
@@ -547,6 +549,10 @@ extern "C" int dfe_solve1d_bwd(const dfe_mesh* m, int64_t B, const double* gbar,
   if (m) make_plan(m, B, R_BWD, &pl);
   int rc = common_checks(m, B, gbar, kappa, kappa_mode, ws, ws_bytes, pl, "dfe_solve1d_bwd");
   if (rc != DFE_OK) return rc;
+  if (kappa_mode >= DFE_KAPPA_PER_ELEMENT && mode != MODE_SPLIT) {
+    dfe::set_error("dfe_solve1d_bwd: per-element kappa needs the split path (n_refine == 1, i.e. meshes up to 2e5 nodes)");
+    return DFE_ERR_UNSUPPORTED;
+  }
   DFE_REQUIRE(u && gkappa, "dfe_solve1d_bwd: null u / gkappa");
   DFE_REQUIRE(ldg >= m->info.n_nodes && ldu >= m->info.n_nodes && (!gf || ldgf >= m->info.n_nodes),
               "dfe_solve1d_bwd: leading dimension smaller than n_nodes");
@@ -562,7 +568,7 @@ extern "C" int dfe_solve1d_bwd(const dfe_mesh* m, int64_t B, const double* gbar,
   p.out = gf;
   p.ldo = ldgf;
   if (mode == MODE_SPLIT) {
-    rc = dfe::split1d_run(m, B, true, gbar, ldg, u, ldu, kappa, p.per_sample, gf, ldgf, gkappa, ws, st);
+    rc = dfe::split1d_run(m, B, true, gbar, ldg, u, ldu, kappa, kappa_mode, gf, ldgf, gkappa, ws, st);
     if (cur != m->info.device) cudaSetDevice(cur);
     return rc;
   }

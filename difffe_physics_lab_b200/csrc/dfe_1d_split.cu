@@ -50,7 +50,12 @@ struct PS {
   double gL, gR;
   double* part;          // [B][G][NP1]
   double* coef;          // [B][G][NP2]
-  double* gk;            // backward: [B] per-sample dL/dkappa
+  double* gk;            // backward, scalar kappa: [B] per-sample dL/dkappa
+  // per-element kappa (PE kernels): kappa row of sample s = kap_row + s*ldk (ldk = 0: field shared by the batch)
+  const double* kap_row;
+  long long ldk;
+  double* gke_out;       // backward PE, per-sample field: (B, n_el) output rows
+  double* gk_cols;       // backward PE, shared field: [NG][n_el] per-column partial sums
 };
 
 // chunk-static bookkeeping shared by both passes
@@ -362,7 +367,7 @@ __global__ void k1d_fold(const PS p) {
       coef[g * NP2 + 3] = C1 - s1in;                // beta1
     }
   }
-  if (BWD) {
+  if (BWD && p.gk != nullptr) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) dotacc += __shfl_xor_sync(0xffffffffu, dotacc, d);
     if (lane == 0) {
@@ -494,6 +499,348 @@ __global__ void __launch_bounds__(ST, 2) k1d_pass2(const PS p) {
   if (tid == 0) bulk_wait_read0();
 }
 
+
+// ================================================================================================ per-element kappa
+// Same two passes with kappa_e read per element: k_e = fl(kappa_e/h_e) (solver.py:88 with kappa -> kappa[e]),
+// w_e = h_e/kappa_e.  R = 9 nodes per thread so that the extra row buffers (kappa, and u in the backward
+// pass 2) still allow two CTAs per SM; no prefetch.  dL/dkappa_e = -(q0_e + q1_e)(u_{e+1}-u_e)/kappa_e with
+// q_e = beta - s_e the flux of lambda in element e (s_e: chunk-local inclusive prefix of the rhs).
+constexpr int PR = 9;
+constexpr int PCH = PR * ST;   // 2304 nodes per chunk
+
+struct ChunkP {
+  int n0, len, tb, nin, nst, nev, eA, ecnt, koff;
+  bool ownsL, ownsR;
+};
+__device__ __forceinline__ ChunkP make_chunk_pe(const PS& p, int c, int tid) {
+  ChunkP k;
+  k.n0 = c * p.chg;
+  const int n1 = min(p.nn, k.n0 + p.chg);
+  k.len = n1 - k.n0;
+  k.tb = tid * PR;
+  k.nin = max(0, min(PR, min(k.len, p.nn - (p.bcR ? 1 : 0) - k.n0) - k.tb));
+  k.nst = max(0, min(PR, k.len - k.tb));
+  k.nev = max(0, min(PR, min(k.len, p.nn - 1 - k.n0) - k.tb));   // elements owned (right element of each node)
+  k.ownsL = p.bcL && c == 0 && tid == 0;
+  k.ownsR = p.bcR && c == p.G - 1 && tid == (k.len - 1) / PR;
+  // kappa elements held: e in [eA, eA+ecnt), slot j (element n0-1+j) lives at kS[2 + mk + j + koff]
+  k.eA = max(k.n0 - 1, 0);
+  const int eB = min(k.n0 + k.len - 1, p.nn - 2);
+  k.ecnt = max(0, eB - k.eA + 1);
+  k.koff = (k.n0 == 0) ? -1 : 0;
+  return k;
+}
+__device__ __forceinline__ void load_mesh_chunk_pe(const PS& p, const ChunkP& k, double* hsS, double* rhS, int tid) {
+  for (int j = tid; j <= PCH; j += ST) {
+    const int e = k.n0 - 1 + j;
+    const bool ex = (e >= 0 && e < p.nn - 1 && j <= k.len);
+    hsS[j] = ex ? p.hs[e] : 0.0;
+    rhS[j] = ex ? p.rh[e] : 0.0;
+  }
+}
+// CTA scan for the PE kernels (same as cta_excl_scan; separate name only for readability of the call sites)
+#define cta_excl_scan_pe cta_excl_scan
+
+constexpr size_t smem_pe(int nrows) { return 2048 + sizeof(double) * (2 * (PCH + 2) + nrows * (PCH + 8)); }
+
+template <bool BWD>
+__global__ void __launch_bounds__(ST, 2) k1d_pe_pass1(const PS p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  Tri* wt = reinterpret_cast<Tri*>(smem_raw + 64);
+  double* red = reinterpret_cast<double*>(smem_raw + 64 + SNW * 24);
+  double* hsS = reinterpret_cast<double*>(smem_raw + 2048);
+  double* rhS = hsS + (PCH + 2);
+  double* rin = rhS + (PCH + 2);        // f / gbar row chunk
+  double* kS = rin + (PCH + 8);         // kappa row chunk
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c = blockIdx.x % p.G, col = blockIdx.x / p.G;
+  const ChunkP ck = make_chunk_pe(p, c, tid);
+  load_mesh_chunk_pe(p, ck, hsS, rhS, tid);
+  for (int j = tid; j < PCH + 8; j += ST) kS[j] = 1.0;   // slots of elements that do not exist stay finite
+  if (tid == 0) mbar_init(bar, 1);
+  __syncthreads();
+  const double* hsT = hsS + ck.tb;
+  const double* rhT = rhS + ck.tb;
+
+  int it = 0;
+  for (long long s = p.s_begin + col; s < p.s_end; s += p.NG, ++it) {
+    const double* g0 = p.in0 + s * p.ld0 + ck.n0;
+    const double* gk = p.kap_row + s * p.ldk + ck.eA;
+    if (tid == 0) {
+      const Seg qk = make_seg(gk, ck.ecnt);
+      if (qk.head) kS[2 + qk.mis] = gk[0];
+      if (qk.tail) kS[2 + qk.mis + ck.ecnt - 1] = gk[ck.ecnt - 1];
+      issue_row(rin, g0, ck.len, bar, 8u * qk.body);
+      if (qk.body) bulk_g2s(kS + 2 + qk.mis + qk.head, gk + qk.head, 8u * qk.body, bar);
+    }
+    const double* r0 = rin + mis_of(g0) + ck.tb;
+    const double* kT = kS + 2 + mis_of(gk) + ck.tb + ck.koff;   // kT[j] = kappa of element n0-1+tb+j
+    mbar_wait(bar, it & 1);
+
+    double v[PR], wv[PR];
+    Tri t = tri_id();
+    {
+      double hp = hsT[0];
+#pragma unroll
+      for (int j = 0; j < PR; ++j) {
+        const double hi = hsT[j + 1];
+        const double in = (j < ck.nin) ? r0[j] : 0.0;
+        double v0 = BWD ? in : __dadd_rn(__dmul_rn(hp, in), __dmul_rn(hi, in));
+        if (j == 0 && ck.ownsL) v0 = 0.0;
+        v[j] = v0;
+        const double w = hi * (2.0 / kT[j + 1]);   // w_e = h_e/kappa_e (hs = h/2)
+        wv[j] = w;
+        t.s += v0;
+        t.w = fma(w, t.s, t.w);
+        t.x += w;
+        hp = hi;
+      }
+    }
+    Tri tot0;
+    const Tri ex = cta_excl_scan_pe(t, wt, lane, warp, tot0);
+    double S = ex.s, X = ex.x, W = ex.w;
+    double a1 = 0, a2 = 0, a3 = 0, B1 = 0, B2 = 0, B3 = 0, Xt = 0;
+    double kp = kdiv(0.5 * kT[0], hsT[0], rhT[0]);
+#pragma unroll
+    for (int j = 0; j < PR; ++j) {
+      const double ki = kdiv(0.5 * kT[j + 1], hsT[j + 1], rhT[j + 1]);
+      const double err = two_sum_err(kp, ki);
+      kp = ki;
+      S += v[j];
+      const double c2 = err * X, c3 = err * W;
+      a1 += err;
+      a2 += c2;
+      a3 += c3;
+      const double w = wv[j];
+      B1 = fma(w, a1, B1);
+      B2 = fma(w, a2, B2);
+      B3 = fma(w, a3, B3);
+      W = fma(w, S, W);
+      X += w;
+      Xt += w;
+    }
+    double p1 = a1, p2 = a2, p3 = a3;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const double o1 = __shfl_up_sync(0xffffffffu, p1, d), o2 = __shfl_up_sync(0xffffffffu, p2, d),
+                   o3 = __shfl_up_sync(0xffffffffu, p3, d);
+      if (lane >= d) { p1 += o1; p2 += o2; p3 += o3; }
+    }
+    double q1 = fma(p1 - a1, Xt, B1), q2 = fma(p2 - a2, Xt, B2), q3 = fma(p3 - a3, Xt, B3), xw = Xt;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      q1 += __shfl_xor_sync(0xffffffffu, q1, d);
+      q2 += __shfl_xor_sync(0xffffffffu, q2, d);
+      q3 += __shfl_xor_sync(0xffffffffu, q3, d);
+      xw += __shfl_xor_sync(0xffffffffu, xw, d);
+    }
+    if (lane == 31) {
+      double* r = red + warp * 12;
+      r[0] = p1; r[1] = p2; r[2] = p3; r[3] = q1; r[4] = q2; r[5] = q3; r[6] = xw;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double A1 = 0, A2 = 0, A3 = 0, Q1 = 0, Q2 = 0, Q3 = 0;
+      for (int w = 0; w < SNW; ++w) {
+        const double* r = red + w * 12;
+        Q1 += fma(A1, r[6], r[3]);
+        Q2 += fma(A2, r[6], r[4]);
+        Q3 += fma(A3, r[6], r[5]);
+        A1 += r[0]; A2 += r[1]; A3 += r[2];
+      }
+      double* o = p.part + (s * p.G + c) * NP1;
+      o[0] = tot0.s; o[1] = tot0.x; o[2] = tot0.w;
+      o[3] = A1; o[4] = Q1; o[5] = A2; o[6] = Q2; o[7] = A3; o[8] = Q3;
+      o[9] = 0.0; o[10] = 0.0; o[11] = 0.0; o[12] = 0.0;
+    }
+    __syncthreads();
+  }
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(ST, 2) k1d_pe_pass2(const PS p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  Tri* wt = reinterpret_cast<Tri*>(smem_raw + 64);               // [2][SNW]
+  double* hsS = reinterpret_cast<double*>(smem_raw + 2048);
+  double* rhS = hsS + (PCH + 2);
+  double* rin = rhS + (PCH + 2);        // f / gbar row chunk -> x0 -> output staging
+  double* kS = rin + (PCH + 8);         // kappa row chunk -> (backward) dL/dkappa_e staging
+  double* uS = kS + (PCH + 8);          // backward: u row chunk with one halo node
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c = blockIdx.x % p.G, col = blockIdx.x / p.G;
+  const ChunkP ck = make_chunk_pe(p, c, tid);
+  load_mesh_chunk_pe(p, ck, hsS, rhS, tid);
+  for (int j = tid; j < PCH + 8; j += ST) kS[j] = 1.0;
+  if (tid == 0) mbar_init(bar, 1);
+  __syncthreads();
+  const double* hsT = hsS + ck.tb;
+  const double* rhT = rhS + ck.tb;
+  const int ulen = BWD ? ck.len + ((ck.n0 + ck.len < p.nn) ? 1 : 0) : 0;
+  const bool shared_field = (p.ldk == 0);
+  double gacc[PR];
+#pragma unroll
+  for (int j = 0; j < PR; ++j) gacc[j] = 0.0;
+
+  int it = 0;
+  for (long long s = p.s_begin + col; s < p.s_end; s += p.NG, ++it) {
+    const double* g0 = p.in0 + s * p.ld0 + ck.n0;
+    const double* gk = p.kap_row + s * p.ldk + ck.eA;
+    const double* gu = BWD ? p.in1 + s * p.ld1 + ck.n0 : nullptr;
+    if (tid == 0) {
+      bulk_wait_read0();   // stores of the previous sample have read rin / kS
+      const Seg qk = make_seg(gk, ck.ecnt);
+      if (qk.head) kS[2 + qk.mis] = gk[0];
+      if (qk.tail) kS[2 + qk.mis + ck.ecnt - 1] = gk[ck.ecnt - 1];
+      uint32_t extra = 8u * qk.body;
+      Seg qu{0, 0, 0, 0};
+      if (BWD) {
+        qu = make_seg(gu, ulen);
+        if (qu.head) uS[qu.mis] = gu[0];
+        if (qu.tail) uS[qu.mis + ulen - 1] = gu[ulen - 1];
+        extra += 8u * qu.body;
+      }
+      issue_row(rin, g0, ck.len, bar, extra);
+      if (qk.body) bulk_g2s(kS + 2 + qk.mis + qk.head, gk + qk.head, 8u * qk.body, bar);
+      if (BWD && qu.body) bulk_g2s(uS + qu.mis + qu.head, gu + qu.head, 8u * qu.body, bar);
+    }
+    const double* cf = p.coef + (s * p.G + c) * NP2;
+    const double alpha = cf[0], beta = cf[1], alpha1 = cf[2], beta1 = cf[3];
+    const int mi = mis_of(g0);
+    const bool have_out = (p.out != nullptr);
+    double* go = have_out ? p.out + s * p.ldo + ck.n0 : nullptr;
+    const int mo = have_out ? mis_of(go) : 0;
+    const double* kT = kS + 2 + mis_of(gk) + ck.tb + ck.koff;
+    const double* uT = BWD ? uS + mis_of(gu) + ck.tb : nullptr;
+    mbar_wait(bar, it & 1);
+
+    double v[PR], ikv[PR], ge[PR];   // ikv = 2/kappa_e
+    Tri t = tri_id();
+    {
+      double hp = hsT[0];
+#pragma unroll
+      for (int j = 0; j < PR; ++j) {
+        const double hi = hsT[j + 1];
+        const double in = (j < ck.nin) ? rin[mi + ck.tb + j] : 0.0;
+        double v0 = BWD ? in : __dadd_rn(__dmul_rn(hp, in), __dmul_rn(hi, in));
+        if (j == 0 && ck.ownsL) v0 = 0.0;
+        v[j] = v0;
+        const double ik = 2.0 / kT[j + 1];
+        ikv[j] = ik;
+        const double w = hi * ik;   // w_e = h_e/kappa_e (hs = h/2)
+        t.s += v0;
+        t.w = fma(w, t.s, t.w);
+        t.x += w;
+        hp = hi;
+      }
+    }
+    Tri tot;
+    const Tri ex = cta_excl_scan_pe(t, wt, lane, warp, tot);
+    Tri t1 = tri_id();
+    {
+      double S = ex.s, X = ex.x, W = ex.w;
+      double kp = kdiv(0.5 * kT[0], hsT[0], rhT[0]);
+#pragma unroll
+      for (int j = 0; j < PR; ++j) {
+        S += v[j];
+        const double x0 = fma(beta, X, alpha) - W;
+        if (have_out) rin[mo + ck.tb + j] = x0;
+        if (BWD) ge[j] = (j < ck.nev) ? (beta - S) * (uT[j + 1] - uT[j]) : 0.0;   // q0_e (u_{e+1}-u_e)
+        const double ki = kdiv(0.5 * kT[j + 1], hsT[j + 1], rhT[j + 1]);
+        const double v1 = __dmul_rn(two_sum_err(kp, ki), x0);
+        kp = ki;
+        v[j] = v1;
+        const double w = hsT[j + 1] * ikv[j];
+        W = fma(w, S, W);
+        X += w;
+        t1.s += v1;
+        t1.w = fma(w, t1.s, t1.w);
+        t1.x += w;
+      }
+    }
+    const Tri ex1 = cta_excl_scan_pe(t1, wt + SNW, lane, warp, tot);   // barrier: all kappa reads of this sample done
+    {
+      double S = ex1.s, X = ex1.x, W = ex1.w;
+      double hp = hsT[0];
+#pragma unroll
+      for (int j = 0; j < PR; ++j) {
+        const double hi = hsT[j + 1];
+        S += v[j];
+        const double x1 = fma(beta1, X, alpha1) - W;
+        const double w = hi * ikv[j];
+        W = fma(w, S, W);
+        X += w;
+        if (have_out && j < ck.nst) {
+          const double xv = rin[mo + ck.tb + j] + x1;
+          rin[mo + ck.tb + j] = BWD ? fma(xv, hp, xv * hi) : xv;
+        }
+        if (BWD) {
+          // dL/dkappa_e = -(q0_e + q1_e)(u_{e+1}-u_e)/kappa_e
+          const double du = (j < ck.nev) ? (uT[j + 1] - uT[j]) : 0.0;
+          const double g = -(ge[j] + (beta1 - S) * du) * (0.5 * ikv[j]);
+          ge[j] = (j < ck.nev) ? g : 0.0;
+        }
+        hp = hi;
+      }
+    }
+    if (have_out) {
+      if (ck.ownsL) rin[mo] = BWD ? 0.0 : p.gL;
+      if (ck.ownsR) rin[mo + ck.len - 1] = BWD ? 0.0 : p.gR;
+    }
+    double* gko = nullptr;
+    int mg = 0;
+    const int nel_chunk = max(0, min(ck.len, p.nn - 1 - ck.n0));   // elements n0 .. n0+nel_chunk-1 belong to this chunk
+    if (BWD) {
+      if (shared_field) {
+#pragma unroll
+        for (int j = 0; j < PR; ++j) gacc[j] += ge[j];   // fixed order over this column's samples
+      } else {
+        gko = p.gke_out + s * static_cast<long long>(p.nn - 1) + ck.n0;
+        mg = mis_of(gko);
+#pragma unroll
+        for (int j = 0; j < PR; ++j)
+          if (j < ck.nev) kS[mg + ck.tb + j] = ge[j];   // kappa chunk no longer needed (barrier above)
+      }
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      if (have_out) {
+        const Seg qo = make_seg(go, ck.len);
+        if (qo.head) go[0] = rin[qo.mis];
+        if (qo.tail) go[ck.len - 1] = rin[qo.mis + ck.len - 1];
+        if (qo.body) bulk_s2g(go + qo.head, rin + qo.mis + qo.head, 8u * qo.body);
+      }
+      if (BWD && !shared_field && nel_chunk > 0) {
+        const Seg qg = make_seg(gko, nel_chunk);
+        if (qg.head) gko[0] = kS[qg.mis];
+        if (qg.tail) gko[nel_chunk - 1] = kS[qg.mis + nel_chunk - 1];
+        if (qg.body) bulk_s2g(gko + qg.head, kS + qg.mis + qg.head, 8u * qg.body);
+      }
+      bulk_commit();
+      bulk_wait_read0();   // kS is refilled with 1.0-padding semantics below / by the next load
+    }
+    __syncthreads();
+  }
+  if (BWD && shared_field) {
+    double* o = p.gk_cols + static_cast<long long>(col) * (p.nn - 1) + ck.n0 + ck.tb;
+#pragma unroll
+    for (int j = 0; j < PR; ++j)
+      if (j < ck.nev) o[j] = gacc[j];
+  }
+  if (tid == 0) bulk_wait_read0();
+}
+
+// shared per-element field: dL/dkappa_e = sum over CTA columns (fixed order)
+__global__ void k1d_gk_cols_sum(const double* cols, int ncols, long long n_el, double* out) {
+  const long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (e >= n_el) return;
+  double a = 0.0;
+  for (int c = 0; c < ncols; ++c) a += cols[c * n_el + e];
+  out[e] = a;
+}
+
 // per-sample dL/dkappa -> output (PER_SAMPLE: copy; SCALAR: fixed-order sum over the batch)
 __global__ void k1d_gk_out(const double* gk, long long B, int per_sample, double* out) {
   if (per_sample) {
@@ -522,17 +869,21 @@ namespace dfe {
 
 size_t split1d_workspace_bytes(const dfe_mesh* m, long long B) {
   const int nn = static_cast<int>(m->info.n_nodes);
-  const size_t G = static_cast<size_t>((nn + SCH - 1) / SCH);
-  return static_cast<size_t>(B) * G * (NP1 + NP2) * sizeof(double) + static_cast<size_t>(B) * sizeof(double) + 1024;
+  const size_t G = static_cast<size_t>((nn + PCH - 1) / PCH);   // the per-element kernels use the smaller chunk
+  return static_cast<size_t>(B) * G * (NP1 + NP2) * sizeof(double) + static_cast<size_t>(B) * sizeof(double) +
+         (static_cast<size_t>(2 * 160) * PCH + static_cast<size_t>(nn)) * sizeof(double) + 1024;
 }
 
 // Runs forward (gbar == nullptr) or backward.  Returns DFE_OK or an error; never falls back.
 int split1d_run(const dfe_mesh* m, long long B, bool bwd, const double* in0, long long ld0, const double* in1,
-                long long ld1, const double* kappa, int per_sample, double* out, long long ldo, double* gkappa,
+                long long ld1, const double* kappa, int kappa_mode, double* out, long long ldo, double* gkappa,
                 void* ws, cudaStream_t st) {
+  const bool pe = kappa_mode == DFE_KAPPA_PER_ELEMENT || kappa_mode == DFE_KAPPA_PER_SAMPLE_ELEMENT;
+  const int per_sample = kappa_mode == DFE_KAPPA_PER_SAMPLE;
+  const int chcap = pe ? PCH : SCH;
   PS p{};
   p.nn = static_cast<int>(m->info.n_nodes);
-  p.G = (p.nn + SCH - 1) / SCH;
+  p.G = (p.nn + chcap - 1) / chcap;
   p.chg = (p.nn + p.G - 1) / p.G;
   p.B = B;
   p.hs = m->d_hs;
@@ -544,6 +895,13 @@ int split1d_run(const dfe_mesh* m, long long B, bool bwd, const double* in0, lon
   p.part = reinterpret_cast<double*>(w);
   p.coef = p.part + static_cast<size_t>(B) * p.G * NP1;
   p.gk = p.coef + static_cast<size_t>(B) * p.G * NP2;
+  p.gk_cols = p.gk + B;
+  if (pe) {
+    p.kap_row = kappa;
+    p.ldk = kappa_mode == DFE_KAPPA_PER_SAMPLE_ELEMENT ? p.nn - 1 : 0;
+    p.gke_out = gkappa;
+    p.gk = nullptr;   // the fold kernel does not produce a scalar gradient in these modes
+  }
 
   static bool attr_done = false;
   if (!attr_done) {
@@ -551,6 +909,10 @@ int split1d_run(const dfe_mesh* m, long long B, bool bwd, const double* in0, lon
     DFE_CUDA_OK(cudaFuncSetAttribute(k1d_pass1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p1(true)));
     DFE_CUDA_OK(cudaFuncSetAttribute(k1d_pass2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p2()));
     DFE_CUDA_OK(cudaFuncSetAttribute(k1d_pass2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p2()));
+    DFE_CUDA_OK(cudaFuncSetAttribute(k1d_pe_pass1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pe(2)));
+    DFE_CUDA_OK(cudaFuncSetAttribute(k1d_pe_pass1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pe(2)));
+    DFE_CUDA_OK(cudaFuncSetAttribute(k1d_pe_pass2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pe(2)));
+    DFE_CUDA_OK(cudaFuncSetAttribute(k1d_pe_pass2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pe(3)));
     attr_done = true;
   }
   // Slabs: the batch is walked in groups of samples whose rows fit the L2, so that pass 2's re-read of
@@ -560,7 +922,7 @@ int split1d_run(const dfe_mesh* m, long long B, bool bwd, const double* in0, lon
     return e ? atoll(e) : 0LL;
   }();
   const long long row_bytes = static_cast<long long>(p.nn) * 8 * (bwd ? 2 : 1);
-  long long slab = slab_mb > 0 ? (slab_mb << 20) / row_bytes : B;
+  long long slab = (slab_mb > 0 && !pe) ? (slab_mb << 20) / row_bytes : B;   // per-element kernels: one slab
   const long long cols_full = (2LL * m->sm_count) / p.G > 0 ? (2LL * m->sm_count) / p.G : 1;   // CTA columns per wave
   if (slab < cols_full) slab = cols_full;
   if (slab > B) slab = B;
@@ -572,7 +934,24 @@ int split1d_run(const dfe_mesh* m, long long B, bool bwd, const double* in0, lon
     p.NG = static_cast<int>(NG);
     const unsigned grid = static_cast<unsigned>(NG * p.G);
     const unsigned fold_blocks = static_cast<unsigned>((ns * 32 + 127) / 128);
-    if (!bwd) {
+    if (pe) {
+      if (NG > 160) NG = 160;   // bound of the per-column partial buffer
+      p.NG = static_cast<int>(NG);
+      const unsigned gpe = static_cast<unsigned>(NG * p.G);
+      if (!bwd) {
+        k1d_pe_pass1<false><<<gpe, ST, smem_pe(2), st>>>(p);
+        k1d_fold<false><<<fold_blocks, 128, 0, st>>>(p);
+        k1d_pe_pass2<false><<<gpe, ST, smem_pe(2), st>>>(p);
+      } else {
+        k1d_pe_pass1<true><<<gpe, ST, smem_pe(2), st>>>(p);
+        k1d_fold<true><<<fold_blocks, 128, 0, st>>>(p);
+        k1d_pe_pass2<true><<<gpe, ST, smem_pe(3), st>>>(p);
+        if (p.ldk == 0) {
+          const long long n_el = p.nn - 1;
+          k1d_gk_cols_sum<<<static_cast<unsigned>((n_el + 255) / 256), 256, 0, st>>>(p.gk_cols, p.NG, n_el, gkappa);
+        }
+      }
+    } else if (!bwd) {
       k1d_pass1<false><<<grid, ST, smem_p1(false), st>>>(p);
       k1d_fold<false><<<fold_blocks, 128, 0, st>>>(p);
       k1d_pass2<false><<<grid, ST, smem_p2(), st>>>(p);
@@ -582,7 +961,7 @@ int split1d_run(const dfe_mesh* m, long long B, bool bwd, const double* in0, lon
       if (out) k1d_pass2<true><<<grid, ST, smem_p2(), st>>>(p);
     }
   }
-  if (bwd) {
+  if (bwd && !pe) {
     if (per_sample) k1d_gk_out<<<static_cast<unsigned>((B + 255) / 256), 256, 0, st>>>(p.gk, B, 1, gkappa);
     else k1d_gk_out<<<1, 1024, 0, st>>>(p.gk, B, 0, gkappa);
   }

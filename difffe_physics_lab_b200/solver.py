@@ -121,7 +121,10 @@ class _FESolve(torch.autograd.Function):
         B, n = f.shape
         L = _native.lib()
         u = torch.empty_like(f)
-        fused = bool(nm.info.chain1d) and mode in (_native.KAPPA_SCALAR, _native.KAPPA_PER_SAMPLE)
+        # fused 1-D path: chain meshes; per-element kappa only where one Neumann sweep suffices (<= 2e5 nodes)
+        per_elem = mode in (_native.KAPPA_PER_ELEMENT, _native.KAPPA_PER_SAMPLE_ELEMENT)
+        one_sweep = int(opts["n_refine"]) == 1 or (int(opts["n_refine"]) < 0 and n <= 200000)
+        fused = bool(nm.info.chain1d) and (not per_elem or one_sweep)
         saved_mats = None
         with torch.cuda.device(dev):
             if fused:

@@ -168,6 +168,42 @@ def test_1d_shared_scalar_kappa_batch_and_determinism():
     assert u0.shape == (n + 1,) and np.array_equal(u0, u[0])
 
 
+@pytest.mark.parametrize("n,bcs", [(40, (0.0, 0.0)), (2304, (0.3, -0.2)), (6001, (0.5, None)), (30000, (None, 1.5))])
+def test_1d_per_element_kappa(n, bcs):
+    """kappa of shape (n_el,) (shared field) and (B, n_el) on the fused 1-D path (reference loop with
+    kappa -> kappa[e]), against the exact oracle."""
+    rng = np.random.default_rng(n + 7)
+    B = 3
+    m = FEMesh.line(n, x_left=0.1, x_right=1.9, bc_left=bcs[0], bc_right=bcs[1])
+    assert m._native(torch.cuda.current_device()).info.chain1d == 1
+    f = rng.uniform(0, 1, (B, n + 1))
+    gbar = rng.standard_normal((B, n + 1))
+    kap = np.exp(rng.uniform(np.log(0.1), np.log(10.0), (B, n)))
+    u, gk, gf, _ = run(m, kap, f, gbar)                       # per-sample per-element field
+    assert gk.shape == (B, n)
+    nodes, el, bc = m.nodes.numpy(), m.elements.numpy(), m.dirichlet_nodes
+    for b in range(B):
+        uo, _, gfo = oracle_run(m, kap[b], f[b], gbar[b])
+        assert relerr(u[b], uo) <= TOL1D
+        # dL/dkappa_e = -(dlambda_e)(du_e)/h_e differences neighbouring u values: it is a function of the STORED
+        # float64 u (ulp(u)/|du_e| ~ 1e-11 here), so the oracle differentiates the same stored u as the kernel
+        gko, _, _ = O.adjoint_and_grads(nodes, el, bc, kap[b], u[b], gbar[b])
+        assert np.abs(gk[b] - gko).max() <= TOL1D * np.abs(gko).max()
+        assert np.abs(gf[b] - gfo).max() <= TOL1D * np.abs(gfo).max()
+    u, gk, gf, _ = run(m, kap[0], f, gbar)                    # one field shared by the batch
+    assert gk.shape == (n,)
+    tot = np.zeros(n)
+    for b in range(B):
+        uo, _, gfo = oracle_run(m, kap[0], f[b], gbar[b])
+        assert relerr(u[b], uo) <= TOL1D
+        assert np.abs(gf[b] - gfo).max() <= TOL1D * np.abs(gfo).max()
+        gko, _, _ = O.adjoint_and_grads(nodes, el, bc, kap[0], u[b], gbar[b])
+        tot += gko
+    assert np.abs(gk - tot).max() <= TOL1D * np.abs(tot).max() * B
+    u2, gk2, gf2, _ = run(m, kap[0], f, gbar)
+    assert np.array_equal(u, u2) and np.array_equal(gk, gk2) and np.array_equal(gf, gf2)
+
+
 def test_1d_unaligned_views_and_strides():
     """Rows that start on 8-byte (not 16-byte) boundaries and non-unit batch strides."""
     rng = np.random.default_rng(9)
