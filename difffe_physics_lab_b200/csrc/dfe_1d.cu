@@ -29,6 +29,12 @@ size_t split1d_workspace_bytes(const dfe_mesh* m, long long B);
 int split1d_run(const dfe_mesh* m, long long B, bool bwd, const double* in0, long long ld0, const double* in1,
                 long long ld1, const double* kappa, int kappa_mode, double* out, long long ldo, double* gkappa,
                 void* ws, cudaStream_t st);
+size_t pipe1d_workspace_bytes(const dfe_mesh* m, long long B);
+bool pipe1d_eligible(const dfe_mesh* m, long long B, int kappa_mode, int n_refine, const double* in0, long long ld0,
+                     const double* out, long long ldo);
+int pipe1d_run(const dfe_mesh* m, long long B, bool bwd, const double* in0, long long ld0, const double* in1,
+               long long ld1, const double* kappa, int kappa_mode, double* out, long long ldo, double* gkappa,
+               void* ws, cudaStream_t st);
 }  // namespace dfe
 
 namespace {
@@ -442,15 +448,20 @@ int auto_refine(int n_refine, long long nn) {
   return n_refine > MAX_STAGES - 1 ? MAX_STAGES - 1 : n_refine;
 }
 
-// Kernel variant for n_refine == 1 (the common case): DFE_1D_MODE = split (default) | seq.
-//   split : two streaming passes + fold kernel (dfe_1d_split.cu) — no cross-CTA waits, any mesh size
+// Kernel variant for n_refine == 1 (the common case): DFE_1D_MODE = pipe (default) | split | seq.
+//   pipe  : software-pipelined single pass (dfe_1d_pipe.cu): one read + one write per row, exchange latency
+//           hidden behind other samples; scalar / per-sample kappa, meshes up to ~2e5 nodes
+//   split : two streaming passes + fold kernel (dfe_1d_split.cu) — no cross-CTA waits, any mesh size,
+//           per-element kappa; also the fallback when pipe does not apply
 //   seq   : single persistent kernel with an on-chip exchange per sweep (k_solve1d)
 // n_refine != 1 always uses seq.
-enum Mode1D { MODE_SEQ = 0, MODE_SPLIT = 2 };
+enum Mode1D { MODE_SEQ = 0, MODE_PIPE = 1, MODE_SPLIT = 2 };
 Mode1D mode_1d(int n_refine) {
   static const Mode1D pref = [] {
     const char* e = getenv("DFE_1D_MODE");
-    return (e && e[0] == 's' && e[1] == 'e') ? MODE_SEQ : MODE_SPLIT;
+    if (e && e[0] == 's' && e[1] == 'e') return MODE_SEQ;
+    if (e && e[0] == 's' && e[1] == 'p') return MODE_SPLIT;
+    return MODE_PIPE;
   }();
   return n_refine == 1 ? pref : MODE_SEQ;
 }
@@ -469,7 +480,8 @@ int common_checks(const dfe_mesh* m, long long B, const void* a, const void* kap
   }
   DFE_REQUIRE(kappa_mode >= DFE_KAPPA_SCALAR && kappa_mode <= DFE_KAPPA_PER_SAMPLE_ELEMENT, "%s: bad kappa_mode %d", who,
               kappa_mode);
-  const size_t need = pl.total > dfe::split1d_workspace_bytes(m, B) ? pl.total : dfe::split1d_workspace_bytes(m, B);
+  size_t need = pl.total > dfe::split1d_workspace_bytes(m, B) ? pl.total : dfe::split1d_workspace_bytes(m, B);
+  if (dfe::pipe1d_workspace_bytes(m, B) > need) need = dfe::pipe1d_workspace_bytes(m, B);
   if (ws_bytes < need) {
     dfe::set_error("%s: workspace %zu bytes < required %zu", who, ws_bytes, need);
     return DFE_ERR_WORKSPACE;
@@ -505,7 +517,8 @@ extern "C" size_t dfe_solve1d_workspace_bytes(const dfe_mesh* m, int64_t B) {
   if (!m || B < 1) return 0;
   Plan pl;
   make_plan(m, B, R_BWD, &pl);
-  const size_t sp = m->chain ? dfe::split1d_workspace_bytes(m, B) : 0;
+  size_t sp = m->chain ? dfe::split1d_workspace_bytes(m, B) : 0;
+  if (m->chain && dfe::pipe1d_workspace_bytes(m, B) > sp) sp = dfe::pipe1d_workspace_bytes(m, B);
   return pl.total > sp ? pl.total : sp;
 }
 
@@ -513,10 +526,12 @@ extern "C" int dfe_solve1d_fwd(const dfe_mesh* m, int64_t B, const double* f, in
                                int kappa_mode, int n_refine, double* u, int64_t ldu, void* ws, size_t ws_bytes,
                                void* stream) {
   Plan pl{};
-  const Mode1D mode = m ? mode_1d(auto_refine(n_refine, m->info.n_nodes)) : MODE_SEQ;
+  Mode1D mode = m ? mode_1d(auto_refine(n_refine, m->info.n_nodes)) : MODE_SEQ;
   if (m) make_plan(m, B, R_FWD, &pl);
   int rc = common_checks(m, B, f, kappa, kappa_mode, ws, ws_bytes, pl, "dfe_solve1d_fwd");
   if (rc != DFE_OK) return rc;
+  if (mode == MODE_PIPE && !dfe::pipe1d_eligible(m, B, kappa_mode, auto_refine(n_refine, m->info.n_nodes), f, ldf, u, ldu))
+    mode = MODE_SPLIT;
   if (kappa_mode >= DFE_KAPPA_PER_ELEMENT && mode != MODE_SPLIT) {
     dfe::set_error("dfe_solve1d_fwd: per-element kappa needs the split path (n_refine == 1, i.e. meshes up to 2e5 nodes)");
     return DFE_ERR_UNSUPPORTED;
@@ -531,7 +546,9 @@ extern "C" int dfe_solve1d_fwd(const dfe_mesh* m, int64_t B, const double* f, in
   p.ld0 = ldf;
   p.out = u;
   p.ldo = ldu;
-  if (mode == MODE_SPLIT) {
+  if (mode == MODE_PIPE) {
+    rc = dfe::pipe1d_run(m, B, false, f, ldf, nullptr, 0, kappa, kappa_mode, u, ldu, nullptr, ws, st);
+  } else if (mode == MODE_SPLIT) {
     rc = dfe::split1d_run(m, B, false, f, ldf, nullptr, 0, kappa, kappa_mode, u, ldu, nullptr, ws, st);
   } else {
     DFE_CUDA_OK(cudaMemsetAsync(p.cnt, 0, static_cast<size_t>(B) * sizeof(int), st));
@@ -545,10 +562,13 @@ extern "C" int dfe_solve1d_bwd(const dfe_mesh* m, int64_t B, const double* gbar,
                                int64_t ldu, const double* kappa, int kappa_mode, int n_refine, double* gf,
                                int64_t ldgf, double* gkappa, void* ws, size_t ws_bytes, void* stream) {
   Plan pl{};
-  const Mode1D mode = m ? mode_1d(auto_refine(n_refine, m->info.n_nodes)) : MODE_SEQ;
+  Mode1D mode = m ? mode_1d(auto_refine(n_refine, m->info.n_nodes)) : MODE_SEQ;
   if (m) make_plan(m, B, R_BWD, &pl);
   int rc = common_checks(m, B, gbar, kappa, kappa_mode, ws, ws_bytes, pl, "dfe_solve1d_bwd");
   if (rc != DFE_OK) return rc;
+  if (mode == MODE_PIPE &&
+      !dfe::pipe1d_eligible(m, B, kappa_mode, auto_refine(n_refine, m->info.n_nodes), gbar, ldg, gf, ldgf))
+    mode = MODE_SPLIT;
   if (kappa_mode >= DFE_KAPPA_PER_ELEMENT && mode != MODE_SPLIT) {
     dfe::set_error("dfe_solve1d_bwd: per-element kappa needs the split path (n_refine == 1, i.e. meshes up to 2e5 nodes)");
     return DFE_ERR_UNSUPPORTED;
@@ -567,8 +587,10 @@ extern "C" int dfe_solve1d_bwd(const dfe_mesh* m, int64_t B, const double* gbar,
   p.ld1 = ldu;
   p.out = gf;
   p.ldo = ldgf;
-  if (mode == MODE_SPLIT) {
-    rc = dfe::split1d_run(m, B, true, gbar, ldg, u, ldu, kappa, kappa_mode, gf, ldgf, gkappa, ws, st);
+  if (mode == MODE_PIPE || mode == MODE_SPLIT) {
+    rc = mode == MODE_PIPE
+             ? dfe::pipe1d_run(m, B, true, gbar, ldg, u, ldu, kappa, kappa_mode, gf, ldgf, gkappa, ws, st)
+             : dfe::split1d_run(m, B, true, gbar, ldg, u, ldu, kappa, kappa_mode, gf, ldgf, gkappa, ws, st);
     if (cur != m->info.device) cudaSetDevice(cur);
     return rc;
   }

@@ -1,0 +1,866 @@
+// Software-pipelined single-pass fused 1-D solve / adjoint for chain meshes (one Neumann sweep), sm_100a.
+//
+// Same mathematics as dfe_1d.cu / dfe_1d_split.cu (reference: diffhe/solver.py:73-98, :153-183 and their
+// autograd backward; K = M + E, x = M^{-1}F - M^{-1}E M^{-1}F with flux-form prefix sums), organised so that
+//   * every row is read from HBM once and written once (16 B/node forward, 24 B/node adjoint: the
+//     algorithmic bytes), like the persistent kernel k_solve1d, and
+//   * no CTA ever waits for another one in its critical path, like the split kernels:
+// a sample spans G CTAs (chunk c of the mesh is owned by CTA c of a group for the whole batch, its mesh
+// constants live in REGISTERS), and every CTA works on three different samples per iteration —
+//     phase A (sample it)          rhs, local prefix sums, publish the chunk totals of sweep 0
+//     phase B (sample it-LB)       x0 from the folded totals, rhs1 = -delta*x0, local sums, publish sweep 1
+//     phase C (sample it-LB-LC)    x = x0 + x1, output
+// so the cross-CTA exchange of sample s (two doubles per chunk and sweep through L2) has LB / LC whole
+// iterations to complete.  Intermediate per-node state (W, then z = x0 - c*W1) stays in the shared-memory
+// ring slot the row chunk was loaded into by TMA; the slot is finally stored back with one bulk store.
+//
+// Prefix sums are kept in MOMENT form: a block of nodes contributes (s, m) with m = w - s*X_end, which makes
+// every combine a plain addition: W_i = W^thread_i + sum_before(m) + X_i * sum_before(s).  Scans are therefore
+// two-component add-scans (warp shuffles), chunk folds are plain sums, and X_i (coordinate in half element
+// lengths, from the mesh handle) is a per-node register constant.
+//
+// A ninth "communication" warp per CTA publishes totals, polls/folds the other chunks' totals (data-as-flag:
+// the exchange buffer is pre-set to an all-ones sentinel, no counters, no fences), and drives the TMA bulk
+// loads/stores; the eight compute warps never touch global memory.
+#include <cstdint>
+#include <cstdlib>
+
+#include "dfe_internal.h"
+
+namespace {
+
+#include "dfe_1d_common.cuh"
+
+constexpr unsigned long long SENT = 0xFFFFFFFFFFFFFFFFull;   // "not yet published"
+constexpr int NLMAX = 4;                                       // chunks per sample <= 32*NLMAX
+constexpr int MISC_BYTES = 4096;
+
+struct PP {
+  int nn, G, chg, NG, slotd;
+  long long B;
+  const double* hs;      // h_e/2
+  const double* rh;      // RN(1/(h_e/2))
+  const double* X;       // X_i = sum_{e<i} h_e/2
+  const double* in0;     // forward: f ; backward: gbar
+  long long ld0;
+  const double* in1;     // backward: u
+  long long ld1;
+  double* out;           // forward: u ; backward: dL/df (may be null)
+  long long ldo;
+  const double* kappa;
+  const double* ck;      // (2/kappa, kappa/2) per sample (or one pair, shared kappa)
+  int per_sample;
+  int bcL, bcR;
+  double gL, gR, Xtot;
+  unsigned long long* part;   // [B][2][G][2] chunk totals (s, m) as bit patterns, pre-set to SENT
+  double* gkpart;             // backward: [B][G+2] partial dL/dkappa (chunks, boundary terms of sweep 0 and 1)
+  int* err;                   // set to 1 if a poll timed out (never expected)
+};
+
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void publish(unsigned long long* slot, double s, double m) {
+  unsigned long long a = static_cast<unsigned long long>(__double_as_longlong(s));
+  unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(m));
+  if (a == SENT) a = 0x7FF8000000000000ull;   // a NaN that happens to carry the sentinel payload
+  if (b == SENT) b = 0x7FF8000000000000ull;
+  st_relaxed_u64(slot, a);
+  st_relaxed_u64(slot + 1, b);
+}
+// wait until the word is published; bounded (a stuck poll sets *err and returns 0 instead of hanging the GPU)
+__device__ __forceinline__ double poll_word(const unsigned long long* p, unsigned long long v, int* err, int* dead) {
+  if (v == SENT) {
+    int spins = 0;
+    while (true) {
+      v = ld_relaxed_u64(p);
+      if (v != SENT) break;
+      if (*reinterpret_cast<volatile int*>(dead)) { v = 0; break; }
+      if (++spins > (1 << 22)) {
+        *reinterpret_cast<volatile int*>(dead) = 1;
+        atomicExch(err, 1);
+        v = 0;
+        break;
+      }
+      __nanosleep(40);
+    }
+  }
+  return __longlong_as_double(static_cast<long long>(v));
+}
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// k_i = fl(kappa/h_i) from the stored reciprocal (Markstein correction: correctly rounded)
+__device__ __forceinline__ double kdiv(double kaph, double h, double y) {
+  const double q0 = kaph * y;
+  return fma(fma(-h, q0, kaph), y, q0);
+}
+// err = (a + b) - fl(a + b), exact (TwoSum)
+__device__ __forceinline__ double two_sum_err(double a, double b) {
+  const double d = __dadd_rn(a, b);
+  const double bb = __dsub_rn(d, a);
+  return __dadd_rn(__dsub_rn(a, __dsub_rn(d, bb)), __dsub_rn(b, bb));
+}
+__device__ __forceinline__ int mis_of(const double* g) {
+  return static_cast<int>((reinterpret_cast<uintptr_t>(g) >> 3) & 1);
+}
+
+// two-component inclusive add-scan over the warp; returns the exclusive prefix in (es, em)
+__device__ __forceinline__ void warp_scan2(double& is, double& im, double& es, double& em, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const double os = __shfl_up_sync(0xffffffffu, is, d), om = __shfl_up_sync(0xffffffffu, im, d);
+    if (lane >= d) { is += os; im += om; }
+  }
+  es = __shfl_up_sync(0xffffffffu, is, 1);
+  em = __shfl_up_sync(0xffffffffu, im, 1);
+  if (lane == 0) { es = 0.0; em = 0.0; }
+}
+
+__device__ __forceinline__ void named_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+// 16-byte poll of one (s, m) pair; tearing is harmless: each word is individually "sentinel or final"
+__device__ __forceinline__ void ld_pair(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void poll_pair(const unsigned long long* p, unsigned long long a, unsigned long long b,
+                                          double& s, double& m, int* err, int* dead) {
+  if (a == SENT || b == SENT) {
+    int spins = 0;
+    while (true) {
+      ld_pair(p, a, b);
+      if (a != SENT && b != SENT) break;
+      if (*reinterpret_cast<volatile int*>(dead)) { a = b = 0; break; }
+      if (++spins > (1 << 22)) {
+        *reinterpret_cast<volatile int*>(dead) = 1;
+        atomicExch(err, 1);
+        a = b = 0;
+        break;
+      }
+      __nanosleep(32);
+    }
+  }
+  s = __longlong_as_double(static_cast<long long>(a));
+  m = __longlong_as_double(static_cast<long long>(b));
+}
+
+// ---- the three per-thread phases.  FULL: every one of the R nodes exists and none is a Dirichlet node (no masks).
+template <bool BWD, int R, bool FULL>
+__device__ __forceinline__ void phase_a(double* buf, const double (&hs)[R + 1], int nin, int nst, bool ownsL, double& S,
+                                        double& Wc) {
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    const double in = (FULL || j < nin) ? buf[j] : 0.0;
+    // forward: F_i = h_{i-1}/2 f_i + h_i/2 f_i (solver.py:95-96); backward: gbar on the free rows
+    double F = BWD ? in : fma(in, hs[j + 1], in * hs[j]);
+    if (!FULL && j == 0 && ownsL) F = 0.0;
+    if (!BWD && (FULL || j < nst)) buf[j] = Wc;   // thread-local W at node j, kept in place for phase B
+    S += F;
+    Wc = fma(hs[j + 1], S, Wc);
+  }
+}
+
+template <bool BWD, int R, bool FULL>
+__device__ __forceinline__ void phase_b(double* buf, const double* ub, const double (&hs)[R + 1], const double (&rh)[R + 1],
+                                        const double (&X)[R], int nin, int nst, bool ownsL, double c0, double kaph,
+                                        double a0, double b0, double& S1, double& W1, double& D) {
+  double S = 0.0, Wc = 0.0;
+  double kp = kdiv(kaph, hs[0], rh[0]);
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    double g = 0.0, Wt;
+    if (BWD) {
+      g = (FULL || j < nin) ? buf[j] : 0.0;
+      if (!FULL && j == 0 && ownsL) g = 0.0;
+      Wt = Wc;
+      S += g;
+      Wc = fma(hs[j + 1], S, Wc);
+    } else {
+      Wt = (FULL || j < nst) ? buf[j] : 0.0;
+    }
+    const double x0 = fma(-c0, Wt, fma(b0, X[j], a0));
+    // k_i = fl(kappa/h_i) bit-exactly (solver.py:88); err = (k_{i-1}+k_i) - fl(k_{i-1}+k_i) is minus the rounding of
+    // the reference's diagonal accumulation (solver.py:89-92); it is 0 on Dirichlet and padding rows.
+    const double ki = kdiv(kaph, hs[j + 1], rh[j + 1]);
+    const double v1 = __dmul_rn(two_sum_err(kp, ki), x0);
+    kp = ki;
+    if (BWD) {
+      const double uj = (FULL || j < nst) ? ub[j] : 0.0;
+      D = fma(g + v1, uj, D);
+    }
+    if (FULL || j < nst) buf[j] = fma(-c0, W1, x0);   // z = x0 - c*W1(thread-local), finished in phase C
+    S1 += v1;
+    W1 = fma(hs[j + 1], S1, W1);
+  }
+}
+
+template <bool BWD, int R, bool FULL>
+__device__ __forceinline__ void phase_c(double* buf, const double (&hs)[R + 1], const double (&X)[R], int nst, double a1,
+                                        double b1) {
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    if (FULL || j < nst) {
+      const double xv = buf[j] + fma(b1, X[j], a1);
+      // forward: u[free] = x (solver.py:180-181); backward: dL/df_i = lambda_i (h_{i-1}/2 + h_i/2)
+      buf[j] = BWD ? fma(xv, hs[j], xv * hs[j + 1]) : xv;
+    }
+  }
+}
+
+// Warps 0..W-1 compute; warp W = communication warp of sweep 0 (publishes/folds sweep-0 totals, TMA loads);
+// warp W+1 = communication warp of sweep 1 (publishes/folds sweep-1 totals, TMA stores, dL/dkappa partials).
+template <bool BWD, int R, int W, int LB, int LC>
+__global__ void __launch_bounds__(32 * (W + 2), 2) k1d_pipe(const PP p) {
+  constexpr int NR = LB + LC + 3;           // ring slots of the in-place chain: prefetch, A..C, store drain
+  constexpr int NRU = BWD ? 2 : 0;          // ring slots of the u row (backward, used by phase B only)
+  constexpr int NB1 = 32 * (W + 1);         // threads on the named barriers 1 and 2
+  static_assert(W <= 16 && NR + NRU <= 16 && LB >= 2 && LC >= 2, "layout");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);     // [NR + NRU]
+  double* wt0 = reinterpret_cast<double*>(smem_raw + 128);   // [2][W][2] per-warp totals of sweep 0
+  double* wt1 = wt0 + 4 * W;                                 // [2][W][2] per-warp totals of sweep 1
+  double* red = wt1 + 4 * W;                                 // [2][W]    backward: per-warp dot partials
+  double* cfw0 = red + 2 * W;                                // [2][W][2] per-warp (A, B) of sweep 0 for phase B
+  double* cfw1 = cfw0 + 4 * W;                               // [2][W][2] per-warp (A, B) of sweep 1 for phase C
+  double* sc = cfw1 + 4 * W;                                 // [2][4]    c0, kaph0, c1
+  double* ckring = sc + 8;                                   // [NR][2]   (2/kappa, kappa/2) of the sample in the slot
+  double* ulr = ckring + 2 * NR;                             // [NR][2]   backward, chunk 0: u at the two end nodes
+  int* dead = reinterpret_cast<int*>(ulr + 2 * NR);
+  static_assert(128 + 8 * (18 * W + 8 + 4 * NR) + 8 <= MISC_BYTES, "misc region");
+  double* ring = reinterpret_cast<double*>(smem_raw + MISC_BYTES);
+  double* uring = ring + static_cast<size_t>(NR) * p.slotd;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int G = p.G, nn = p.nn;
+  const int c = blockIdx.x % G, grp = blockIdx.x / G;
+  const int n0 = c * p.chg;
+  const int len = min(nn, n0 + p.chg) - n0;
+  const int nIt = static_cast<int>((p.B - grp + p.NG - 1) / p.NG);
+  const int nTot = nIt + LB + LC + 1;
+  const bool have_out = (p.out != nullptr);
+  const int slotd = p.slotd;
+  // 16-byte phase of a row chunk: element j of the chunk lives at slot[mis + j]; mis depends on the sample only
+  // through its parity (when the leading dimension is odd)
+  const int mis0c = static_cast<int>(((reinterpret_cast<uintptr_t>(p.in0) >> 3) + n0) & 1);
+  const int mis1c = BWD ? static_cast<int>(((reinterpret_cast<uintptr_t>(p.in1) >> 3) + n0) & 1) : 0;
+  const int ld0p = static_cast<int>(p.ld0 & 1), ld1p = static_cast<int>(p.ld1 & 1), ngp = p.NG & 1, grpp = grp & 1;
+  auto mis0_of = [&](int j) { return mis0c ^ (ld0p & (grpp ^ (j & ngp))); };
+  auto mis1_of = [&](int j) { return mis1c ^ (ld1p & (grpp ^ (j & ngp))); };
+
+  if (tid == 0) {
+    for (int k = 0; k < NR + NRU; ++k) mbar_init(bar + k, 1);
+    *dead = 0;
+  }
+  __syncthreads();
+
+  if (warp < W) {
+    // ============================================================================ compute warps
+    const int tb = tid * R;
+    const int nin = max(0, min(R, min(len, nn - (p.bcR ? 1 : 0) - n0) - tb));   // nodes whose input is read
+    const int nst = max(0, min(R, len - tb));                                  // nodes of the chunk held
+    const bool ownsL = p.bcL && c == 0 && tid == 0;
+    const bool ownsR = p.bcR && c == G - 1 && tb <= len - 1 && len - 1 < tb + R;
+    const bool full = (nin == R) && (nst == R) && !ownsL && !ownsR;
+    // mesh constants of this thread's R nodes: hs[j] / rh[j] = element left of node j (hs[R]: right of the last)
+    double hs[R + 1], rh[R + 1], X[R];
+#pragma unroll
+    for (int j = 0; j <= R; ++j) {
+      const int e = n0 - 1 + tb + j;
+      const bool ex = (e >= 0 && e < nn - 1 && tb + j <= len);
+      hs[j] = ex ? p.hs[e] : 0.0;
+      rh[j] = ex ? p.rh[e] : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < R; ++j) X[j] = p.X[min(n0 + tb + j, nn - 1)];
+    const double Xe = p.X[min(n0 + min(tb + R, len), nn - 1)];   // where the block after this thread starts
+    double q0s[LB + 1], q0m[LB + 1], q1s[LC + 1], q1m[LC + 1];   // this thread's exclusive prefixes in flight
+#pragma unroll
+    for (int k = 0; k <= LB; ++k) q0s[k] = q0m[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k <= LC; ++k) q1s[k] = q1m[k] = 0.0;
+    __syncthreads();   // prologue loads of the communication warps
+
+    int slotA = 0, roundA = 0;   // ring slot of phase A's sample and its use count parity
+    for (int it = 0; it < nTot; ++it) {
+      const int par = it & 1;
+      // ---------------------------------------------------------------- phase A (sample it)
+      {
+        double S = 0.0, Wc = 0.0;
+        if (it < nIt) {
+          double* buf = ring + slotA * slotd + mis0_of(it) + tb;
+          mbar_wait(bar + slotA, roundA);
+          if (full) phase_a<BWD, R, true>(buf, hs, nin, nst, ownsL, S, Wc);
+          else phase_a<BWD, R, false>(buf, hs, nin, nst, ownsL, S, Wc);
+        }
+        double is = S, im = fma(-S, Xe, Wc), es, em;
+        warp_scan2(is, im, es, em, lane);
+#pragma unroll
+        for (int k = LB; k > 0; --k) { q0s[k] = q0s[k - 1]; q0m[k] = q0m[k - 1]; }
+        q0s[0] = es;
+        q0m[0] = em;
+        if (lane == 31) {
+          wt0[par * 2 * W + 2 * warp] = is;
+          wt0[par * 2 * W + 2 * warp + 1] = im;
+        }
+        __syncwarp();
+        named_arrive(1, NB1);
+      }
+      // ---------------------------------------------------------------- phase B (sample it-LB)
+      {
+        const int jB = it - LB;
+        int slotB = slotA - LB;
+        if (slotB < 0) slotB += NR;
+        double S1 = 0.0, W1 = 0.0, D = 0.0;
+        if (jB >= 0 && jB < nIt) {
+          double* buf = ring + slotB * slotd + mis0_of(jB) + tb;
+          const double c0 = sc[4 * par], kaph = sc[4 * par + 1];
+          const double a0 = fma(-c0, q0m[LB], cfw0[par * 2 * W + 2 * warp]);
+          const double b0 = fma(-c0, q0s[LB], cfw0[par * 2 * W + 2 * warp + 1]);
+          const double* ub = nullptr;
+          if (BWD) {
+            const int us = jB & 1;
+            ub = uring + us * slotd + mis1_of(jB) + tb;
+            mbar_wait(bar + NR + us, (jB >> 1) & 1);
+          }
+          if (full) phase_b<BWD, R, true>(buf, ub, hs, rh, X, nin, nst, ownsL, c0, kaph, a0, b0, S1, W1, D);
+          else phase_b<BWD, R, false>(buf, ub, hs, rh, X, nin, nst, ownsL, c0, kaph, a0, b0, S1, W1, D);
+        }
+        double is = S1, im = fma(-S1, Xe, W1), es, em;
+        warp_scan2(is, im, es, em, lane);
+#pragma unroll
+        for (int k = LC; k > 0; --k) { q1s[k] = q1s[k - 1]; q1m[k] = q1m[k - 1]; }
+        q1s[0] = es;
+        q1m[0] = em;
+        if (BWD) {
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) D += __shfl_xor_sync(0xffffffffu, D, d);
+        }
+        if (lane == 31) {
+          wt1[par * 2 * W + 2 * warp] = is;
+          wt1[par * 2 * W + 2 * warp + 1] = im;
+          if (BWD) red[par * W + warp] = D;
+        }
+        __syncwarp();
+        named_arrive(2, NB1);
+      }
+      // ---------------------------------------------------------------- phase C (sample it-LB-LC)
+      {
+        const int jC = it - LB - LC;
+        if (jC >= 0 && jC < nIt && have_out) {
+          int slotC = slotA - LB - LC;
+          if (slotC < 0) slotC += NR;
+          double* buf = ring + slotC * slotd + mis0_of(jC) + tb;
+          const double c1 = sc[4 * par + 2];
+          const double a1 = fma(-c1, q1m[LC], cfw1[par * 2 * W + 2 * warp]);
+          const double b1 = fma(-c1, q1s[LC], cfw1[par * 2 * W + 2 * warp + 1]);
+          if (full) {
+            phase_c<BWD, R, true>(buf, hs, X, nst, a1, b1);
+          } else {
+            phase_c<BWD, R, false>(buf, hs, X, nst, a1, b1);
+            if (ownsL) buf[0] = BWD ? 0.0 : p.gL;                 // u[d] = g (solver.py:177-179); dL/df = 0 there
+            if (ownsR) buf[len - 1 - tb] = BWD ? 0.0 : p.gR;
+          }
+          fence_async_smem();
+        }
+      }
+      if (++slotA == NR) { slotA = 0; roundA ^= 1; }
+      __syncthreads();
+    }
+  } else if (warp == W) {
+    // ============================================================================ communication warp, sweep 0
+    const bool LR = p.bcL && p.bcR;
+    const int GP = G + 2;
+    const double rXtot = 1.0 / p.Xtot;
+    const double ga = (!BWD && LR) ? (p.gR - p.gL) * rXtot : 0.0;   // harmonic interpolant of the Dirichlet data
+    const double gb = BWD ? 0.0 : (p.bcL ? p.gL : p.gR);
+    double qs[LB], qm[LB];   // per-lane (= per compute warp) exclusive offsets of the samples in flight
+#pragma unroll
+    for (int k = 0; k < LB; ++k) qs[k] = qm[k] = 0.0;
+
+    // One row-chunk load = one TMA bulk copy (lane 0) + up to eight 8-byte side loads done by lanes 1-8 in ONE
+    // load instruction (unaligned head/tail element of the row, the kappa constants, the end values of u).
+    auto issue_load = [&](int j, const double*& src, double*& dst) {
+      const long long s = grp + static_cast<long long>(j) * p.NG;
+      const int slot = j % NR;
+      const double* g = p.in0 + s * p.ld0 + n0;
+      const Seg q = make_seg(g, len);
+      double* base = ring + slot * slotd;
+      if (lane == 0) {
+        mbar_arrive_expect_tx(bar + slot, 8u * static_cast<uint32_t>(q.body));
+        if (q.body) bulk_g2s(base + q.mis + q.head, g + q.head, 8u * q.body, bar + slot);
+      } else if (lane == 1) {
+        if (q.head) { src = g; dst = base + q.mis; }
+      } else if (lane == 2) {
+        if (q.tail) { src = g + len - 1; dst = base + q.mis + len - 1; }
+      } else if (lane == 3 || lane == 4) {
+        src = p.ck + 2 * (p.per_sample ? s : 0) + (lane - 3);
+        dst = ckring + 2 * slot + (lane - 3);
+      } else if (BWD && c == 0 && lane == 5) {
+        src = p.in1 + s * p.ld1;
+        dst = ulr + 2 * slot;
+      } else if (BWD && c == 0 && lane == 6) {
+        src = p.in1 + s * p.ld1 + nn - 1;
+        dst = ulr + 2 * slot + 1;
+      }
+    };
+    auto issue_load_u = [&](int j, const double*& src, double*& dst) {
+      const long long s = grp + static_cast<long long>(j) * p.NG;
+      const int us = j & 1;
+      const double* g = p.in1 + s * p.ld1 + n0;
+      const Seg q = make_seg(g, len);
+      double* base = uring + us * slotd;
+      if (lane == 0) {
+        mbar_arrive_expect_tx(bar + NR + us, 8u * static_cast<uint32_t>(q.body));
+        if (q.body) bulk_g2s(base + q.mis + q.head, g + q.head, 8u * q.body, bar + NR + us);
+      } else if (lane == 7) {
+        if (q.head) { src = g; dst = base + q.mis; }
+      } else if (lane == 8) {
+        if (q.tail) { src = g + len - 1; dst = base + q.mis + len - 1; }
+      }
+    };
+
+    {   // prologue: sample 0 (phase A of iteration 0)
+      const double* src = nullptr;
+      double* dst = nullptr;
+      if (nIt > 0) issue_load(0, src, dst);
+      double v = 0.0;
+      if (src) v = *src;
+      if (src) *dst = v;
+    }
+    __syncthreads();
+
+    for (int it = 0; it < nTot; ++it) {
+      const int par = it & 1, nxt = par ^ 1;
+      const int f0 = it + 1 - LB;   // sample of phase B in the next iteration
+      const bool v0 = f0 >= 0 && f0 < nIt;
+      const long long sB = grp + static_cast<long long>(v0 ? f0 : 0) * p.NG;
+      const unsigned long long* base0 = p.part + ((sB * 2 + 0) * G) * 2;
+      // ---- all global loads of this iteration go out first: chunk totals of f0, then the row prefetch + side loads
+      unsigned long long ra[2], rb[2];
+#pragma unroll
+      for (int l = 0; l < 2; ++l) {
+        const int ci = lane + 32 * l;
+        ra[l] = rb[l] = SENT;
+        if (v0 && ci < G) ld_pair(base0 + 2 * ci, ra[l], rb[l]);
+      }
+      const double* src = nullptr;
+      double* dst = nullptr;
+      if (it + 1 < nIt) {
+        // the store that last used this slot was issued (by the other communication warp) one iteration ago and
+        // that warp waited for its shared-memory reads before the barrier that ended the previous iteration
+        issue_load(it + 1, src, dst);
+      }
+      if (BWD && v0) issue_load_u(f0, src, dst);   // u row for phase B of the next iteration
+      double side = 0.0;
+      if (src) side = *src;
+      // ---- totals of phase A (this iteration): publish, keep the per-warp exclusive offsets
+      named_sync(1, NB1);
+      {
+        double is = (lane < W) ? wt0[par * 2 * W + 2 * lane] : 0.0, im = (lane < W) ? wt0[par * 2 * W + 2 * lane + 1] : 0.0;
+#pragma unroll
+        for (int d = 1; d < W; d <<= 1) {
+          const double os = __shfl_up_sync(0xffffffffu, is, d), om = __shfl_up_sync(0xffffffffu, im, d);
+          if (lane >= d) { is += os; im += om; }
+        }
+        double es = __shfl_up_sync(0xffffffffu, is, 1), em = __shfl_up_sync(0xffffffffu, im, 1);
+        if (lane == 0) { es = 0.0; em = 0.0; }
+#pragma unroll
+        for (int k = LB - 1; k > 0; --k) { qs[k] = qs[k - 1]; qm[k] = qm[k - 1]; }
+        qs[0] = es;
+        qm[0] = em;
+        if (lane == W - 1 && it < nIt) {
+          const long long s = grp + static_cast<long long>(it) * p.NG;
+          publish(p.part + ((s * 2 + 0) * G + c) * 2, is, im);
+        }
+      }
+      // ---- fold sweep 0 of sample f0: chunk totals -> boundary constants -> per-warp (A, B) for the next iteration
+      if (v0) {
+        double Sx = 0.0, Mx = 0.0, St = 0.0, Mt = 0.0;
+#pragma unroll
+        for (int l = 0; l < 2; ++l) {
+          const int ci = lane + 32 * l;
+          if (ci < G) {
+            double sv, mv;
+            poll_pair(base0 + 2 * ci, ra[l], rb[l], sv, mv, p.err, dead);
+            St += sv; Mt += mv;
+            if (ci < c) { Sx += sv; Mx += mv; }
+          }
+        }
+        for (int l0 = 64; l0 < G; l0 += 32) {   // more than 64 chunks per sample (rare): extra trips
+          const int ci = lane + l0;
+          if (ci < G) {
+            double sv, mv;
+            poll_pair(base0 + 2 * ci, SENT, SENT, sv, mv, p.err, dead);
+            St += sv; Mt += mv;
+            if (ci < c) { Sx += sv; Mx += mv; }
+          }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+          Sx += __shfl_xor_sync(0xffffffffu, Sx, d);
+          Mx += __shfl_xor_sync(0xffffffffu, Mx, d);
+          St += __shfl_xor_sync(0xffffffffu, St, d);
+          Mt += __shfl_xor_sync(0xffffffffu, Mt, d);
+        }
+        const int slot = f0 % NR;
+        const double cc = ckring[2 * slot], kaph = ckring[2 * slot + 1];
+        const double Wtot = fma(St, p.Xtot, Mt);                  // sum_e h_e/2 S_e over the whole sample
+        const double C = LR ? Wtot * rXtot : (p.bcL ? St : 0.0);   // flux constant fixed by the boundary conditions
+        const double A = gb + (p.bcL ? 0.0 : cc * Wtot) - cc * Mx;
+        const double Bc = ga + cc * (C - Sx);
+        if (lane < W) {
+          cfw0[nxt * 2 * W + 2 * lane] = fma(-cc, qm[LB - 1], A);
+          cfw0[nxt * 2 * W + 2 * lane + 1] = fma(-cc, qs[LB - 1], Bc);
+        }
+        if (lane == 0) {
+          sc[4 * nxt] = cc;
+          sc[4 * nxt + 1] = kaph;
+          if (BWD && c == 0) {
+            // boundary terms of sum_e q_e (u_{e+1}-u_e) = C (u_R-u_L) - S_tot u_R + sum_i rhs_i u_i
+            const double uL = ulr[2 * slot], uR = ulr[2 * slot + 1];
+            p.gkpart[sB * GP + G] = C * (uR - uL) - St * uR;
+          }
+        }
+      }
+      if (src) *dst = side;   // side loads land in shared memory
+      __syncthreads();
+    }
+  } else {
+    // ============================================================================ communication warp, sweep 1
+    const bool LR = p.bcL && p.bcR;
+    const int GP = G + 2;
+    const double rXtot = 1.0 / p.Xtot;
+    double qs[LC], qm[LC];
+#pragma unroll
+    for (int k = 0; k < LC; ++k) qs[k] = qm[k] = 0.0;
+    __syncthreads();   // prologue
+
+    for (int it = 0; it < nTot; ++it) {
+      const int par = it & 1, nxt = par ^ 1;
+      const int f1 = it + 1 - LB - LC;   // sample of phase C in the next iteration
+      const bool v1 = f1 >= 0 && f1 < nIt;
+      const long long sC = grp + static_cast<long long>(v1 ? f1 : 0) * p.NG;
+      const unsigned long long* base1 = p.part + ((sC * 2 + 1) * G) * 2;
+      // ---- store the row phase C finished in the previous iteration
+      {
+        const int js = it - 1 - LB - LC;
+        if (js >= 0 && js < nIt && have_out) {
+          const long long s = grp + static_cast<long long>(js) * p.NG;
+          double* go = p.out + s * p.ldo + n0;
+          const double* ssrc = ring + (js % NR) * slotd;
+          const Seg qo = make_seg(go, len);
+          if (lane == 0) {
+            if (qo.body) bulk_s2g(go + qo.head, ssrc + qo.mis + qo.head, 8u * qo.body);
+            bulk_commit();
+          } else if (lane == 1) {
+            if (qo.head) go[0] = ssrc[qo.mis];
+          } else if (lane == 2) {
+            if (qo.tail) go[len - 1] = ssrc[qo.mis + len - 1];
+          }
+        }
+      }
+      // ---- backward: dot partial of the sample phase B handled in the previous iteration
+      if (BWD) {
+        const int jb = it - 1 - LB;
+        double a = (lane < W) ? red[nxt * W + lane] : 0.0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+        if (jb >= 0 && jb < nIt && lane == 0) {
+          const long long s = grp + static_cast<long long>(jb) * p.NG;
+          p.gkpart[s * GP + c] = a;
+        }
+      }
+      // ---- chunk totals of f1 (published about one iteration ago): loads go out before the wait for phase B
+      unsigned long long ra[2], rb[2];
+#pragma unroll
+      for (int l = 0; l < 2; ++l) {
+        const int ci = lane + 32 * l;
+        ra[l] = rb[l] = SENT;
+        if (v1 && ci < G) ld_pair(base1 + 2 * ci, ra[l], rb[l]);
+      }
+      // ---- totals of phase B (this iteration): publish, keep the per-warp exclusive offsets
+      named_sync(2, NB1);
+      double es, em;
+      {
+        double is = (lane < W) ? wt1[par * 2 * W + 2 * lane] : 0.0, im = (lane < W) ? wt1[par * 2 * W + 2 * lane + 1] : 0.0;
+#pragma unroll
+        for (int d = 1; d < W; d <<= 1) {
+          const double os = __shfl_up_sync(0xffffffffu, is, d), om = __shfl_up_sync(0xffffffffu, im, d);
+          if (lane >= d) { is += os; im += om; }
+        }
+        es = __shfl_up_sync(0xffffffffu, is, 1);
+        em = __shfl_up_sync(0xffffffffu, im, 1);
+        if (lane == 0) { es = 0.0; em = 0.0; }
+        const int jB = it - LB;
+        if (lane == W - 1 && jB >= 0 && jB < nIt) {
+          const long long s = grp + static_cast<long long>(jB) * p.NG;
+          publish(p.part + ((s * 2 + 1) * G + c) * 2, is, im);
+        }
+      }
+      // ---- fold sweep 1 of sample f1 (its offsets were pushed LC-1 iterations ago)
+      if (v1) {
+        double Sx = 0.0, Mx = 0.0, St = 0.0, Mt = 0.0;
+#pragma unroll
+        for (int l = 0; l < 2; ++l) {
+          const int ci = lane + 32 * l;
+          if (ci < G) {
+            double sv, mv;
+            poll_pair(base1 + 2 * ci, ra[l], rb[l], sv, mv, p.err, dead);
+            St += sv; Mt += mv;
+            if (ci < c) { Sx += sv; Mx += mv; }
+          }
+        }
+        for (int l0 = 64; l0 < G; l0 += 32) {
+          const int ci = lane + l0;
+          if (ci < G) {
+            double sv, mv;
+            poll_pair(base1 + 2 * ci, SENT, SENT, sv, mv, p.err, dead);
+            St += sv; Mt += mv;
+            if (ci < c) { Sx += sv; Mx += mv; }
+          }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+          Sx += __shfl_xor_sync(0xffffffffu, Sx, d);
+          Mx += __shfl_xor_sync(0xffffffffu, Mx, d);
+          St += __shfl_xor_sync(0xffffffffu, St, d);
+          Mt += __shfl_xor_sync(0xffffffffu, Mt, d);
+        }
+        const int slot = f1 % NR;
+        const double cc = ckring[2 * slot];
+        const double Wtot = fma(St, p.Xtot, Mt);
+        const double C = LR ? Wtot * rXtot : (p.bcL ? St : 0.0);
+        const double A = (p.bcL ? 0.0 : cc * Wtot) - cc * Mx;
+        const double Bc = cc * (C - Sx);
+        if (lane < W) {
+          cfw1[nxt * 2 * W + 2 * lane] = fma(-cc, qm[LC - 2], A);
+          cfw1[nxt * 2 * W + 2 * lane + 1] = fma(-cc, qs[LC - 2], Bc);
+        }
+        if (lane == 0) {
+          sc[4 * nxt + 2] = cc;
+          if (BWD && c == 0) {
+            const double uL = ulr[2 * slot], uR = ulr[2 * slot + 1];
+            p.gkpart[sC * GP + G + 1] = C * (uR - uL) - St * uR;
+          }
+        }
+      }
+#pragma unroll
+      for (int k = LC - 1; k > 0; --k) { qs[k] = qs[k - 1]; qm[k] = qm[k - 1]; }
+      qs[0] = es;
+      qm[0] = em;
+      if (lane == 0) bulk_wait_read0();   // the slot just stored may be reloaded next iteration
+      __syncthreads();
+    }
+    if (lane == 0) bulk_wait_all0();
+  }
+}
+
+// (2/kappa, kappa/2) per sample (or once, shared kappa): keeps every division out of the pipelined kernel
+__global__ void k1d_pipe_ck(const double* kappa, long long n, double* ck) {
+  const long long s = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (s < n) {
+    const double k = kappa[s];
+    ck[2 * s] = 2.0 / k;
+    ck[2 * s + 1] = 0.5 * k;
+  }
+}
+
+// dL/dkappa = -(1/kappa) * (sum of the per-(sample, chunk) partials + boundary terms), fixed summation order
+// (no float atomics).
+__global__ void k1d_pipe_gk(const double* part, const double* kappa, long long B, int GP, int per_sample, double* out) {
+  if (per_sample) {
+    const long long s = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (s < B) {
+      double a = 0.0;
+      for (int g = 0; g < GP; ++g) a += part[s * GP + g];
+      out[s] = -a / kappa[s];
+    }
+  } else {
+    __shared__ double sh[1024];
+    double a = 0.0;
+    for (long long s = threadIdx.x; s < B; s += blockDim.x) {
+      double r = 0.0;
+      for (int g = 0; g < GP; ++g) r += part[s * GP + g];
+      a += r;
+    }
+    sh[threadIdx.x] = a;
+    __syncthreads();
+    for (int d = blockDim.x / 2; d > 0; d >>= 1) {
+      if (static_cast<int>(threadIdx.x) < d) sh[threadIdx.x] += sh[threadIdx.x + d];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = -sh[0] / kappa[0];
+  }
+}
+
+struct Geo {
+  int G, chg, NG, slotd;
+  size_t smem;
+};
+
+template <bool BWD, int R, int W, int LB, int LC>
+int run_cfg(const dfe_mesh* m, PP p, cudaStream_t st, int gbound, int* G_used) {
+  constexpr int NR = LB + LC + 3, NRU = BWD ? 2 : 0;
+  constexpr int CAP = R * 32 * W, THREADS = 32 * (W + 2);
+  auto kern = k1d_pipe<BWD, R, W, LB, LC>;
+  const int nn = p.nn;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DFE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done = true;
+  }
+  // geometry: the throughput is proportional to the number of groups NG resident at once (every CTA does the
+  // same work per iteration), so take the largest NG whose chunk size fits the shared memory at the assumed
+  // occupancy; within that NG use as many chunks as there are CTA slots (smaller slots, no idle SM).
+  Geo g{};
+  bool found = false;
+  for (int per_sm = 2; per_sm >= 1 && !found; --per_sm) {
+    const long long slots = static_cast<long long>(per_sm) * m->sm_count;
+    const long long gcap = slots < gbound ? slots : gbound;   // gbound: what the workspace was sized for
+    const long long gmin = (nn + CAP - 1) / CAP;
+    if (gmin > gcap) continue;
+    long long NGmax = slots / gmin;
+    if (NGmax > p.B) NGmax = p.B;
+    for (long long NG = NGmax; NG >= 1 && !found; --NG) {
+      long long G = slots / NG;
+      if (G > gcap) G = gcap;
+      if (G > nn) G = nn;
+      if (p.B <= NG) G = gmin;   // tiny batches: nothing to gain from more chunks
+      g.chg = static_cast<int>((nn + G - 1) / G);
+      g.G = (nn + g.chg - 1) / g.chg;   // drop empty trailing chunks
+      g.NG = static_cast<int>(NG);
+      g.slotd = ((g.chg + 2) + 1) & ~1;
+      g.smem = MISC_BYTES + sizeof(double) * static_cast<size_t>(NR + NRU) * g.slotd;
+      if (g.smem > 227 * 1024) continue;
+      int occ = 0;
+      DFE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, g.smem));
+      found = occ >= per_sm;
+    }
+  }
+  if (!found) {
+    dfe::set_error("dfe_solve1d (pipelined): no resident configuration for a mesh of %d nodes", nn);
+    return DFE_ERR_UNSUPPORTED;
+  }
+  p.G = g.G;
+  p.chg = g.chg;
+  p.NG = g.NG;
+  p.slotd = g.slotd;
+  *G_used = g.G;
+  // exchange buffer [B][2][G][2] <- "not yet published"
+  DFE_CUDA_OK(cudaMemsetAsync(p.part, 0xFF, static_cast<size_t>(p.B) * 2 * g.G * 2 * sizeof(double), st));
+  DFE_CUDA_OK(cudaMemsetAsync(p.err, 0, sizeof(int), st));
+  {
+    const long long nk = p.per_sample ? p.B : 1;
+    k1d_pipe_ck<<<static_cast<unsigned>((nk + 255) / 256), 256, 0, st>>>(p.kappa, nk, const_cast<double*>(p.ck));
+  }
+  kern<<<static_cast<unsigned>(g.NG * g.G), THREADS, g.smem, st>>>(p);
+  DFE_CUDA_OK(cudaGetLastError());
+  return DFE_OK;
+}
+
+int cfg_id() {
+  static const int id = [] {
+    const char* e = getenv("DFE_PIPE_CFG");
+    return e ? atoi(e) : 0;
+  }();
+  return id;
+}
+
+}  // namespace
+
+namespace dfe {
+
+// upper bound of the chunks per sample over every configuration (smallest thread capacity 5*256, and the
+// geometry pass never more than doubles the minimum chunk count)
+static size_t g_bound(const dfe_mesh* m) {
+  const size_t gmin = (static_cast<size_t>(m->info.n_nodes) + 1279) / 1280;
+  const size_t b = 2 * gmin + 2;
+  return b < 32 * NLMAX ? b : 32 * NLMAX;
+}
+
+size_t pipe1d_workspace_bytes(const dfe_mesh* m, long long B) {
+  const size_t gmax = g_bound(m);
+  return static_cast<size_t>(B) * 2 * gmax * 2 * sizeof(double) + static_cast<size_t>(B) * (gmax + 2) * sizeof(double) + static_cast<size_t>(B) * 2 * sizeof(double) + 512;
+}
+
+// Can the pipelined kernel take this call?  (chain mesh, one Neumann sweep, scalar / per-sample kappa, and the
+// output row of every sample has the 16-byte phase of its input row — the chain works in place in shared memory.)
+bool pipe1d_eligible(const dfe_mesh* m, long long B, int kappa_mode, int n_refine, const double* in0, long long ld0,
+                     const double* out, long long ldo) {
+  if (!m->chain || n_refine != 1) return false;
+  if (kappa_mode != DFE_KAPPA_SCALAR && kappa_mode != DFE_KAPPA_PER_SAMPLE) return false;
+  if (m->info.n_nodes > 5LL * 256 * 32 * NLMAX) return false;
+  if (out) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(in0) >> 3, b = reinterpret_cast<uintptr_t>(out) >> 3;
+    if ((a ^ b) & 1) return false;
+    if (B > 1 && ((ld0 ^ ldo) & 1)) return false;
+  }
+  return true;
+}
+
+int pipe1d_run(const dfe_mesh* m, long long B, bool bwd, const double* in0, long long ld0, const double* in1,
+               long long ld1, const double* kappa, int kappa_mode, double* out, long long ldo, double* gkappa,
+               void* ws, cudaStream_t st) {
+  PP p{};
+  p.nn = static_cast<int>(m->info.n_nodes);
+  p.B = B;
+  p.hs = m->d_hs;
+  p.rh = m->d_rh;
+  p.X = m->d_X;
+  p.Xtot = m->x_total;
+  p.in0 = in0; p.ld0 = ld0; p.in1 = in1; p.ld1 = ld1; p.out = out; p.ldo = ldo;
+  p.kappa = kappa;
+  p.per_sample = kappa_mode == DFE_KAPPA_PER_SAMPLE;
+  p.bcL = m->bc_left; p.bcR = m->bc_right; p.gL = m->g_left; p.gR = m->g_right;
+  const size_t gmax = g_bound(m);
+  unsigned char* w = static_cast<unsigned char*>(ws);
+  const size_t part_bytes = static_cast<size_t>(B) * 2 * gmax * 2 * sizeof(double);
+  p.part = reinterpret_cast<unsigned long long*>(w);
+  p.gkpart = reinterpret_cast<double*>(w + part_bytes);
+  p.ck = reinterpret_cast<double*>(w + part_bytes + static_cast<size_t>(B) * (gmax + 2) * sizeof(double));
+  p.err = reinterpret_cast<int*>(w + part_bytes + static_cast<size_t>(B) * (gmax + 2 + 2) * sizeof(double));
+  int rc, G = 0;
+  const int id = cfg_id();
+  if (!bwd) {
+    switch (id) {
+      case 1: rc = run_cfg<false, 7, 8, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 2: rc = run_cfg<false, 11, 4, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 3: rc = run_cfg<false, 13, 4, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 4: rc = run_cfg<false, 9, 5, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 5: rc = run_cfg<false, 15, 4, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 6: rc = run_cfg<false, 11, 5, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 7: rc = run_cfg<false, 9, 6, 3, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 8: rc = run_cfg<false, 9, 6, 2, 3>(m, p, st, static_cast<int>(gmax), &G); break;
+      default: rc = run_cfg<false, 9, 6, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+    }
+  } else {
+    switch (id) {
+      case 1: rc = run_cfg<true, 7, 8, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 2: rc = run_cfg<true, 11, 4, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 3: rc = run_cfg<true, 13, 4, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 4: rc = run_cfg<true, 9, 6, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 5: rc = run_cfg<true, 7, 6, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 6: rc = run_cfg<true, 11, 5, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 7: rc = run_cfg<true, 9, 5, 3, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 8: rc = run_cfg<true, 9, 5, 2, 3>(m, p, st, static_cast<int>(gmax), &G); break;
+      default: rc = run_cfg<true, 9, 5, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+    }
+  }
+  if (rc != DFE_OK) return rc;
+  if (bwd) {
+    if (p.per_sample) k1d_pipe_gk<<<static_cast<unsigned>((B + 255) / 256), 256, 0, st>>>(p.gkpart, kappa, B, G + 2, 1, gkappa);
+    else k1d_pipe_gk<<<1, 1024, 0, st>>>(p.gkpart, kappa, B, G + 2, 0, gkappa);
+    DFE_CUDA_OK(cudaGetLastError());
+  }
+  return DFE_OK;
+}
+
+}  // namespace dfe

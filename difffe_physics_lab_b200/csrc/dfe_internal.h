@@ -72,6 +72,8 @@ struct dfe_mesh {
   double g_left = 0.0, g_right = 0.0;
   const double* d_hs = nullptr;  // chain: h_e/2 (h_e = x_{e+1}-x_e as the reference computes it), device, n_el
   const double* d_rh = nullptr;  // chain: correctly rounded 1/(h_e/2), device, n_el
+  const double* d_X = nullptr;   // chain: X_i = sum_{e<i} h_e/2, device, n_nodes
+  double x_total = 0.0;          // chain: X_{n_nodes-1}
   // ---- device
   dfe::MeshDev dev{};
   std::vector<void*> allocs;  // every cudaMalloc owned by the handle

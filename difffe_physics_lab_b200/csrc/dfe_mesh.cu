@@ -307,6 +307,17 @@ extern "C" int dfe_mesh_create(int dim, int64_t n_nodes, int64_t n_el, const dou
       }
       rc = upload(m, hsv, &m->d_hs);
       if (rc == DFE_OK) rc = upload(m, rhv, &m->d_rh);
+      // X_i = sum_{e<i} h_e/2 (coordinate measured in half element lengths), accumulated in long double so that
+      // the table is correct to the last bit or two of a double: the pipelined 1-D kernel writes the prefix
+      // sums in moment form (W_i = m + s X_i) and needs one consistent, accurate coordinate per node.
+      std::vector<double> xv(n);
+      long double acc = 0.0L;
+      for (int i = 0; i < n; ++i) {
+        xv[i] = static_cast<double>(acc);
+        if (i < ne) acc += static_cast<long double>(hsv[i]);
+      }
+      if (rc == DFE_OK) rc = upload(m, xv, &m->d_X);
+      m->x_total = xv[n - 1];
     }
     cudaDeviceProp prop;
     if (rc == DFE_OK && cudaGetDeviceProperties(&prop, device) == cudaSuccess) m->sm_count = prop.multiProcessorCount;
