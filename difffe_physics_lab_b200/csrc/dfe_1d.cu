@@ -31,7 +31,7 @@ int split1d_run(const dfe_mesh* m, long long B, bool bwd, const double* in0, lon
                 void* ws, cudaStream_t st);
 size_t pipe1d_workspace_bytes(const dfe_mesh* m, long long B);
 bool pipe1d_eligible(const dfe_mesh* m, long long B, int kappa_mode, int n_refine, const double* in0, long long ld0,
-                     const double* out, long long ldo);
+                     const double* in1, const double* out, long long ldo);
 int pipe1d_run(const dfe_mesh* m, long long B, bool bwd, const double* in0, long long ld0, const double* in1,
                long long ld1, const double* kappa, int kappa_mode, double* out, long long ldo, double* gkappa,
                void* ws, cudaStream_t st);
@@ -530,7 +530,7 @@ extern "C" int dfe_solve1d_fwd(const dfe_mesh* m, int64_t B, const double* f, in
   if (m) make_plan(m, B, R_FWD, &pl);
   int rc = common_checks(m, B, f, kappa, kappa_mode, ws, ws_bytes, pl, "dfe_solve1d_fwd");
   if (rc != DFE_OK) return rc;
-  if (mode == MODE_PIPE && !dfe::pipe1d_eligible(m, B, kappa_mode, auto_refine(n_refine, m->info.n_nodes), f, ldf, u, ldu))
+  if (mode == MODE_PIPE && !dfe::pipe1d_eligible(m, B, kappa_mode, auto_refine(n_refine, m->info.n_nodes), f, ldf, nullptr, u, ldu))
     mode = MODE_SPLIT;
   if (kappa_mode >= DFE_KAPPA_PER_ELEMENT && mode != MODE_SPLIT) {
     dfe::set_error("dfe_solve1d_fwd: per-element kappa needs the split path (n_refine == 1, i.e. meshes up to 2e5 nodes)");
@@ -567,7 +567,7 @@ extern "C" int dfe_solve1d_bwd(const dfe_mesh* m, int64_t B, const double* gbar,
   int rc = common_checks(m, B, gbar, kappa, kappa_mode, ws, ws_bytes, pl, "dfe_solve1d_bwd");
   if (rc != DFE_OK) return rc;
   if (mode == MODE_PIPE &&
-      !dfe::pipe1d_eligible(m, B, kappa_mode, auto_refine(n_refine, m->info.n_nodes), gbar, ldg, gf, ldgf))
+      !dfe::pipe1d_eligible(m, B, kappa_mode, auto_refine(n_refine, m->info.n_nodes), gbar, ldg, u, gf, ldgf))
     mode = MODE_SPLIT;
   if (kappa_mode >= DFE_KAPPA_PER_ELEMENT && mode != MODE_SPLIT) {
     dfe::set_error("dfe_solve1d_bwd: per-element kappa needs the split path (n_refine == 1, i.e. meshes up to 2e5 nodes)");

@@ -55,6 +55,7 @@ struct PP {
   unsigned long long* part;   // [B][2][G][2] chunk totals (s, m) as bit patterns, pre-set to SENT
   double* gkpart;             // backward: [B][G+2] partial dL/dkappa (chunks, boundary terms of sweep 0 and 1)
   int* err;                   // set to 1 if a poll timed out (never expected)
+  long long* trace;           // debug (DFE_PIPE_TRACE=1): [3 CTAs][16 iterations][4 roles][8 events] clock64 stamps
 };
 
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
@@ -152,6 +153,12 @@ __device__ __forceinline__ void poll_pair(const unsigned long long* p, unsigned 
   m = __longlong_as_double(static_cast<long long>(b));
 }
 
+// debug timeline: CTAs 0 / 100 / 200, iterations 200..215
+__device__ __forceinline__ void tr(const PP& p, int it, int role, int ev) {
+  if (p.trace != nullptr && it >= 200 && it < 216 && (blockIdx.x % 100) == 0 && blockIdx.x < 300)
+    p.trace[(((blockIdx.x / 100) * 16 + (it - 200)) * 4 + role) * 8 + ev] = clock64();
+}
+
 // ---- the three per-thread phases.  FULL: every one of the R nodes exists and none is a Dirichlet node (no masks).
 template <bool BWD, int R, bool FULL>
 __device__ __forceinline__ void phase_a(double* buf, const double (&hs)[R + 1], int nin, int nst, bool ownsL, double& S,
@@ -215,10 +222,156 @@ __device__ __forceinline__ void phase_c(double* buf, const double (&hs)[R + 1], 
   }
 }
 
-// Warps 0..W-1 compute; warp W = communication warp of sweep 0 (publishes/folds sweep-0 totals, TMA loads);
-// warp W+1 = communication warp of sweep 1 (publishes/folds sweep-1 totals, TMA stores, dL/dkappa partials).
+// One fold warp per sweep ST (0 or 1).  Per iteration it:
+//   * after the compute warps finished the sweep's phase for this iteration (named barrier 1+ST): scan their W
+//     per-warp totals, publish the CTA total of that sample, keep the per-warp exclusive offsets (register queue);
+//   * fold the G chunk totals of the sample the NEXT iteration consumes (published about one iteration ago, its
+//     loads are issued before the barrier wait): boundary constants -> per-warp (A, B) -> shared memory.
+template <bool BWD, int W, int LB, int LC, int ST>
+__device__ __forceinline__ void fold_warp(const PP& p, int lane, int c, int grp, int nIt, int nTot, const double* wt,
+                                          double* cfw, double* sc, int* dead) {
+  constexpr int LAG = ST == 0 ? LB : LB + LC;   // the sample folded in iteration it is it + 1 - LAG
+  constexpr int QD = ST == 0 ? LB : LC;         // offsets queue depth
+  constexpr int QI = ST == 0 ? LB - 1 : LC - 2; // queue index of the folded sample at fold time (see the pushes)
+  constexpr int NB1 = 32 * (W + 1);
+  const int G = p.G, GP = G + 2;
+  const bool LR = p.bcL && p.bcR;
+  const double rXtot = 1.0 / p.Xtot;
+  const bool lift = (!BWD && ST == 0);   // harmonic interpolant of the Dirichlet data: forward, sweep 0 only
+  const double ga = (lift && LR) ? (p.gR - p.gL) * rXtot : 0.0;
+  const double gb = lift ? (p.bcL ? p.gL : p.gR) : 0.0;
+  double qs[QD], qm[QD];
+#pragma unroll
+  for (int k = 0; k < QD; ++k) qs[k] = qm[k] = 0.0;
+  const long long sstep = p.NG;
+  long long sF = grp + static_cast<long long>(1 - LAG) * sstep;   // sample folded in iteration 0 (may be negative)
+  long long sP = grp + static_cast<long long>(ST == 0 ? 0 : -LB) * sstep;   // sample published in iteration 0
+  const bool ends = BWD && c == 0;
+  // constants of the sample folded in the current iteration, fetched one iteration ahead
+  double ccur = 0.0, khcur = 0.0, uLcur = 0.0, uRcur = 0.0;
+  {
+    const int f = 1 - LAG;
+    if (f >= 0 && f < nIt) {
+      const double* ck = p.ck + (p.per_sample ? 2 * sF : 0);
+      ccur = ck[0];
+      khcur = ck[1];
+      if (ends) { uLcur = p.in1[sF * p.ld1]; uRcur = p.in1[sF * p.ld1 + p.nn - 1]; }
+    }
+  }
+  __syncthreads();   // prologue
+
+  for (int it = 0; it < nTot; ++it) {
+    const int par = it & 1, nxt = par ^ 1;
+    const int f = it + 1 - LAG;
+    const bool vf = f >= 0 && f < nIt;
+    const unsigned long long* base = p.part + ((sF * 2 + ST) * G) * 2;
+    if (lane == 0) tr(p, it, 1 + ST, 0);
+    // ---- loads first: chunk totals of sample f, constants of sample f+1
+    unsigned long long ra[3], rb[3];
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+      const int ci = lane + 32 * l;
+      ra[l] = rb[l] = SENT;
+      if (vf && ci < G) ld_pair(base + 2 * ci, ra[l], rb[l]);
+    }
+    double cnx = 0.0, khnx = 0.0, uLnx = 0.0, uRnx = 0.0;
+    if (f + 1 >= 0 && f + 1 < nIt) {
+      const long long sN = sF + sstep;
+      const double* ck = p.ck + (p.per_sample ? 2 * sN : 0);
+      cnx = ck[0];
+      khnx = ck[1];
+      if (ends) { uLnx = p.in1[sN * p.ld1]; uRnx = p.in1[sN * p.ld1 + p.nn - 1]; }
+    }
+    // ---- totals of this iteration's phase: publish, keep the per-warp exclusive offsets
+    if (lane == 0) tr(p, it, 1 + ST, 1);
+    named_sync(1 + ST, NB1);
+    if (lane == 0) tr(p, it, 1 + ST, 2);
+    double es, em;
+    {
+      double is = (lane < W) ? wt[par * 2 * W + 2 * lane] : 0.0, im = (lane < W) ? wt[par * 2 * W + 2 * lane + 1] : 0.0;
+#pragma unroll
+      for (int d = 1; d < W; d <<= 1) {
+        const double os = __shfl_up_sync(0xffffffffu, is, d), om = __shfl_up_sync(0xffffffffu, im, d);
+        if (lane >= d) { is += os; im += om; }
+      }
+      es = __shfl_up_sync(0xffffffffu, is, 1);
+      em = __shfl_up_sync(0xffffffffu, im, 1);
+      if (lane == 0) { es = 0.0; em = 0.0; }
+      const int jp = ST == 0 ? it : it - LB;
+      if (lane == W - 1 && jp >= 0 && jp < nIt) publish(p.part + ((sP * 2 + ST) * G + c) * 2, is, im);
+    }
+    if (ST == 0) {   // sweep 0: the fold below is LB-1 pushes behind, this iteration's push included
+#pragma unroll
+      for (int k = QD - 1; k > 0; --k) { qs[k] = qs[k - 1]; qm[k] = qm[k - 1]; }
+      qs[0] = es;
+      qm[0] = em;
+    }
+    // ---- fold
+    if (lane == 0) tr(p, it, 1 + ST, 3);
+    if (vf) {
+      double Sx = 0.0, Mx = 0.0, St = 0.0, Mt = 0.0;
+#pragma unroll
+      for (int l = 0; l < 3; ++l) {
+        const int ci = lane + 32 * l;
+        if (ci < G) {
+          double sv, mv;
+          poll_pair(base + 2 * ci, ra[l], rb[l], sv, mv, p.err, dead);
+          St += sv; Mt += mv;
+          if (ci < c) { Sx += sv; Mx += mv; }
+        }
+      }
+      for (int l0 = 96; l0 < G; l0 += 32) {   // more than 96 chunks per sample (rare): extra trips
+        const int ci = lane + l0;
+        if (ci < G) {
+          double sv, mv;
+          poll_pair(base + 2 * ci, SENT, SENT, sv, mv, p.err, dead);
+          St += sv; Mt += mv;
+          if (ci < c) { Sx += sv; Mx += mv; }
+        }
+      }
+      if (lane == 0) tr(p, it, 1 + ST, 4);
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        Sx += __shfl_xor_sync(0xffffffffu, Sx, d);
+        Mx += __shfl_xor_sync(0xffffffffu, Mx, d);
+        St += __shfl_xor_sync(0xffffffffu, St, d);
+        Mt += __shfl_xor_sync(0xffffffffu, Mt, d);
+      }
+      const double cc = ccur;
+      const double Wtot = fma(St, p.Xtot, Mt);                   // sum_e h_e/2 S_e over the whole sample
+      const double C = LR ? Wtot * rXtot : (p.bcL ? St : 0.0);    // flux constant fixed by the boundary conditions
+      const double A = gb + (p.bcL ? 0.0 : cc * Wtot) - cc * Mx;
+      const double Bc = ga + cc * (C - Sx);
+      if (lane < W) {
+        cfw[nxt * 2 * W + 2 * lane] = fma(-cc, qm[QI], A);
+        cfw[nxt * 2 * W + 2 * lane + 1] = fma(-cc, qs[QI], Bc);
+      }
+      if (lane == 0) {
+        sc[4 * nxt + 2 * ST] = cc;
+        if (ST == 0) sc[4 * nxt + 1] = khcur;
+        // backward, chunk 0: boundary terms of sum_e q_e (u_{e+1}-u_e) = C (u_R-u_L) - S_tot u_R + sum_i rhs_i u_i
+        if (ends) p.gkpart[sF * GP + G + ST] = C * (uRcur - uLcur) - St * uRcur;
+      }
+    }
+    if (ST == 1) {   // sweep 1: the fold above is LC-2 pushes behind, this iteration's push excluded
+#pragma unroll
+      for (int k = QD - 1; k > 0; --k) { qs[k] = qs[k - 1]; qm[k] = qm[k - 1]; }
+      qs[0] = es;
+      qm[0] = em;
+    }
+    ccur = cnx; khcur = khnx; uLcur = uLnx; uRcur = uRnx;
+    sF += sstep;
+    sP += sstep;
+    if (lane == 0) tr(p, it, 1 + ST, 5);
+    __syncthreads();
+    if (lane == 0) tr(p, it, 1 + ST, 6);
+  }
+}
+
+// Warps 0..W-1 compute; warp W / W+1 = fold warps of sweep 0 / 1; warp W+2 = I/O warp (TMA loads and stores,
+// dL/dkappa partials).
 template <bool BWD, int R, int W, int LB, int LC>
-__global__ void __launch_bounds__(32 * (W + 2), 2) k1d_pipe(const PP p) {
+__global__ void __launch_bounds__(32 * (W + 3), 2) k1d_pipe(const PP p) {
   constexpr int NR = LB + LC + 3;           // ring slots of the in-place chain: prefetch, A..C, store drain
   constexpr int NRU = BWD ? 2 : 0;          // ring slots of the u row (backward, used by phase B only)
   constexpr int NB1 = 32 * (W + 1);         // threads on the named barriers 1 and 2
@@ -231,10 +384,8 @@ __global__ void __launch_bounds__(32 * (W + 2), 2) k1d_pipe(const PP p) {
   double* cfw0 = red + 2 * W;                                // [2][W][2] per-warp (A, B) of sweep 0 for phase B
   double* cfw1 = cfw0 + 4 * W;                               // [2][W][2] per-warp (A, B) of sweep 1 for phase C
   double* sc = cfw1 + 4 * W;                                 // [2][4]    c0, kaph0, c1
-  double* ckring = sc + 8;                                   // [NR][2]   (2/kappa, kappa/2) of the sample in the slot
-  double* ulr = ckring + 2 * NR;                             // [NR][2]   backward, chunk 0: u at the two end nodes
-  int* dead = reinterpret_cast<int*>(ulr + 2 * NR);
-  static_assert(128 + 8 * (18 * W + 8 + 4 * NR) + 8 <= MISC_BYTES, "misc region");
+  int* dead = reinterpret_cast<int*>(sc + 8);
+  static_assert(128 + 8 * (18 * W + 8) + 8 <= MISC_BYTES, "misc region");
   double* ring = reinterpret_cast<double*>(smem_raw + MISC_BYTES);
   double* uring = ring + static_cast<size_t>(NR) * p.slotd;
 
@@ -286,7 +437,7 @@ __global__ void __launch_bounds__(32 * (W + 2), 2) k1d_pipe(const PP p) {
     for (int k = 0; k <= LB; ++k) q0s[k] = q0m[k] = 0.0;
 #pragma unroll
     for (int k = 0; k <= LC; ++k) q1s[k] = q1m[k] = 0.0;
-    __syncthreads();   // prologue loads of the communication warps
+    __syncthreads();   // prologue loads of the service warps
 
     int slotA = 0, roundA = 0;   // ring slot of phase A's sample and its use count parity
     for (int it = 0; it < nTot; ++it) {
@@ -294,9 +445,11 @@ __global__ void __launch_bounds__(32 * (W + 2), 2) k1d_pipe(const PP p) {
       // ---------------------------------------------------------------- phase A (sample it)
       {
         double S = 0.0, Wc = 0.0;
+        if (tid == 0) tr(p, it, 0, 0);
         if (it < nIt) {
           double* buf = ring + slotA * slotd + mis0_of(it) + tb;
           mbar_wait(bar + slotA, roundA);
+          if (tid == 0) tr(p, it, 0, 1);
           if (full) phase_a<BWD, R, true>(buf, hs, nin, nst, ownsL, S, Wc);
           else phase_a<BWD, R, false>(buf, hs, nin, nst, ownsL, S, Wc);
         }
@@ -312,6 +465,7 @@ __global__ void __launch_bounds__(32 * (W + 2), 2) k1d_pipe(const PP p) {
         }
         __syncwarp();
         named_arrive(1, NB1);
+        if (tid == 0) tr(p, it, 0, 2);
       }
       // ---------------------------------------------------------------- phase B (sample it-LB)
       {
@@ -330,6 +484,7 @@ __global__ void __launch_bounds__(32 * (W + 2), 2) k1d_pipe(const PP p) {
             ub = uring + us * slotd + mis1_of(jB) + tb;
             mbar_wait(bar + NR + us, (jB >> 1) & 1);
           }
+          if (tid == 0) tr(p, it, 0, 3);
           if (full) phase_b<BWD, R, true>(buf, ub, hs, rh, X, nin, nst, ownsL, c0, kaph, a0, b0, S1, W1, D);
           else phase_b<BWD, R, false>(buf, ub, hs, rh, X, nin, nst, ownsL, c0, kaph, a0, b0, S1, W1, D);
         }
@@ -350,6 +505,7 @@ __global__ void __launch_bounds__(32 * (W + 2), 2) k1d_pipe(const PP p) {
         }
         __syncwarp();
         named_arrive(2, NB1);
+        if (tid == 0) tr(p, it, 0, 4);
       }
       // ---------------------------------------------------------------- phase C (sample it-LB-LC)
       {
@@ -372,183 +528,50 @@ __global__ void __launch_bounds__(32 * (W + 2), 2) k1d_pipe(const PP p) {
         }
       }
       if (++slotA == NR) { slotA = 0; roundA ^= 1; }
+      if (tid == 0) tr(p, it, 0, 5);
       __syncthreads();
+      if (tid == 0) tr(p, it, 0, 6);
     }
   } else if (warp == W) {
-    // ============================================================================ communication warp, sweep 0
-    const bool LR = p.bcL && p.bcR;
+    fold_warp<BWD, W, LB, LC, 0>(p, lane, c, grp, nIt, nTot, wt0, cfw0, sc, dead);
+  } else if (warp == W + 1) {
+    fold_warp<BWD, W, LB, LC, 1>(p, lane, c, grp, nIt, nTot, wt1, cfw1, sc, dead);
+  } else {
+    // ============================================================================ I/O warp
+    // Row chunks are loaded as the 16-byte aligned superset [g - mis, g + len rounded up): the element before /
+    // after the chunk belongs to the same array (the host checks the base alignment; the very last element of
+    // the array is fetched separately), so a load is ONE bulk copy and element j lands at slot[mis + j].
     const int GP = G + 2;
-    const double rXtot = 1.0 / p.Xtot;
-    const double ga = (!BWD && LR) ? (p.gR - p.gL) * rXtot : 0.0;   // harmonic interpolant of the Dirichlet data
-    const double gb = BWD ? 0.0 : (p.bcL ? p.gL : p.gR);
-    double qs[LB], qm[LB];   // per-lane (= per compute warp) exclusive offsets of the samples in flight
-#pragma unroll
-    for (int k = 0; k < LB; ++k) qs[k] = qm[k] = 0.0;
-
-    // One row-chunk load = one TMA bulk copy (lane 0) + up to eight 8-byte side loads done by lanes 1-8 in ONE
-    // load instruction (unaligned head/tail element of the row, the kappa constants, the end values of u).
-    auto issue_load = [&](int j, const double*& src, double*& dst) {
-      const long long s = grp + static_cast<long long>(j) * p.NG;
-      const int slot = j % NR;
-      const double* g = p.in0 + s * p.ld0 + n0;
-      const Seg q = make_seg(g, len);
-      double* base = ring + slot * slotd;
+    const long long last_s = p.B - 1;
+    auto load_row = [&](const double* rowbase, long long ld, long long s, double* dst, uint64_t* mb) {
+      const double* g = rowbase + s * ld + n0;
+      const int mis = static_cast<int>((reinterpret_cast<uintptr_t>(g) >> 3) & 1);
+      int cnt = (mis + len + 1) & ~1;
+      const bool clip = (s == last_s && c == G - 1 && ((mis + len) & 1));   // would read past the end of the array
+      if (clip) cnt -= 2;
       if (lane == 0) {
-        mbar_arrive_expect_tx(bar + slot, 8u * static_cast<uint32_t>(q.body));
-        if (q.body) bulk_g2s(base + q.mis + q.head, g + q.head, 8u * q.body, bar + slot);
-      } else if (lane == 1) {
-        if (q.head) { src = g; dst = base + q.mis; }
-      } else if (lane == 2) {
-        if (q.tail) { src = g + len - 1; dst = base + q.mis + len - 1; }
-      } else if (lane == 3 || lane == 4) {
-        src = p.ck + 2 * (p.per_sample ? s : 0) + (lane - 3);
-        dst = ckring + 2 * slot + (lane - 3);
-      } else if (BWD && c == 0 && lane == 5) {
-        src = p.in1 + s * p.ld1;
-        dst = ulr + 2 * slot;
-      } else if (BWD && c == 0 && lane == 6) {
-        src = p.in1 + s * p.ld1 + nn - 1;
-        dst = ulr + 2 * slot + 1;
+        mbar_arrive_expect_tx(mb, 8u * static_cast<uint32_t>(cnt));
+        if (cnt) bulk_g2s(dst, g - mis, 8u * cnt, mb);
+        if (clip) dst[mis + len - 1] = g[len - 1];
       }
     };
-    auto issue_load_u = [&](int j, const double*& src, double*& dst) {
-      const long long s = grp + static_cast<long long>(j) * p.NG;
-      const int us = j & 1;
-      const double* g = p.in1 + s * p.ld1 + n0;
-      const Seg q = make_seg(g, len);
-      double* base = uring + us * slotd;
-      if (lane == 0) {
-        mbar_arrive_expect_tx(bar + NR + us, 8u * static_cast<uint32_t>(q.body));
-        if (q.body) bulk_g2s(base + q.mis + q.head, g + q.head, 8u * q.body, bar + NR + us);
-      } else if (lane == 7) {
-        if (q.head) { src = g; dst = base + q.mis; }
-      } else if (lane == 8) {
-        if (q.tail) { src = g + len - 1; dst = base + q.mis + len - 1; }
-      }
-    };
-
-    {   // prologue: sample 0 (phase A of iteration 0)
-      const double* src = nullptr;
-      double* dst = nullptr;
-      if (nIt > 0) issue_load(0, src, dst);
-      double v = 0.0;
-      if (src) v = *src;
-      if (src) *dst = v;
-    }
+    if (nIt > 0) load_row(p.in0, p.ld0, grp, ring, bar);   // prologue: sample 0 (phase A of iteration 0)
     __syncthreads();
 
     for (int it = 0; it < nTot; ++it) {
-      const int par = it & 1, nxt = par ^ 1;
-      const int f0 = it + 1 - LB;   // sample of phase B in the next iteration
-      const bool v0 = f0 >= 0 && f0 < nIt;
-      const long long sB = grp + static_cast<long long>(v0 ? f0 : 0) * p.NG;
-      const unsigned long long* base0 = p.part + ((sB * 2 + 0) * G) * 2;
-      // ---- all global loads of this iteration go out first: chunk totals of f0, then the row prefetch + side loads
-      unsigned long long ra[2], rb[2];
-#pragma unroll
-      for (int l = 0; l < 2; ++l) {
-        const int ci = lane + 32 * l;
-        ra[l] = rb[l] = SENT;
-        if (v0 && ci < G) ld_pair(base0 + 2 * ci, ra[l], rb[l]);
-      }
-      const double* src = nullptr;
-      double* dst = nullptr;
+      const int nxt = (it + 1) & 1;
+      if (lane == 0) tr(p, it, 3, 0);
+      // ---- prefetch: the row of phase A in the next iteration (its slot was stored one iteration ago and that
+      // store's shared-memory reads were awaited before the barrier), the u row of phase B in the next iteration
       if (it + 1 < nIt) {
-        // the store that last used this slot was issued (by the other communication warp) one iteration ago and
-        // that warp waited for its shared-memory reads before the barrier that ended the previous iteration
-        issue_load(it + 1, src, dst);
+        const int j = it + 1;
+        load_row(p.in0, p.ld0, grp + static_cast<long long>(j) * p.NG, ring + (j % NR) * slotd, bar + (j % NR));
       }
-      if (BWD && v0) issue_load_u(f0, src, dst);   // u row for phase B of the next iteration
-      double side = 0.0;
-      if (src) side = *src;
-      // ---- totals of phase A (this iteration): publish, keep the per-warp exclusive offsets
-      named_sync(1, NB1);
-      {
-        double is = (lane < W) ? wt0[par * 2 * W + 2 * lane] : 0.0, im = (lane < W) ? wt0[par * 2 * W + 2 * lane + 1] : 0.0;
-#pragma unroll
-        for (int d = 1; d < W; d <<= 1) {
-          const double os = __shfl_up_sync(0xffffffffu, is, d), om = __shfl_up_sync(0xffffffffu, im, d);
-          if (lane >= d) { is += os; im += om; }
-        }
-        double es = __shfl_up_sync(0xffffffffu, is, 1), em = __shfl_up_sync(0xffffffffu, im, 1);
-        if (lane == 0) { es = 0.0; em = 0.0; }
-#pragma unroll
-        for (int k = LB - 1; k > 0; --k) { qs[k] = qs[k - 1]; qm[k] = qm[k - 1]; }
-        qs[0] = es;
-        qm[0] = em;
-        if (lane == W - 1 && it < nIt) {
-          const long long s = grp + static_cast<long long>(it) * p.NG;
-          publish(p.part + ((s * 2 + 0) * G + c) * 2, is, im);
-        }
+      if (BWD) {
+        const int f0 = it + 1 - LB;
+        if (f0 >= 0 && f0 < nIt)
+          load_row(p.in1, p.ld1, grp + static_cast<long long>(f0) * p.NG, uring + (f0 & 1) * slotd, bar + NR + (f0 & 1));
       }
-      // ---- fold sweep 0 of sample f0: chunk totals -> boundary constants -> per-warp (A, B) for the next iteration
-      if (v0) {
-        double Sx = 0.0, Mx = 0.0, St = 0.0, Mt = 0.0;
-#pragma unroll
-        for (int l = 0; l < 2; ++l) {
-          const int ci = lane + 32 * l;
-          if (ci < G) {
-            double sv, mv;
-            poll_pair(base0 + 2 * ci, ra[l], rb[l], sv, mv, p.err, dead);
-            St += sv; Mt += mv;
-            if (ci < c) { Sx += sv; Mx += mv; }
-          }
-        }
-        for (int l0 = 64; l0 < G; l0 += 32) {   // more than 64 chunks per sample (rare): extra trips
-          const int ci = lane + l0;
-          if (ci < G) {
-            double sv, mv;
-            poll_pair(base0 + 2 * ci, SENT, SENT, sv, mv, p.err, dead);
-            St += sv; Mt += mv;
-            if (ci < c) { Sx += sv; Mx += mv; }
-          }
-        }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-          Sx += __shfl_xor_sync(0xffffffffu, Sx, d);
-          Mx += __shfl_xor_sync(0xffffffffu, Mx, d);
-          St += __shfl_xor_sync(0xffffffffu, St, d);
-          Mt += __shfl_xor_sync(0xffffffffu, Mt, d);
-        }
-        const int slot = f0 % NR;
-        const double cc = ckring[2 * slot], kaph = ckring[2 * slot + 1];
-        const double Wtot = fma(St, p.Xtot, Mt);                  // sum_e h_e/2 S_e over the whole sample
-        const double C = LR ? Wtot * rXtot : (p.bcL ? St : 0.0);   // flux constant fixed by the boundary conditions
-        const double A = gb + (p.bcL ? 0.0 : cc * Wtot) - cc * Mx;
-        const double Bc = ga + cc * (C - Sx);
-        if (lane < W) {
-          cfw0[nxt * 2 * W + 2 * lane] = fma(-cc, qm[LB - 1], A);
-          cfw0[nxt * 2 * W + 2 * lane + 1] = fma(-cc, qs[LB - 1], Bc);
-        }
-        if (lane == 0) {
-          sc[4 * nxt] = cc;
-          sc[4 * nxt + 1] = kaph;
-          if (BWD && c == 0) {
-            // boundary terms of sum_e q_e (u_{e+1}-u_e) = C (u_R-u_L) - S_tot u_R + sum_i rhs_i u_i
-            const double uL = ulr[2 * slot], uR = ulr[2 * slot + 1];
-            p.gkpart[sB * GP + G] = C * (uR - uL) - St * uR;
-          }
-        }
-      }
-      if (src) *dst = side;   // side loads land in shared memory
-      __syncthreads();
-    }
-  } else {
-    // ============================================================================ communication warp, sweep 1
-    const bool LR = p.bcL && p.bcR;
-    const int GP = G + 2;
-    const double rXtot = 1.0 / p.Xtot;
-    double qs[LC], qm[LC];
-#pragma unroll
-    for (int k = 0; k < LC; ++k) qs[k] = qm[k] = 0.0;
-    __syncthreads();   // prologue
-
-    for (int it = 0; it < nTot; ++it) {
-      const int par = it & 1, nxt = par ^ 1;
-      const int f1 = it + 1 - LB - LC;   // sample of phase C in the next iteration
-      const bool v1 = f1 >= 0 && f1 < nIt;
-      const long long sC = grp + static_cast<long long>(v1 ? f1 : 0) * p.NG;
-      const unsigned long long* base1 = p.part + ((sC * 2 + 1) * G) * 2;
       // ---- store the row phase C finished in the previous iteration
       {
         const int js = it - 1 - LB - LC;
@@ -578,85 +601,9 @@ __global__ void __launch_bounds__(32 * (W + 2), 2) k1d_pipe(const PP p) {
           p.gkpart[s * GP + c] = a;
         }
       }
-      // ---- chunk totals of f1 (published about one iteration ago): loads go out before the wait for phase B
-      unsigned long long ra[2], rb[2];
-#pragma unroll
-      for (int l = 0; l < 2; ++l) {
-        const int ci = lane + 32 * l;
-        ra[l] = rb[l] = SENT;
-        if (v1 && ci < G) ld_pair(base1 + 2 * ci, ra[l], rb[l]);
-      }
-      // ---- totals of phase B (this iteration): publish, keep the per-warp exclusive offsets
-      named_sync(2, NB1);
-      double es, em;
-      {
-        double is = (lane < W) ? wt1[par * 2 * W + 2 * lane] : 0.0, im = (lane < W) ? wt1[par * 2 * W + 2 * lane + 1] : 0.0;
-#pragma unroll
-        for (int d = 1; d < W; d <<= 1) {
-          const double os = __shfl_up_sync(0xffffffffu, is, d), om = __shfl_up_sync(0xffffffffu, im, d);
-          if (lane >= d) { is += os; im += om; }
-        }
-        es = __shfl_up_sync(0xffffffffu, is, 1);
-        em = __shfl_up_sync(0xffffffffu, im, 1);
-        if (lane == 0) { es = 0.0; em = 0.0; }
-        const int jB = it - LB;
-        if (lane == W - 1 && jB >= 0 && jB < nIt) {
-          const long long s = grp + static_cast<long long>(jB) * p.NG;
-          publish(p.part + ((s * 2 + 1) * G + c) * 2, is, im);
-        }
-      }
-      // ---- fold sweep 1 of sample f1 (its offsets were pushed LC-1 iterations ago)
-      if (v1) {
-        double Sx = 0.0, Mx = 0.0, St = 0.0, Mt = 0.0;
-#pragma unroll
-        for (int l = 0; l < 2; ++l) {
-          const int ci = lane + 32 * l;
-          if (ci < G) {
-            double sv, mv;
-            poll_pair(base1 + 2 * ci, ra[l], rb[l], sv, mv, p.err, dead);
-            St += sv; Mt += mv;
-            if (ci < c) { Sx += sv; Mx += mv; }
-          }
-        }
-        for (int l0 = 64; l0 < G; l0 += 32) {
-          const int ci = lane + l0;
-          if (ci < G) {
-            double sv, mv;
-            poll_pair(base1 + 2 * ci, SENT, SENT, sv, mv, p.err, dead);
-            St += sv; Mt += mv;
-            if (ci < c) { Sx += sv; Mx += mv; }
-          }
-        }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-          Sx += __shfl_xor_sync(0xffffffffu, Sx, d);
-          Mx += __shfl_xor_sync(0xffffffffu, Mx, d);
-          St += __shfl_xor_sync(0xffffffffu, St, d);
-          Mt += __shfl_xor_sync(0xffffffffu, Mt, d);
-        }
-        const int slot = f1 % NR;
-        const double cc = ckring[2 * slot];
-        const double Wtot = fma(St, p.Xtot, Mt);
-        const double C = LR ? Wtot * rXtot : (p.bcL ? St : 0.0);
-        const double A = (p.bcL ? 0.0 : cc * Wtot) - cc * Mx;
-        const double Bc = cc * (C - Sx);
-        if (lane < W) {
-          cfw1[nxt * 2 * W + 2 * lane] = fma(-cc, qm[LC - 2], A);
-          cfw1[nxt * 2 * W + 2 * lane + 1] = fma(-cc, qs[LC - 2], Bc);
-        }
-        if (lane == 0) {
-          sc[4 * nxt + 2] = cc;
-          if (BWD && c == 0) {
-            const double uL = ulr[2 * slot], uR = ulr[2 * slot + 1];
-            p.gkpart[sC * GP + G + 1] = C * (uR - uL) - St * uR;
-          }
-        }
-      }
-#pragma unroll
-      for (int k = LC - 1; k > 0; --k) { qs[k] = qs[k - 1]; qm[k] = qm[k - 1]; }
-      qs[0] = es;
-      qm[0] = em;
-      if (lane == 0) bulk_wait_read0();   // the slot just stored may be reloaded next iteration
+      if (lane == 0) tr(p, it, 3, 1);
+      if (lane == 0) bulk_wait_read0();   // the slot just stored is reloaded next iteration
+      if (lane == 0) tr(p, it, 3, 2);
       __syncthreads();
     }
     if (lane == 0) bulk_wait_all0();
@@ -709,7 +656,7 @@ struct Geo {
 template <bool BWD, int R, int W, int LB, int LC>
 int run_cfg(const dfe_mesh* m, PP p, cudaStream_t st, int gbound, int* G_used) {
   constexpr int NR = LB + LC + 3, NRU = BWD ? 2 : 0;
-  constexpr int CAP = R * 32 * W, THREADS = 32 * (W + 2);
+  constexpr int CAP = R * 32 * W, THREADS = 32 * (W + 3);
   auto kern = k1d_pipe<BWD, R, W, LB, LC>;
   const int nn = p.nn;
   static bool attr_done = false;
@@ -794,10 +741,11 @@ size_t pipe1d_workspace_bytes(const dfe_mesh* m, long long B) {
 // Can the pipelined kernel take this call?  (chain mesh, one Neumann sweep, scalar / per-sample kappa, and the
 // output row of every sample has the 16-byte phase of its input row — the chain works in place in shared memory.)
 bool pipe1d_eligible(const dfe_mesh* m, long long B, int kappa_mode, int n_refine, const double* in0, long long ld0,
-                     const double* out, long long ldo) {
+                     const double* in1, const double* out, long long ldo) {
   if (!m->chain || n_refine != 1) return false;
   if (kappa_mode != DFE_KAPPA_SCALAR && kappa_mode != DFE_KAPPA_PER_SAMPLE) return false;
   if (m->info.n_nodes > 5LL * 256 * 32 * NLMAX) return false;
+  if ((reinterpret_cast<uintptr_t>(in0) | reinterpret_cast<uintptr_t>(in1)) & 15) return false;   // aligned-superset TMA loads (see the I/O warp)
   if (out) {
     const uintptr_t a = reinterpret_cast<uintptr_t>(in0) >> 3, b = reinterpret_cast<uintptr_t>(out) >> 3;
     if ((a ^ b) & 1) return false;
@@ -829,32 +777,53 @@ int pipe1d_run(const dfe_mesh* m, long long B, bool bwd, const double* in0, long
   p.err = reinterpret_cast<int*>(w + part_bytes + static_cast<size_t>(B) * (gmax + 2 + 2) * sizeof(double));
   int rc, G = 0;
   const int id = cfg_id();
+  static const bool want_trace = getenv("DFE_PIPE_TRACE") != nullptr;
+  const size_t trace_n = 3 * 16 * 4 * 8;
+  if (want_trace) {
+    DFE_CUDA_OK(cudaMalloc(&p.trace, trace_n * sizeof(long long)));
+    DFE_CUDA_OK(cudaMemsetAsync(p.trace, 0, trace_n * sizeof(long long), st));
+  }
   if (!bwd) {
     switch (id) {
-      case 1: rc = run_cfg<false, 7, 8, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 2: rc = run_cfg<false, 11, 4, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 3: rc = run_cfg<false, 13, 4, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 1: rc = run_cfg<false, 9, 6, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 2: rc = run_cfg<false, 13, 4, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 3: rc = run_cfg<false, 15, 4, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
       case 4: rc = run_cfg<false, 9, 5, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 5: rc = run_cfg<false, 15, 4, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 6: rc = run_cfg<false, 11, 5, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 7: rc = run_cfg<false, 9, 6, 3, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 8: rc = run_cfg<false, 9, 6, 2, 3>(m, p, st, static_cast<int>(gmax), &G); break;
-      default: rc = run_cfg<false, 9, 6, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 5: rc = run_cfg<false, 11, 5, 3, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 6: rc = run_cfg<false, 11, 5, 2, 3>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 7: rc = run_cfg<false, 7, 8, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 8: rc = run_cfg<false, 13, 5, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      default: rc = run_cfg<false, 11, 5, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
     }
   } else {
     switch (id) {
-      case 1: rc = run_cfg<true, 7, 8, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 2: rc = run_cfg<true, 11, 4, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 1: rc = run_cfg<true, 11, 4, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 2: rc = run_cfg<true, 7, 7, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
       case 3: rc = run_cfg<true, 13, 4, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
       case 4: rc = run_cfg<true, 9, 6, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 5: rc = run_cfg<true, 7, 6, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 6: rc = run_cfg<true, 11, 5, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 7: rc = run_cfg<true, 9, 5, 3, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 8: rc = run_cfg<true, 9, 5, 2, 3>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 5: rc = run_cfg<true, 9, 5, 3, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 6: rc = run_cfg<true, 9, 5, 2, 3>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 7: rc = run_cfg<true, 7, 8, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 8: rc = run_cfg<true, 11, 5, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
       default: rc = run_cfg<true, 9, 5, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
     }
   }
   if (rc != DFE_OK) return rc;
+  if (want_trace) {
+    std::vector<long long> h(trace_n);
+    DFE_CUDA_OK(cudaStreamSynchronize(st));
+    DFE_CUDA_OK(cudaMemcpy(h.data(), p.trace, trace_n * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(p.trace);
+    FILE* fo = fopen(bwd ? "gpurun_out/trace_bwd.txt" : "gpurun_out/trace_fwd.txt", "w");
+    if (fo) {
+      for (size_t i = 0; i < trace_n; i += 8) {
+        fprintf(fo, "cta %zu it %zu role %zu:", i / (16 * 4 * 8), (i / 32) % 16 + 200, (i / 8) % 4);
+        for (int e = 0; e < 8; ++e) fprintf(fo, " %lld", h[i + e]);
+        fprintf(fo, "\n");
+      }
+      fclose(fo);
+    }
+  }
   if (bwd) {
     if (p.per_sample) k1d_pipe_gk<<<static_cast<unsigned>((B + 255) / 256), 256, 0, st>>>(p.gkpart, kappa, B, G + 2, 1, gkappa);
     else k1d_pipe_gk<<<1, 1024, 0, st>>>(p.gkpart, kappa, B, G + 2, 0, gkappa);

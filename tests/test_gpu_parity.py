@@ -215,7 +215,7 @@ def test_1d_unaligned_views_and_strides():
     s = DifferentiableFESolver(m, kappa=0.9)
     u_view = s(f)
     u_cont = s(f.contiguous())
-    assert torch.equal(u_view, u_cont)
+    assert torch.equal(u_view, u_cont)   # the host layer makes the view contiguous: same kernel, same bits
     L = _native.lib()                   # straight through the C ABI with ld > n_nodes and odd offsets
     nm = m._native(torch.cuda.current_device())
     out = torch.zeros((B, n + 1 + 3), dtype=torch.float64, device="cuda")
@@ -226,7 +226,9 @@ def test_1d_unaligned_views_and_strides():
                            torch.cuda.current_stream().cuda_stream)
     assert rc == 0, L.dfe_last_error()
     torch.cuda.synchronize()
-    assert torch.equal(out[:, 1:n + 2], u_cont) and float(out[:, 0].abs().max()) == 0.0 and float(out[:, n + 2:].abs().max()) == 0.0
+    # rows on odd 8-byte offsets take the two-pass kernels (different summation order than the pipelined one)
+    assert float((out[:, 1:n + 2] - u_cont).abs().max()) <= 1e-13 * float(u_cont.abs().max())
+    assert float(out[:, 0].abs().max()) == 0.0 and float(out[:, n + 2:].abs().max()) == 0.0
 
 
 def test_1d_full_size_properties():
