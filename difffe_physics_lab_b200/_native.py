@@ -84,6 +84,9 @@ def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
     ] + [str(PKG / "csrc" / s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
+    extra = os.environ.get("DFE_NVCC_FLAGS")      # e.g. -DDFE_PIPE_TRACE_BUILD=1 (debug timeline of the 1-D kernel)
+    if extra:
+        cmd[1:1] = extra.split()
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)

@@ -16,12 +16,15 @@
 //
 // Prefix sums are kept in MOMENT form: a block of nodes contributes (s, m) with m = w - s*X_end, which makes
 // every combine a plain addition: W_i = W^thread_i + sum_before(m) + X_i * sum_before(s).  Scans are therefore
-// two-component add-scans (warp shuffles), chunk folds are plain sums, and X_i (coordinate in half element
-// lengths, from the mesh handle) is a per-node register constant.
+// two-component add-scans (warp shuffles), chunk folds are plain sums; the affine part a + b*X_i is carried along
+// the thread's nodes incrementally (X_i = coordinate in half element lengths, from the mesh handle).
 //
-// A ninth "communication" warp per CTA publishes totals, polls/folds the other chunks' totals (data-as-flag:
-// the exchange buffer is pre-set to an all-ones sentinel, no counters, no fences), and drives the TMA bulk
-// loads/stores; the eight compute warps never touch global memory.
+// Roles inside a CTA: W compute warps (never touch global memory); one fold warp per sweep (publishes the CTA's
+// totals, polls/folds the other chunks' totals — data-as-flag: the exchange buffer is pre-set to an all-ones
+// sentinel, no counters, no fences); one I/O warp (TMA bulk loads and stores).  The roles are coupled only through
+// shared-memory mbarriers (slot full / slot written / totals ready / constants ready): there is no CTA-wide barrier
+// in the main loop, so a role waits exactly for the event it depends on and the fold / I/O latencies stay off the
+// compute warps' critical path.
 #include <cstdint>
 #include <cstdlib>
 
@@ -110,12 +113,24 @@ __device__ __forceinline__ int mis_of(const double* g) {
   return static_cast<int>((reinterpret_cast<uintptr_t>(g) >> 3) & 1);
 }
 
+// x += (value of lane - d), only where that lane exists: the shuffle's own predicate guards the add (3 instructions)
+__device__ __forceinline__ void scan_step(double& x, int d) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b32 lo, hi, olo, ohi;\n\t.reg .f64 o;\n\t"
+      "mov.b64 {lo, hi}, %0;\n\t"
+      "shfl.sync.up.b32 olo|p, lo, %1, 0, 0xffffffff;\n\t"
+      "shfl.sync.up.b32 ohi, hi, %1, 0, 0xffffffff;\n\t"
+      "mov.b64 o, {olo, ohi};\n\t"
+      "@p add.rn.f64 %0, %0, o;\n\t}"
+      : "+d"(x)
+      : "r"(d));
+}
 // two-component inclusive add-scan over the warp; returns the exclusive prefix in (es, em)
 __device__ __forceinline__ void warp_scan2(double& is, double& im, double& es, double& em, int lane) {
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
-    const double os = __shfl_up_sync(0xffffffffu, is, d), om = __shfl_up_sync(0xffffffffu, im, d);
-    if (lane >= d) { is += os; im += om; }
+    scan_step(is, d);
+    scan_step(im, d);
   }
   es = __shfl_up_sync(0xffffffffu, is, 1);
   em = __shfl_up_sync(0xffffffffu, im, 1);
@@ -153,13 +168,56 @@ __device__ __forceinline__ void poll_pair(const unsigned long long* p, unsigned 
   m = __longlong_as_double(static_cast<long long>(b));
 }
 
-// debug timeline: CTAs 0 / 100 / 200, iterations 200..215
+// debug timeline (build with -DDFE_PIPE_TRACE_BUILD=1, run with DFE_PIPE_TRACE=1): CTAs 0 / 100 / 200, iterations 200..215
+#ifndef DFE_PIPE_TRACE_BUILD
+#define DFE_PIPE_TRACE_BUILD 0
+#endif
 __device__ __forceinline__ void tr(const PP& p, int it, int role, int ev) {
+#if DFE_PIPE_TRACE_BUILD
   if (p.trace != nullptr && it >= 200 && it < 216 && (blockIdx.x % 100) == 0 && blockIdx.x < 300)
     p.trace[(((blockIdx.x / 100) * 16 + (it - 200)) * 4 + role) * 8 + ev] = clock64();
+#endif
+}
+
+// ---- bounded waits: a protocol bug must never hang the GPU.  After LIMIT cycles a waiter raises the CTA-wide
+// `dead` flag (and the global error word); every later wait returns at once, the results are garbage and
+// dfe_solve1d reports the error.
+constexpr long long WAIT_LIMIT = 4000000000ll;   // ~2 s at 1.965 GHz
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int* err, int* dead) {
+  const long long t0 = clock64();
+  int spins = 0;
+  while (!mbar_try(bar, parity)) {
+    if ((++spins & 63) == 0) {
+      if (*reinterpret_cast<volatile int*>(dead)) return;
+      if (clock64() - t0 > WAIT_LIMIT) {
+        *reinterpret_cast<volatile int*>(dead) = 1;
+        atomicExch(err, 1);
+        return;
+      }
+    }
+  }
+}
+__device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity, int* err, int* dead) {
+  if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity, err, dead);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // ---- the three per-thread phases.  FULL: every one of the R nodes exists and none is a Dirichlet node (no masks).
+// The coordinate X_j of node j (in half element lengths) is never held per node: a + b*X_j is carried along as
+// t_{j+1} = t_j + b*hs[j+1] (one fma per node, the one the direct evaluation would need as well).
 template <bool BWD, int R, bool FULL>
 __device__ __forceinline__ void phase_a(double* buf, const double (&hs)[R + 1], int nin, int nst, bool ownsL, double& S,
                                         double& Wc) {
@@ -177,10 +235,11 @@ __device__ __forceinline__ void phase_a(double* buf, const double (&hs)[R + 1], 
 
 template <bool BWD, int R, bool FULL>
 __device__ __forceinline__ void phase_b(double* buf, const double* ub, const double (&hs)[R + 1], const double (&rh)[R + 1],
-                                        const double (&X)[R], int nin, int nst, bool ownsL, double c0, double kaph,
-                                        double a0, double b0, double& S1, double& W1, double& D) {
+                                        double X0, int nin, int nst, bool ownsL, double c0, double kaph, double a0,
+                                        double b0, double& S1, double& W1, double& D) {
   double S = 0.0, Wc = 0.0;
   double kp = kdiv(kaph, hs[0], rh[0]);
+  double t = fma(b0, X0, a0);
 #pragma unroll
   for (int j = 0; j < R; ++j) {
     double g = 0.0, Wt;
@@ -193,7 +252,8 @@ __device__ __forceinline__ void phase_b(double* buf, const double* ub, const dou
     } else {
       Wt = (FULL || j < nst) ? buf[j] : 0.0;
     }
-    const double x0 = fma(-c0, Wt, fma(b0, X[j], a0));
+    const double x0 = fma(-c0, Wt, t);
+    t = fma(b0, hs[j + 1], t);
     // k_i = fl(kappa/h_i) bit-exactly (solver.py:88); err = (k_{i-1}+k_i) - fl(k_{i-1}+k_i) is minus the rounding of
     // the reference's diagonal accumulation (solver.py:89-92); it is 0 on Dirichlet and padding rows.
     const double ki = kdiv(kaph, hs[j + 1], rh[j + 1]);
@@ -210,30 +270,49 @@ __device__ __forceinline__ void phase_b(double* buf, const double* ub, const dou
 }
 
 template <bool BWD, int R, bool FULL>
-__device__ __forceinline__ void phase_c(double* buf, const double (&hs)[R + 1], const double (&X)[R], int nst, double a1,
-                                        double b1) {
+__device__ __forceinline__ void phase_c(double* buf, const double (&hs)[R + 1], double X0, int nst, double a1, double b1) {
+  double t = fma(b1, X0, a1);
 #pragma unroll
   for (int j = 0; j < R; ++j) {
     if (FULL || j < nst) {
-      const double xv = buf[j] + fma(b1, X[j], a1);
+      const double xv = buf[j] + t;
       // forward: u[free] = x (solver.py:180-181); backward: dL/df_i = lambda_i (h_{i-1}/2 + h_i/2)
       buf[j] = BWD ? fma(xv, hs[j], xv * hs[j + 1]) : xv;
     }
+    t = fma(b1, hs[j + 1], t);
   }
 }
 
-// One fold warp per sweep ST (0 or 1).  Per iteration it:
-//   * after the compute warps finished the sweep's phase for this iteration (named barrier 1+ST): scan their W
-//     per-warp totals, publish the CTA total of that sample, keep the per-warp exclusive offsets (register queue);
-//   * fold the G chunk totals of the sample the NEXT iteration consumes (published about one iteration ago, its
-//     loads are issued before the barrier wait): boundary constants -> per-warp (A, B) -> shared memory.
-template <bool BWD, int W, int LB, int LC, int ST>
-__device__ __forceinline__ void fold_warp(const PP& p, int lane, int c, int grp, int nIt, int nTot, const double* wt,
-                                          double* cfw, double* sc, int* dead) {
-  constexpr int LAG = ST == 0 ? LB : LB + LC;   // the sample folded in iteration it is it + 1 - LAG
-  constexpr int QD = ST == 0 ? LB : LC;         // offsets queue depth
-  constexpr int QI = ST == 0 ? LB - 1 : LC - 2; // queue index of the folded sample at fold time (see the pushes)
-  constexpr int NB1 = 32 * (W + 1);
+// Shared-memory control block of one CTA.  All synchronisation between the roles goes through these mbarriers
+// (no CTA-wide barrier inside the main loop): a role only ever waits for the event it really depends on.
+template <int W, int NR>
+struct Ctl {
+  uint64_t full[NR];    // TMA load of ring slot k landed                       (tx bytes)     I/O -> compute
+  uint64_t outr[NR];    // phase C finished writing ring slot k                 (W arrivals)   compute -> I/O
+  uint64_t ufull[2];    // backward: u-row slot landed                          (tx bytes)     I/O -> compute
+  uint64_t ufree[2];    // backward: phase B finished reading the u-row slot    (W arrivals)   compute -> I/O
+  uint64_t tot[2][2];   // [sweep][it & 1] per-warp totals of this iteration    (W arrivals)   compute -> fold warp
+  uint64_t cf[2][2];    // [sweep][it & 1] folded constants for iteration `it`  (1 arrival)    fold warp -> compute
+  double wt[2][2][W][2];    // [sweep][it & 1][warp] (s, m) totals
+  double cfw[2][2][W][2];   // [sweep][it & 1][warp] (A, B) constants
+  double red[2][W];         // backward: [it & 1][warp] dot partials of phase B
+  double sc[2][4];          // [it & 1] c0, kappa/2, c1
+  int dead;
+};
+
+// One fold warp per sweep ST (0 or 1).  In iteration `it` it
+//   * waits for the compute warps' totals of this iteration's phase (A for sweep 0, B for sweep 1), scans them,
+//     publishes the CTA total of that sample and keeps the per-warp exclusive offsets (register queue);
+//   * folds the G chunk totals of the sample the NEXT iteration consumes (published about one iteration ago by
+//     every CTA of the group; its loads are issued before the wait): boundary constants -> per-warp (A, B) ->
+//     shared memory, then signals cf[ST][(it + 1) & 1].
+// ST is a run-time value: both fold warps share ONE copy of this code (instruction-cache footprint).
+template <bool BWD, int W, int NR, int LB, int LC>
+__device__ __forceinline__ void fold_warp(const PP& p, Ctl<W, NR>* ctl, int lane, int c, int grp, int nIt, int nTot,
+                                          const int ST) {
+  const int LAG = ST == 0 ? LB : LB + LC;       // the sample folded in iteration it is it + 1 - LAG
+  constexpr int QD = LB > LC ? LB : LC;         // offsets queue depth; the folded sample's entry is qd - 1 deep
+  const int qd = ST == 0 ? LB : LC;
   const int G = p.G, GP = G + 2;
   const bool LR = p.bcL && p.bcR;
   const double rXtot = 1.0 / p.Xtot;
@@ -258,14 +337,14 @@ __device__ __forceinline__ void fold_warp(const PP& p, int lane, int c, int grp,
       if (ends) { uLcur = p.in1[sF * p.ld1]; uRcur = p.in1[sF * p.ld1 + p.nn - 1]; }
     }
   }
-  __syncthreads();   // prologue
+  if (lane == 0) mbar_arrive(&ctl->cf[ST][0]);   // iteration 0 consumes no folded constants
 
   for (int it = 0; it < nTot; ++it) {
     const int par = it & 1, nxt = par ^ 1;
+    const uint32_t ph = (it >> 1) & 1;
     const int f = it + 1 - LAG;
     const bool vf = f >= 0 && f < nIt;
     const unsigned long long* base = p.part + ((sF * 2 + ST) * G) * 2;
-    if (lane == 0) tr(p, it, 1 + ST, 0);
     // ---- loads first: chunk totals of sample f, constants of sample f+1
     unsigned long long ra[3], rb[3];
 #pragma unroll
@@ -283,31 +362,35 @@ __device__ __forceinline__ void fold_warp(const PP& p, int lane, int c, int grp,
       if (ends) { uLnx = p.in1[sN * p.ld1]; uRnx = p.in1[sN * p.ld1 + p.nn - 1]; }
     }
     // ---- totals of this iteration's phase: publish, keep the per-warp exclusive offsets
+    if (lane == 0) tr(p, it, 1 + ST, 0);
+    mbar_wait_b(&ctl->tot[ST][par], ph, p.err, &ctl->dead);
     if (lane == 0) tr(p, it, 1 + ST, 1);
-    named_sync(1 + ST, NB1);
-    if (lane == 0) tr(p, it, 1 + ST, 2);
-    double es, em;
     {
-      double is = (lane < W) ? wt[par * 2 * W + 2 * lane] : 0.0, im = (lane < W) ? wt[par * 2 * W + 2 * lane + 1] : 0.0;
+      double is = (lane < W) ? ctl->wt[ST][par][lane < W ? lane : 0][0] : 0.0;
+      double im = (lane < W) ? ctl->wt[ST][par][lane < W ? lane : 0][1] : 0.0;
 #pragma unroll
       for (int d = 1; d < W; d <<= 1) {
         const double os = __shfl_up_sync(0xffffffffu, is, d), om = __shfl_up_sync(0xffffffffu, im, d);
         if (lane >= d) { is += os; im += om; }
       }
-      es = __shfl_up_sync(0xffffffffu, is, 1);
-      em = __shfl_up_sync(0xffffffffu, im, 1);
+      double es = __shfl_up_sync(0xffffffffu, is, 1);
+      double em = __shfl_up_sync(0xffffffffu, im, 1);
       if (lane == 0) { es = 0.0; em = 0.0; }
       const int jp = ST == 0 ? it : it - LB;
       if (lane == W - 1 && jp >= 0 && jp < nIt) publish(p.part + ((sP * 2 + ST) * G + c) * 2, is, im);
-    }
-    if (ST == 0) {   // sweep 0: the fold below is LB-1 pushes behind, this iteration's push included
 #pragma unroll
       for (int k = QD - 1; k > 0; --k) { qs[k] = qs[k - 1]; qm[k] = qm[k - 1]; }
       qs[0] = es;
       qm[0] = em;
+      if (BWD && ST == 1) {   // dot partial of the sample phase B handled in this iteration
+        double a = (lane < W) ? ctl->red[par][lane < W ? lane : 0] : 0.0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+        if (jp >= 0 && jp < nIt && lane == 0) p.gkpart[sP * GP + c] = a;
+      }
     }
     // ---- fold
-    if (lane == 0) tr(p, it, 1 + ST, 3);
+    if (lane == 0) tr(p, it, 1 + ST, 2);
     if (vf) {
       double Sx = 0.0, Mx = 0.0, St = 0.0, Mt = 0.0;
 #pragma unroll
@@ -315,7 +398,7 @@ __device__ __forceinline__ void fold_warp(const PP& p, int lane, int c, int grp,
         const int ci = lane + 32 * l;
         if (ci < G) {
           double sv, mv;
-          poll_pair(base + 2 * ci, ra[l], rb[l], sv, mv, p.err, dead);
+          poll_pair(base + 2 * ci, ra[l], rb[l], sv, mv, p.err, &ctl->dead);
           St += sv; Mt += mv;
           if (ci < c) { Sx += sv; Mx += mv; }
         }
@@ -324,12 +407,12 @@ __device__ __forceinline__ void fold_warp(const PP& p, int lane, int c, int grp,
         const int ci = lane + l0;
         if (ci < G) {
           double sv, mv;
-          poll_pair(base + 2 * ci, SENT, SENT, sv, mv, p.err, dead);
+          poll_pair(base + 2 * ci, SENT, SENT, sv, mv, p.err, &ctl->dead);
           St += sv; Mt += mv;
           if (ci < c) { Sx += sv; Mx += mv; }
         }
       }
-      if (lane == 0) tr(p, it, 1 + ST, 4);
+      if (lane == 0) tr(p, it, 1 + ST, 3);
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1) {
         Sx += __shfl_xor_sync(0xffffffffu, Sx, d);
@@ -343,49 +426,38 @@ __device__ __forceinline__ void fold_warp(const PP& p, int lane, int c, int grp,
       const double A = gb + (p.bcL ? 0.0 : cc * Wtot) - cc * Mx;
       const double Bc = ga + cc * (C - Sx);
       if (lane < W) {
-        cfw[nxt * 2 * W + 2 * lane] = fma(-cc, qm[QI], A);
-        cfw[nxt * 2 * W + 2 * lane + 1] = fma(-cc, qs[QI], Bc);
+        double qmo = qm[0], qso = qs[0];
+#pragma unroll
+        for (int k = 1; k < QD; ++k)
+          if (k == qd - 1) { qmo = qm[k]; qso = qs[k]; }
+        ctl->cfw[ST][nxt][lane][0] = fma(-cc, qmo, A);
+        ctl->cfw[ST][nxt][lane][1] = fma(-cc, qso, Bc);
       }
       if (lane == 0) {
-        sc[4 * nxt + 2 * ST] = cc;
-        if (ST == 0) sc[4 * nxt + 1] = khcur;
+        ctl->sc[nxt][2 * ST] = cc;
+        if (ST == 0) ctl->sc[nxt][1] = khcur;
         // backward, chunk 0: boundary terms of sum_e q_e (u_{e+1}-u_e) = C (u_R-u_L) - S_tot u_R + sum_i rhs_i u_i
         if (ends) p.gkpart[sF * GP + G + ST] = C * (uRcur - uLcur) - St * uRcur;
       }
     }
-    if (ST == 1) {   // sweep 1: the fold above is LC-2 pushes behind, this iteration's push excluded
-#pragma unroll
-      for (int k = QD - 1; k > 0; --k) { qs[k] = qs[k - 1]; qm[k] = qm[k - 1]; }
-      qs[0] = es;
-      qm[0] = em;
-    }
     ccur = cnx; khcur = khnx; uLcur = uLnx; uRcur = uRnx;
     sF += sstep;
     sP += sstep;
-    if (lane == 0) tr(p, it, 1 + ST, 5);
-    __syncthreads();
-    if (lane == 0) tr(p, it, 1 + ST, 6);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&ctl->cf[ST][nxt]);
+    if (lane == 0) tr(p, it, 1 + ST, 4);
   }
 }
 
-// Warps 0..W-1 compute; warp W / W+1 = fold warps of sweep 0 / 1; warp W+2 = I/O warp (TMA loads and stores,
-// dL/dkappa partials).
+// Warps 0..W-1 compute; warp W / W+1 = fold warps of sweep 0 / 1; warp W+2 = I/O warp (TMA loads and stores).
 template <bool BWD, int R, int W, int LB, int LC>
-__global__ void __launch_bounds__(32 * (W + 3), 2) k1d_pipe(const PP p) {
+__global__ void __launch_bounds__(32 * (W + 3), (W > 8 ? 1 : 2)) k1d_pipe(const PP p) {
   constexpr int NR = LB + LC + 3;           // ring slots of the in-place chain: prefetch, A..C, store drain
-  constexpr int NRU = BWD ? 2 : 0;          // ring slots of the u row (backward, used by phase B only)
-  constexpr int NB1 = 32 * (W + 1);         // threads on the named barriers 1 and 2
-  static_assert(W <= 16 && NR + NRU <= 16 && LB >= 2 && LC >= 2, "layout");
+  constexpr int NRU = 2;                    // ring slots of the u row (backward, used by phase B only)
+  static_assert(W <= 16 && LB >= 1 && LC >= 1, "layout");
+  static_assert(sizeof(Ctl<W, NR>) <= MISC_BYTES, "misc region");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);     // [NR + NRU]
-  double* wt0 = reinterpret_cast<double*>(smem_raw + 128);   // [2][W][2] per-warp totals of sweep 0
-  double* wt1 = wt0 + 4 * W;                                 // [2][W][2] per-warp totals of sweep 1
-  double* red = wt1 + 4 * W;                                 // [2][W]    backward: per-warp dot partials
-  double* cfw0 = red + 2 * W;                                // [2][W][2] per-warp (A, B) of sweep 0 for phase B
-  double* cfw1 = cfw0 + 4 * W;                               // [2][W][2] per-warp (A, B) of sweep 1 for phase C
-  double* sc = cfw1 + 4 * W;                                 // [2][4]    c0, kaph0, c1
-  int* dead = reinterpret_cast<int*>(sc + 8);
-  static_assert(128 + 8 * (18 * W + 8) + 8 <= MISC_BYTES, "misc region");
+  Ctl<W, NR>* ctl = reinterpret_cast<Ctl<W, NR>*>(smem_raw);
   double* ring = reinterpret_cast<double*>(smem_raw + MISC_BYTES);
   double* uring = ring + static_cast<size_t>(NR) * p.slotd;
 
@@ -395,7 +467,7 @@ __global__ void __launch_bounds__(32 * (W + 3), 2) k1d_pipe(const PP p) {
   const int n0 = c * p.chg;
   const int len = min(nn, n0 + p.chg) - n0;
   const int nIt = static_cast<int>((p.B - grp + p.NG - 1) / p.NG);
-  const int nTot = nIt + LB + LC + 1;
+  const int nTot = nIt + LB + LC;
   const bool have_out = (p.out != nullptr);
   const int slotd = p.slotd;
   // 16-byte phase of a row chunk: element j of the chunk lives at slot[mis + j]; mis depends on the sample only
@@ -407,8 +479,13 @@ __global__ void __launch_bounds__(32 * (W + 3), 2) k1d_pipe(const PP p) {
   auto mis1_of = [&](int j) { return mis1c ^ (ld1p & (grpp ^ (j & ngp))); };
 
   if (tid == 0) {
-    for (int k = 0; k < NR + NRU; ++k) mbar_init(bar + k, 1);
-    *dead = 0;
+    for (int k = 0; k < NR; ++k) { mbar_init(&ctl->full[k], 1); mbar_init(&ctl->outr[k], W); }
+    for (int k = 0; k < 2; ++k) {
+      mbar_init(&ctl->ufull[k], 1);
+      mbar_init(&ctl->ufree[k], W);
+      for (int s = 0; s < 2; ++s) { mbar_init(&ctl->tot[s][k], W); mbar_init(&ctl->cf[s][k], 1); }
+    }
+    ctl->dead = 0;
   }
   __syncthreads();
 
@@ -419,9 +496,10 @@ __global__ void __launch_bounds__(32 * (W + 3), 2) k1d_pipe(const PP p) {
     const int nst = max(0, min(R, len - tb));                                  // nodes of the chunk held
     const bool ownsL = p.bcL && c == 0 && tid == 0;
     const bool ownsR = p.bcR && c == G - 1 && tb <= len - 1 && len - 1 < tb + R;
-    const bool full = (nin == R) && (nst == R) && !ownsL && !ownsR;
+    // one variant per WARP (uniform branch): the mask-free code if every lane's R nodes are ordinary free nodes
+    const bool full = __all_sync(0xffffffffu, (nin == R) && (nst == R) && !ownsL && !ownsR);
     // mesh constants of this thread's R nodes: hs[j] / rh[j] = element left of node j (hs[R]: right of the last)
-    double hs[R + 1], rh[R + 1], X[R];
+    double hs[R + 1], rh[R + 1];
 #pragma unroll
     for (int j = 0; j <= R; ++j) {
       const int e = n0 - 1 + tb + j;
@@ -429,26 +507,25 @@ __global__ void __launch_bounds__(32 * (W + 3), 2) k1d_pipe(const PP p) {
       hs[j] = ex ? p.hs[e] : 0.0;
       rh[j] = ex ? p.rh[e] : 0.0;
     }
-#pragma unroll
-    for (int j = 0; j < R; ++j) X[j] = p.X[min(n0 + tb + j, nn - 1)];
+    const double X0 = p.X[min(n0 + tb, nn - 1)];
     const double Xe = p.X[min(n0 + min(tb + R, len), nn - 1)];   // where the block after this thread starts
     double q0s[LB + 1], q0m[LB + 1], q1s[LC + 1], q1m[LC + 1];   // this thread's exclusive prefixes in flight
 #pragma unroll
     for (int k = 0; k <= LB; ++k) q0s[k] = q0m[k] = 0.0;
 #pragma unroll
     for (int k = 0; k <= LC; ++k) q1s[k] = q1m[k] = 0.0;
-    __syncthreads();   // prologue loads of the service warps
 
     int slotA = 0, roundA = 0;   // ring slot of phase A's sample and its use count parity
     for (int it = 0; it < nTot; ++it) {
       const int par = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
       // ---------------------------------------------------------------- phase A (sample it)
       {
         double S = 0.0, Wc = 0.0;
         if (tid == 0) tr(p, it, 0, 0);
         if (it < nIt) {
           double* buf = ring + slotA * slotd + mis0_of(it) + tb;
-          mbar_wait(bar + slotA, roundA);
+          mbar_wait_b(&ctl->full[slotA], roundA, p.err, &ctl->dead);
           if (tid == 0) tr(p, it, 0, 1);
           if (full) phase_a<BWD, R, true>(buf, hs, nin, nst, ownsL, S, Wc);
           else phase_a<BWD, R, false>(buf, hs, nin, nst, ownsL, S, Wc);
@@ -460,12 +537,10 @@ __global__ void __launch_bounds__(32 * (W + 3), 2) k1d_pipe(const PP p) {
         q0s[0] = es;
         q0m[0] = em;
         if (lane == 31) {
-          wt0[par * 2 * W + 2 * warp] = is;
-          wt0[par * 2 * W + 2 * warp + 1] = im;
+          ctl->wt[0][par][warp][0] = is;
+          ctl->wt[0][par][warp][1] = im;
+          mbar_arrive(&ctl->tot[0][par]);
         }
-        __syncwarp();
-        named_arrive(1, NB1);
-        if (tid == 0) tr(p, it, 0, 2);
       }
       // ---------------------------------------------------------------- phase B (sample it-LB)
       {
@@ -473,20 +548,24 @@ __global__ void __launch_bounds__(32 * (W + 3), 2) k1d_pipe(const PP p) {
         int slotB = slotA - LB;
         if (slotB < 0) slotB += NR;
         double S1 = 0.0, W1 = 0.0, D = 0.0;
-        if (jB >= 0 && jB < nIt) {
+        if (tid == 0) tr(p, it, 0, 2);
+        mbar_wait_b(&ctl->cf[0][par], ph, p.err, &ctl->dead);
+        if (tid == 0) tr(p, it, 0, 3);
+        const bool act = jB >= 0 && jB < nIt;
+        if (act) {
           double* buf = ring + slotB * slotd + mis0_of(jB) + tb;
-          const double c0 = sc[4 * par], kaph = sc[4 * par + 1];
-          const double a0 = fma(-c0, q0m[LB], cfw0[par * 2 * W + 2 * warp]);
-          const double b0 = fma(-c0, q0s[LB], cfw0[par * 2 * W + 2 * warp + 1]);
+          const double c0 = ctl->sc[par][0], kaph = ctl->sc[par][1];
+          const double a0 = fma(-c0, q0m[LB], ctl->cfw[0][par][warp][0]);
+          const double b0 = fma(-c0, q0s[LB], ctl->cfw[0][par][warp][1]);
           const double* ub = nullptr;
           if (BWD) {
             const int us = jB & 1;
             ub = uring + us * slotd + mis1_of(jB) + tb;
-            mbar_wait(bar + NR + us, (jB >> 1) & 1);
+            mbar_wait_b(&ctl->ufull[us], (jB >> 1) & 1, p.err, &ctl->dead);
           }
-          if (tid == 0) tr(p, it, 0, 3);
-          if (full) phase_b<BWD, R, true>(buf, ub, hs, rh, X, nin, nst, ownsL, c0, kaph, a0, b0, S1, W1, D);
-          else phase_b<BWD, R, false>(buf, ub, hs, rh, X, nin, nst, ownsL, c0, kaph, a0, b0, S1, W1, D);
+          if (tid == 0) tr(p, it, 0, 4);
+          if (full) phase_b<BWD, R, true>(buf, ub, hs, rh, X0, nin, nst, ownsL, c0, kaph, a0, b0, S1, W1, D);
+          else phase_b<BWD, R, false>(buf, ub, hs, rh, X0, nin, nst, ownsL, c0, kaph, a0, b0, S1, W1, D);
         }
         double is = S1, im = fma(-S1, Xe, W1), es, em;
         warp_scan2(is, im, es, em, lane);
@@ -498,50 +577,51 @@ __global__ void __launch_bounds__(32 * (W + 3), 2) k1d_pipe(const PP p) {
 #pragma unroll
           for (int d = 16; d > 0; d >>= 1) D += __shfl_xor_sync(0xffffffffu, D, d);
         }
-        if (lane == 31) {
-          wt1[par * 2 * W + 2 * warp] = is;
-          wt1[par * 2 * W + 2 * warp + 1] = im;
-          if (BWD) red[par * W + warp] = D;
+        if (lane == 31) {   // (the shuffles above order every lane's shared-memory reads of this phase before this point)
+          ctl->wt[1][par][warp][0] = is;
+          ctl->wt[1][par][warp][1] = im;
+          if (BWD) ctl->red[par][warp] = D;
+          mbar_arrive(&ctl->tot[1][par]);
+          if (BWD && act) mbar_arrive(&ctl->ufree[jB & 1]);
         }
-        __syncwarp();
-        named_arrive(2, NB1);
-        if (tid == 0) tr(p, it, 0, 4);
       }
       // ---------------------------------------------------------------- phase C (sample it-LB-LC)
       {
         const int jC = it - LB - LC;
-        if (jC >= 0 && jC < nIt && have_out) {
+        if (tid == 0) tr(p, it, 0, 5);
+        mbar_wait_b(&ctl->cf[1][par], ph, p.err, &ctl->dead);
+        if (tid == 0) tr(p, it, 0, 6);
+        if (jC >= 0 && jC < nIt) {
           int slotC = slotA - LB - LC;
           if (slotC < 0) slotC += NR;
-          double* buf = ring + slotC * slotd + mis0_of(jC) + tb;
-          const double c1 = sc[4 * par + 2];
-          const double a1 = fma(-c1, q1m[LC], cfw1[par * 2 * W + 2 * warp]);
-          const double b1 = fma(-c1, q1s[LC], cfw1[par * 2 * W + 2 * warp + 1]);
-          if (full) {
-            phase_c<BWD, R, true>(buf, hs, X, nst, a1, b1);
-          } else {
-            phase_c<BWD, R, false>(buf, hs, X, nst, a1, b1);
-            if (ownsL) buf[0] = BWD ? 0.0 : p.gL;                 // u[d] = g (solver.py:177-179); dL/df = 0 there
-            if (ownsR) buf[len - 1 - tb] = BWD ? 0.0 : p.gR;
+          if (have_out) {
+            double* buf = ring + slotC * slotd + mis0_of(jC) + tb;
+            const double c1 = ctl->sc[par][2];
+            const double a1 = fma(-c1, q1m[LC], ctl->cfw[1][par][warp][0]);
+            const double b1 = fma(-c1, q1s[LC], ctl->cfw[1][par][warp][1]);
+            if (full) {
+              phase_c<BWD, R, true>(buf, hs, X0, nst, a1, b1);
+            } else {
+              phase_c<BWD, R, false>(buf, hs, X0, nst, a1, b1);
+              if (ownsL) buf[0] = BWD ? 0.0 : p.gL;                 // u[d] = g (solver.py:177-179); dL/df = 0 there
+              if (ownsR) buf[len - 1 - tb] = BWD ? 0.0 : p.gR;
+            }
+            fence_async_smem();
           }
-          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ctl->outr[slotC]);
         }
       }
       if (++slotA == NR) { slotA = 0; roundA ^= 1; }
-      if (tid == 0) tr(p, it, 0, 5);
-      __syncthreads();
-      if (tid == 0) tr(p, it, 0, 6);
+      if (tid == 0) tr(p, it, 0, 7);
     }
-  } else if (warp == W) {
-    fold_warp<BWD, W, LB, LC, 0>(p, lane, c, grp, nIt, nTot, wt0, cfw0, sc, dead);
-  } else if (warp == W + 1) {
-    fold_warp<BWD, W, LB, LC, 1>(p, lane, c, grp, nIt, nTot, wt1, cfw1, sc, dead);
+  } else if (warp <= W + 1) {
+    fold_warp<BWD, W, NR, LB, LC>(p, ctl, lane, c, grp, nIt, nTot, warp - W);
   } else {
     // ============================================================================ I/O warp
     // Row chunks are loaded as the 16-byte aligned superset [g - mis, g + len rounded up): the element before /
     // after the chunk belongs to the same array (the host checks the base alignment; the very last element of
     // the array is fetched separately), so a load is ONE bulk copy and element j lands at slot[mis + j].
-    const int GP = G + 2;
     const long long last_s = p.B - 1;
     auto load_row = [&](const double* rowbase, long long ld, long long s, double* dst, uint64_t* mb) {
       const double* g = rowbase + s * ld + n0;
@@ -550,35 +630,39 @@ __global__ void __launch_bounds__(32 * (W + 3), 2) k1d_pipe(const PP p) {
       const bool clip = (s == last_s && c == G - 1 && ((mis + len) & 1));   // would read past the end of the array
       if (clip) cnt -= 2;
       if (lane == 0) {
+        if (clip) dst[mis + len - 1] = g[len - 1];   // before the arrive: its release orders this store
         mbar_arrive_expect_tx(mb, 8u * static_cast<uint32_t>(cnt));
         if (cnt) bulk_g2s(dst, g - mis, 8u * cnt, mb);
-        if (clip) dst[mis + len - 1] = g[len - 1];
       }
     };
-    if (nIt > 0) load_row(p.in0, p.ld0, grp, ring, bar);   // prologue: sample 0 (phase A of iteration 0)
-    __syncthreads();
+    for (int j = 0; j < NR && j < nIt; ++j)
+      load_row(p.in0, p.ld0, grp + static_cast<long long>(j) * p.NG, ring + j * slotd, &ctl->full[j]);
+    if (BWD)
+      for (int j = 0; j < NRU && j < nIt; ++j)
+        load_row(p.in1, p.ld1, grp + static_cast<long long>(j) * p.NG, uring + j * slotd, &ctl->ufull[j]);
 
-    for (int it = 0; it < nTot; ++it) {
-      const int nxt = (it + 1) & 1;
+    int slotC = 0, roundC = 0;
+    for (int it = LB; it < nTot; ++it) {
+      // ---- backward: the u-row slot phase B released in this iteration takes the row two samples ahead
       if (lane == 0) tr(p, it, 3, 0);
-      // ---- prefetch: the row of phase A in the next iteration (its slot was stored one iteration ago and that
-      // store's shared-memory reads were awaited before the barrier), the u row of phase B in the next iteration
-      if (it + 1 < nIt) {
-        const int j = it + 1;
-        load_row(p.in0, p.ld0, grp + static_cast<long long>(j) * p.NG, ring + (j % NR) * slotd, bar + (j % NR));
-      }
       if (BWD) {
-        const int f0 = it + 1 - LB;
-        if (f0 >= 0 && f0 < nIt)
-          load_row(p.in1, p.ld1, grp + static_cast<long long>(f0) * p.NG, uring + (f0 & 1) * slotd, bar + NR + (f0 & 1));
+        const int jb = it - LB;
+        if (jb < nIt) {
+          mbar_wait_b(&ctl->ufree[jb & 1], (jb >> 1) & 1, p.err, &ctl->dead);
+          if (jb + NRU < nIt)
+            load_row(p.in1, p.ld1, grp + static_cast<long long>(jb + NRU) * p.NG, uring + (jb & 1) * slotd, &ctl->ufull[jb & 1]);
+        }
       }
-      // ---- store the row phase C finished in the previous iteration
-      {
-        const int js = it - 1 - LB - LC;
-        if (js >= 0 && js < nIt && have_out) {
-          const long long s = grp + static_cast<long long>(js) * p.NG;
+      // ---- store the row phase C finished in this iteration, then refill its slot
+      const int jc = it - LB - LC;
+      if (lane == 0) tr(p, it, 3, 1);
+      if (jc >= 0 && jc < nIt) {
+        mbar_wait_b(&ctl->outr[slotC], roundC, p.err, &ctl->dead);
+        if (lane == 0) tr(p, it, 3, 2);
+        if (have_out) {
+          const long long s = grp + static_cast<long long>(jc) * p.NG;
           double* go = p.out + s * p.ldo + n0;
-          const double* ssrc = ring + (js % NR) * slotd;
+          const double* ssrc = ring + slotC * slotd;
           const Seg qo = make_seg(go, len);
           if (lane == 0) {
             if (qo.body) bulk_s2g(go + qo.head, ssrc + qo.mis + qo.head, 8u * qo.body);
@@ -588,23 +672,14 @@ __global__ void __launch_bounds__(32 * (W + 3), 2) k1d_pipe(const PP p) {
           } else if (lane == 2) {
             if (qo.tail) go[len - 1] = ssrc[qo.mis + len - 1];
           }
+          if (lane == 0) bulk_wait_read0();   // the slot is reloaded right away
+          __syncwarp();
         }
+        if (lane == 0) tr(p, it, 3, 3);
+        if (jc + NR < nIt)
+          load_row(p.in0, p.ld0, grp + static_cast<long long>(jc + NR) * p.NG, ring + slotC * slotd, &ctl->full[slotC]);
+        if (++slotC == NR) { slotC = 0; roundC ^= 1; }
       }
-      // ---- backward: dot partial of the sample phase B handled in the previous iteration
-      if (BWD) {
-        const int jb = it - 1 - LB;
-        double a = (lane < W) ? red[nxt * W + lane] : 0.0;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
-        if (jb >= 0 && jb < nIt && lane == 0) {
-          const long long s = grp + static_cast<long long>(jb) * p.NG;
-          p.gkpart[s * GP + c] = a;
-        }
-      }
-      if (lane == 0) tr(p, it, 3, 1);
-      if (lane == 0) bulk_wait_read0();   // the slot just stored is reloaded next iteration
-      if (lane == 0) tr(p, it, 3, 2);
-      __syncthreads();
     }
     if (lane == 0) bulk_wait_all0();
   }
@@ -681,7 +756,12 @@ int run_cfg(const dfe_mesh* m, PP p, cudaStream_t st, int gbound, int* G_used) {
       if (G > gcap) G = gcap;
       if (G > nn) G = nn;
       if (p.B <= NG) G = gmin;   // tiny batches: nothing to gain from more chunks
+      // whole warps of fully populated threads: only the last chunk of a sample has a ragged tail, so every
+      // other warp runs the mask-free code (a partially filled warp would run the slower masked variant in
+      // EVERY CTA and set the pace of the whole group)
       g.chg = static_cast<int>((nn + G - 1) / G);
+      g.chg = ((g.chg + 32 * R - 1) / (32 * R)) * (32 * R);
+      if (g.chg > CAP) g.chg = CAP;
       g.G = (nn + g.chg - 1) / g.chg;   // drop empty trailing chunks
       g.NG = static_cast<int>(NG);
       g.slotd = ((g.chg + 2) + 1) & ~1;
@@ -785,26 +865,22 @@ int pipe1d_run(const dfe_mesh* m, long long B, bool bwd, const double* in0, long
   }
   if (!bwd) {
     switch (id) {
-      case 1: rc = run_cfg<false, 9, 6, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 2: rc = run_cfg<false, 13, 4, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 3: rc = run_cfg<false, 15, 4, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 4: rc = run_cfg<false, 9, 5, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 5: rc = run_cfg<false, 11, 5, 3, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 6: rc = run_cfg<false, 11, 5, 2, 3>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 7: rc = run_cfg<false, 7, 8, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 8: rc = run_cfg<false, 13, 5, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 1: rc = run_cfg<false, 11, 10, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 2: rc = run_cfg<false, 13, 9, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 3: rc = run_cfg<false, 9, 12, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 4: rc = run_cfg<false, 11, 10, 1, 1>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 5: rc = run_cfg<false, 7, 8, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 6: rc = run_cfg<false, 9, 6, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
       default: rc = run_cfg<false, 11, 5, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
     }
   } else {
     switch (id) {
-      case 1: rc = run_cfg<true, 11, 4, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 2: rc = run_cfg<true, 7, 7, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 3: rc = run_cfg<true, 13, 4, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 4: rc = run_cfg<true, 9, 6, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 5: rc = run_cfg<true, 9, 5, 3, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 6: rc = run_cfg<true, 9, 5, 2, 3>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 7: rc = run_cfg<true, 7, 8, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 8: rc = run_cfg<true, 11, 5, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 1: rc = run_cfg<true, 9, 10, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 2: rc = run_cfg<true, 11, 9, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 3: rc = run_cfg<true, 7, 12, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 4: rc = run_cfg<true, 9, 10, 1, 1>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 5: rc = run_cfg<true, 7, 7, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 6: rc = run_cfg<true, 9, 6, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
       default: rc = run_cfg<true, 9, 5, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
     }
   }
