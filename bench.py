@@ -285,8 +285,8 @@ def run_b200(args):
     dom = max(kern, key=lambda k: kern[k]["ms_per_launch"] * kern[k]["calls"]) if kern else None
     roofline = None
     if dom:
-        knames = {"solve1d_fwd": "dfe_solve1d_fwd = k1d_pass1<0> + k1d_fold<0> + k1d_pass2<0>",
-                  "solve1d_bwd": "dfe_solve1d_bwd = k1d_pass1<1> + k1d_fold<1> + k1d_pass2<1> + k1d_gk_out"}
+        knames = {"solve1d_fwd": "dfe_solve1d_fwd = k1d_pipe<fwd> (+ k1d_pipe_ck, exchange-buffer memset)",
+                  "solve1d_bwd": "dfe_solve1d_bwd = k1d_pipe<bwd> (+ k1d_pipe_ck, k1d_pipe_gk, exchange-buffer memset)"}
         roofline = {"bound": "hbm", "kernel": knames[dom],
                     "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                     "frac": kern[dom]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,

@@ -142,7 +142,8 @@ __device__ __forceinline__ void run_stage(const P1D& p, const Ctx& cx, int st, d
   if (cx.warp == 0) {
     if (cx.lane == 0) {
       const int target = (st + 1) * cx.G;
-      while (ld_relaxed(p.cnt + cx.s) < target) __nanosleep(20);
+      // plain spin: __nanosleep occasionally oversleeps by microseconds on B200 (measured, see dfe_1d_pipe.cu)
+      while (ld_relaxed(p.cnt + cx.s) < target) {}
     }
     __syncwarp();
     Tri carry, total;

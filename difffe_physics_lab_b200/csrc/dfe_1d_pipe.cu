@@ -58,6 +58,8 @@ struct PP {
   unsigned long long* part;   // [B][2][G][2] chunk totals (s, m) as bit patterns, pre-set to SENT
   double* gkpart;             // backward: [B][G+2] partial dL/dkappa (chunks, boundary terms of sweep 0 and 1)
   int* err;                   // set to 1 if a poll timed out (never expected)
+  long long* gt;              // debug (trace build): [CTAs][32][8] globaltimer stamps
+  long long* wstat;           // debug (trace build): [CTAs][12 categories][sum, max] wait cycles
   long long* trace;           // debug (DFE_PIPE_TRACE=1): [3 CTAs][16 iterations][4 roles][8 events] clock64 stamps
 };
 
@@ -91,7 +93,6 @@ __device__ __forceinline__ double poll_word(const unsigned long long* p, unsigne
         v = 0;
         break;
       }
-      __nanosleep(40);
     }
   }
   return __longlong_as_double(static_cast<long long>(v));
@@ -161,7 +162,9 @@ __device__ __forceinline__ void poll_pair(const unsigned long long* p, unsigned 
         a = b = 0;
         break;
       }
-      __nanosleep(32);
+      // no __nanosleep here: measured on B200, a sleeping poller occasionally oversleeps by ~4.5 us, and every such
+      // hiccup stalls the whole group of CTAs two iterations later (1.7x on the config-2 step); the L2 round trip of
+      // the load itself paces the loop
     }
   }
   s = __longlong_as_double(static_cast<long long>(a));
@@ -179,6 +182,39 @@ __device__ __forceinline__ void tr(const PP& p, int it, int role, int ev) {
 #endif
 }
 
+// global timeline (trace build): [CTA][32 iterations from 200][8 events] globaltimer stamps (ns, common to all SMs)
+__device__ __forceinline__ void gts(const PP& p, int it, int ev) {
+#if DFE_PIPE_TRACE_BUILD
+  if (p.gt != nullptr && it >= 200 && it < 232) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    p.gt[(static_cast<long long>(blockIdx.x) * 32 + (it - 200)) * 8 + ev] = static_cast<long long>(t);
+  }
+#endif
+}
+
+// wait accounting (trace build): per CTA and category, total and longest wait in cycles
+struct WStat {
+  long long sum = 0, mx = 0, t0 = 0;
+  __device__ __forceinline__ void begin() {
+#if DFE_PIPE_TRACE_BUILD
+    t0 = clock64();
+#endif
+  }
+  __device__ __forceinline__ void end() {
+#if DFE_PIPE_TRACE_BUILD
+    const long long d = clock64() - t0;
+    sum += d;
+    if (d > mx) mx = d;
+#endif
+  }
+  __device__ __forceinline__ void save(const PP& p, int cat) {
+#if DFE_PIPE_TRACE_BUILD
+    if (p.wstat) { p.wstat[(blockIdx.x * 12 + cat) * 2] = sum; p.wstat[(blockIdx.x * 12 + cat) * 2 + 1] = mx; }
+#endif
+  }
+};
+
 // ---- bounded waits: a protocol bug must never hang the GPU.  After LIMIT cycles a waiter raises the CTA-wide
 // `dead` flag (and the global error word); every later wait returns at once, the results are garbage and
 // dfe_solve1d reports the error.
@@ -188,6 +224,17 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
@@ -209,7 +256,7 @@ __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int*
   }
 }
 __device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity, int* err, int* dead) {
-  if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity, err, dead);
+  if (!mbar_test(bar, parity)) mbar_wait_slow(bar, parity, err, dead);
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -338,6 +385,7 @@ __device__ __forceinline__ void fold_warp(const PP& p, Ctl<W, NR>* ctl, int lane
     }
   }
   if (lane == 0) mbar_arrive(&ctl->cf[ST][0]);   // iteration 0 consumes no folded constants
+  WStat ws_tot, ws_poll;
 
   for (int it = 0; it < nTot; ++it) {
     const int par = it & 1, nxt = par ^ 1;
@@ -363,7 +411,9 @@ __device__ __forceinline__ void fold_warp(const PP& p, Ctl<W, NR>* ctl, int lane
     }
     // ---- totals of this iteration's phase: publish, keep the per-warp exclusive offsets
     if (lane == 0) tr(p, it, 1 + ST, 0);
+    ws_tot.begin();
     mbar_wait_b(&ctl->tot[ST][par], ph, p.err, &ctl->dead);
+    ws_tot.end();
     if (lane == 0) tr(p, it, 1 + ST, 1);
     {
       double is = (lane < W) ? ctl->wt[ST][par][lane < W ? lane : 0][0] : 0.0;
@@ -378,6 +428,7 @@ __device__ __forceinline__ void fold_warp(const PP& p, Ctl<W, NR>* ctl, int lane
       if (lane == 0) { es = 0.0; em = 0.0; }
       const int jp = ST == 0 ? it : it - LB;
       if (lane == W - 1 && jp >= 0 && jp < nIt) publish(p.part + ((sP * 2 + ST) * G + c) * 2, is, im);
+      if (lane == W - 1) gts(p, it, 6 + ST);
 #pragma unroll
       for (int k = QD - 1; k > 0; --k) { qs[k] = qs[k - 1]; qm[k] = qm[k - 1]; }
       qs[0] = es;
@@ -392,6 +443,7 @@ __device__ __forceinline__ void fold_warp(const PP& p, Ctl<W, NR>* ctl, int lane
     // ---- fold
     if (lane == 0) tr(p, it, 1 + ST, 2);
     if (vf) {
+      ws_poll.begin();
       double Sx = 0.0, Mx = 0.0, St = 0.0, Mt = 0.0;
 #pragma unroll
       for (int l = 0; l < 3; ++l) {
@@ -420,6 +472,7 @@ __device__ __forceinline__ void fold_warp(const PP& p, Ctl<W, NR>* ctl, int lane
         St += __shfl_xor_sync(0xffffffffu, St, d);
         Mt += __shfl_xor_sync(0xffffffffu, Mt, d);
       }
+      ws_poll.end();
       const double cc = ccur;
       const double Wtot = fma(St, p.Xtot, Mt);                   // sum_e h_e/2 S_e over the whole sample
       const double C = LR ? Wtot * rXtot : (p.bcL ? St : 0.0);    // flux constant fixed by the boundary conditions
@@ -447,11 +500,12 @@ __device__ __forceinline__ void fold_warp(const PP& p, Ctl<W, NR>* ctl, int lane
     if (lane == 0) mbar_arrive(&ctl->cf[ST][nxt]);
     if (lane == 0) tr(p, it, 1 + ST, 4);
   }
+  if (lane == 0) { ws_tot.save(p, 4 + ST); ws_poll.save(p, 6 + ST); }
 }
 
 // Warps 0..W-1 compute; warp W / W+1 = fold warps of sweep 0 / 1; warp W+2 = I/O warp (TMA loads and stores).
 template <bool BWD, int R, int W, int LB, int LC>
-__global__ void __launch_bounds__(32 * (W + 3), (W > 8 ? 1 : 2)) k1d_pipe(const PP p) {
+__global__ void __launch_bounds__(32 * (W + 3), (W >= 8 ? 1 : 2)) k1d_pipe(const PP p) {
   constexpr int NR = LB + LC + 3;           // ring slots of the in-place chain: prefetch, A..C, store drain
   constexpr int NRU = 2;                    // ring slots of the u row (backward, used by phase B only)
   static_assert(W <= 16 && LB >= 1 && LC >= 1, "layout");
@@ -516,6 +570,7 @@ __global__ void __launch_bounds__(32 * (W + 3), (W > 8 ? 1 : 2)) k1d_pipe(const 
     for (int k = 0; k <= LC; ++k) q1s[k] = q1m[k] = 0.0;
 
     int slotA = 0, roundA = 0;   // ring slot of phase A's sample and its use count parity
+    WStat ws_full, ws_cf0, ws_uf, ws_cf1;
     for (int it = 0; it < nTot; ++it) {
       const int par = it & 1;
       const uint32_t ph = (it >> 1) & 1;
@@ -523,9 +578,12 @@ __global__ void __launch_bounds__(32 * (W + 3), (W > 8 ? 1 : 2)) k1d_pipe(const 
       {
         double S = 0.0, Wc = 0.0;
         if (tid == 0) tr(p, it, 0, 0);
+        if (tid == 0) gts(p, it, 0);
         if (it < nIt) {
           double* buf = ring + slotA * slotd + mis0_of(it) + tb;
+          ws_full.begin();
           mbar_wait_b(&ctl->full[slotA], roundA, p.err, &ctl->dead);
+          ws_full.end();
           if (tid == 0) tr(p, it, 0, 1);
           if (full) phase_a<BWD, R, true>(buf, hs, nin, nst, ownsL, S, Wc);
           else phase_a<BWD, R, false>(buf, hs, nin, nst, ownsL, S, Wc);
@@ -549,7 +607,11 @@ __global__ void __launch_bounds__(32 * (W + 3), (W > 8 ? 1 : 2)) k1d_pipe(const 
         if (slotB < 0) slotB += NR;
         double S1 = 0.0, W1 = 0.0, D = 0.0;
         if (tid == 0) tr(p, it, 0, 2);
+        if (tid == 0) gts(p, it, 1);
+        ws_cf0.begin();
         mbar_wait_b(&ctl->cf[0][par], ph, p.err, &ctl->dead);
+        ws_cf0.end();
+        if (tid == 0) gts(p, it, 2);
         if (tid == 0) tr(p, it, 0, 3);
         const bool act = jB >= 0 && jB < nIt;
         if (act) {
@@ -561,7 +623,9 @@ __global__ void __launch_bounds__(32 * (W + 3), (W > 8 ? 1 : 2)) k1d_pipe(const 
           if (BWD) {
             const int us = jB & 1;
             ub = uring + us * slotd + mis1_of(jB) + tb;
+            ws_uf.begin();
             mbar_wait_b(&ctl->ufull[us], (jB >> 1) & 1, p.err, &ctl->dead);
+            ws_uf.end();
           }
           if (tid == 0) tr(p, it, 0, 4);
           if (full) phase_b<BWD, R, true>(buf, ub, hs, rh, X0, nin, nst, ownsL, c0, kaph, a0, b0, S1, W1, D);
@@ -589,7 +653,11 @@ __global__ void __launch_bounds__(32 * (W + 3), (W > 8 ? 1 : 2)) k1d_pipe(const 
       {
         const int jC = it - LB - LC;
         if (tid == 0) tr(p, it, 0, 5);
+        if (tid == 0) gts(p, it, 3);
+        ws_cf1.begin();
         mbar_wait_b(&ctl->cf[1][par], ph, p.err, &ctl->dead);
+        ws_cf1.end();
+        if (tid == 0) gts(p, it, 4);
         if (tid == 0) tr(p, it, 0, 6);
         if (jC >= 0 && jC < nIt) {
           int slotC = slotA - LB - LC;
@@ -614,7 +682,9 @@ __global__ void __launch_bounds__(32 * (W + 3), (W > 8 ? 1 : 2)) k1d_pipe(const 
       }
       if (++slotA == NR) { slotA = 0; roundA ^= 1; }
       if (tid == 0) tr(p, it, 0, 7);
+      if (tid == 0) gts(p, it, 5);
     }
+    if (tid == 0) { ws_full.save(p, 0); ws_cf0.save(p, 1); ws_uf.save(p, 2); ws_cf1.save(p, 3); }
   } else if (warp <= W + 1) {
     fold_warp<BWD, W, NR, LB, LC>(p, ctl, lane, c, grp, nIt, nTot, warp - W);
   } else {
@@ -642,13 +712,16 @@ __global__ void __launch_bounds__(32 * (W + 3), (W > 8 ? 1 : 2)) k1d_pipe(const 
         load_row(p.in1, p.ld1, grp + static_cast<long long>(j) * p.NG, uring + j * slotd, &ctl->ufull[j]);
 
     int slotC = 0, roundC = 0;
+    WStat ws_out, ws_rd, ws_ufree;
     for (int it = LB; it < nTot; ++it) {
       // ---- backward: the u-row slot phase B released in this iteration takes the row two samples ahead
       if (lane == 0) tr(p, it, 3, 0);
       if (BWD) {
         const int jb = it - LB;
         if (jb < nIt) {
+          ws_ufree.begin();
           mbar_wait_b(&ctl->ufree[jb & 1], (jb >> 1) & 1, p.err, &ctl->dead);
+          ws_ufree.end();
           if (jb + NRU < nIt)
             load_row(p.in1, p.ld1, grp + static_cast<long long>(jb + NRU) * p.NG, uring + (jb & 1) * slotd, &ctl->ufull[jb & 1]);
         }
@@ -657,7 +730,9 @@ __global__ void __launch_bounds__(32 * (W + 3), (W > 8 ? 1 : 2)) k1d_pipe(const 
       const int jc = it - LB - LC;
       if (lane == 0) tr(p, it, 3, 1);
       if (jc >= 0 && jc < nIt) {
+        ws_out.begin();
         mbar_wait_b(&ctl->outr[slotC], roundC, p.err, &ctl->dead);
+        ws_out.end();
         if (lane == 0) tr(p, it, 3, 2);
         if (have_out) {
           const long long s = grp + static_cast<long long>(jc) * p.NG;
@@ -672,8 +747,10 @@ __global__ void __launch_bounds__(32 * (W + 3), (W > 8 ? 1 : 2)) k1d_pipe(const 
           } else if (lane == 2) {
             if (qo.tail) go[len - 1] = ssrc[qo.mis + len - 1];
           }
+          ws_rd.begin();
           if (lane == 0) bulk_wait_read0();   // the slot is reloaded right away
           __syncwarp();
+          ws_rd.end();
         }
         if (lane == 0) tr(p, it, 3, 3);
         if (jc + NR < nIt)
@@ -682,6 +759,7 @@ __global__ void __launch_bounds__(32 * (W + 3), (W > 8 ? 1 : 2)) k1d_pipe(const 
       }
     }
     if (lane == 0) bulk_wait_all0();
+    if (lane == 0) { ws_out.save(p, 8); ws_rd.save(p, 9); ws_ufree.save(p, 10); }
   }
 }
 
@@ -862,26 +940,30 @@ int pipe1d_run(const dfe_mesh* m, long long B, bool bwd, const double* in0, long
   if (want_trace) {
     DFE_CUDA_OK(cudaMalloc(&p.trace, trace_n * sizeof(long long)));
     DFE_CUDA_OK(cudaMemsetAsync(p.trace, 0, trace_n * sizeof(long long), st));
+    DFE_CUDA_OK(cudaMalloc(&p.gt, 512 * 256 * sizeof(long long)));
+    DFE_CUDA_OK(cudaMemsetAsync(p.gt, 0, 512 * 256 * sizeof(long long), st));
+    DFE_CUDA_OK(cudaMalloc(&p.wstat, 512 * 24 * sizeof(long long)));
+    DFE_CUDA_OK(cudaMemsetAsync(p.wstat, 0, 512 * 24 * sizeof(long long), st));
   }
+  // <BWD, R nodes per thread, W compute warps, LB, LC>.  Default: one large CTA per SM (10 compute warps share the
+  // instruction stream and one set of service warps); DFE_PIPE_CFG selects the alternatives kept for tuning.
   if (!bwd) {
     switch (id) {
-      case 1: rc = run_cfg<false, 11, 10, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 2: rc = run_cfg<false, 13, 9, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 3: rc = run_cfg<false, 9, 12, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 4: rc = run_cfg<false, 11, 10, 1, 1>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 5: rc = run_cfg<false, 7, 8, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 6: rc = run_cfg<false, 9, 6, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      default: rc = run_cfg<false, 11, 5, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 1: rc = run_cfg<false, 9, 12, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 2: rc = run_cfg<false, 7, 16, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 3: rc = run_cfg<false, 13, 8, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 4: rc = run_cfg<false, 11, 8, 3, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 5: rc = run_cfg<false, 11, 5, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      default: rc = run_cfg<false, 11, 10, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
     }
   } else {
     switch (id) {
-      case 1: rc = run_cfg<true, 9, 10, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 2: rc = run_cfg<true, 11, 9, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 3: rc = run_cfg<true, 7, 12, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 4: rc = run_cfg<true, 9, 10, 1, 1>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 5: rc = run_cfg<true, 7, 7, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 6: rc = run_cfg<true, 9, 6, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      default: rc = run_cfg<true, 9, 5, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 1: rc = run_cfg<true, 9, 11, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 2: rc = run_cfg<true, 7, 14, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 3: rc = run_cfg<true, 11, 8, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 4: rc = run_cfg<true, 9, 8, 3, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 5: rc = run_cfg<true, 9, 5, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      default: rc = run_cfg<true, 9, 10, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
     }
   }
   if (rc != DFE_OK) return rc;
@@ -890,6 +972,27 @@ int pipe1d_run(const dfe_mesh* m, long long B, bool bwd, const double* in0, long
     DFE_CUDA_OK(cudaStreamSynchronize(st));
     DFE_CUDA_OK(cudaMemcpy(h.data(), p.trace, trace_n * sizeof(long long), cudaMemcpyDeviceToHost));
     cudaFree(p.trace);
+    {
+      std::vector<long long> hw(512 * 24);
+      DFE_CUDA_OK(cudaMemcpy(hw.data(), p.wstat, hw.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+      cudaFree(p.wstat);
+      {
+        std::vector<long long> hg(512 * 256);
+        DFE_CUDA_OK(cudaMemcpy(hg.data(), p.gt, hg.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        cudaFree(p.gt);
+        FILE* fg = fopen(bwd ? "gpurun_out/gt_bwd.bin" : "gpurun_out/gt_fwd.bin", "wb");
+        if (fg) { fwrite(hg.data(), sizeof(long long), hg.size(), fg); fclose(fg); }
+      }
+      FILE* fw = fopen(bwd ? "gpurun_out/wstat_bwd.txt" : "gpurun_out/wstat_fwd.txt", "w");
+      if (fw) {
+        for (int b = 0; b < 512; ++b) {
+          fprintf(fw, "%d", b);
+          for (int k = 0; k < 24; ++k) fprintf(fw, " %lld", hw[b * 24 + k]);
+          fprintf(fw, "\n");
+        }
+        fclose(fw);
+      }
+    }
     FILE* fo = fopen(bwd ? "gpurun_out/trace_bwd.txt" : "gpurun_out/trace_fwd.txt", "w");
     if (fo) {
       for (size_t i = 0; i < trace_n; i += 8) {
