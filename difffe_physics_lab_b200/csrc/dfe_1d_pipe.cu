@@ -949,21 +949,21 @@ int pipe1d_run(const dfe_mesh* m, long long B, bool bwd, const double* in0, long
   // instruction stream and one set of service warps); DFE_PIPE_CFG selects the alternatives kept for tuning.
   if (!bwd) {
     switch (id) {
-      case 1: rc = run_cfg<false, 9, 12, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 1: rc = run_cfg<false, 11, 10, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
       case 2: rc = run_cfg<false, 7, 16, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
       case 3: rc = run_cfg<false, 13, 8, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
       case 4: rc = run_cfg<false, 11, 8, 3, 2>(m, p, st, static_cast<int>(gmax), &G); break;
       case 5: rc = run_cfg<false, 11, 5, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      default: rc = run_cfg<false, 11, 10, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      default: rc = run_cfg<false, 9, 12, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
     }
   } else {
     switch (id) {
       case 1: rc = run_cfg<true, 9, 11, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
       case 2: rc = run_cfg<true, 7, 14, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 3: rc = run_cfg<true, 11, 8, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 3: rc = run_cfg<true, 9, 10, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
       case 4: rc = run_cfg<true, 9, 8, 3, 2>(m, p, st, static_cast<int>(gmax), &G); break;
       case 5: rc = run_cfg<true, 9, 5, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      default: rc = run_cfg<true, 9, 10, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      default: rc = run_cfg<true, 11, 8, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
     }
   }
   if (rc != DFE_OK) return rc;
