@@ -34,7 +34,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
   __syncthreads();
 }
 
-constexpr int PT = 256;  // threads per CTA
+constexpr int PT = 768;  // threads per CTA: one CTA per SM (148 arrivals per grid barrier instead of 444)
 constexpr int PW = PT / 32;
 
 struct PcgArgs {
@@ -77,7 +77,7 @@ __device__ __forceinline__ double grid_sum(unsigned int* bar, unsigned int& epoc
   return a;
 }
 
-__global__ void __launch_bounds__(PT, 4) k_pcg(const PcgArgs A) {
+__global__ void __launch_bounds__(PT, 1) k_pcg(const PcgArgs A) {
   unsigned int epoch = 0;
   __shared__ double sh[3][PW];
   const int lane = threadIdx.x & 31;
@@ -121,24 +121,39 @@ __global__ void __launch_bounds__(PT, 4) k_pcg(const PcgArgs A) {
       // ---- phase A
       double pq = 0.0;
       for (int s = gw; s < A.n_slices; s += 2 * nwarps) {
-        // two slices per trip: their column / value / gather loads are independent and overlap
+        // two slices per trip, four columns of each per batch: all column / value loads of a batch are issued
+        // before the first dependent gather, so ~16 gathers per thread are in flight (the kernel is bound by
+        // memory latency, not bandwidth: ncu long_scoreboard 73 % with one column at a time)
         const int s2 = s + nwarps;
         const bool has2 = s2 < A.n_slices;
         const int i = 32 * s + lane, i2 = 32 * s2 + lane;
         const int beg = A.slice_ptr[s], end = A.slice_ptr[s + 1];
         const int beg2 = has2 ? A.slice_ptr[s2] : 0, end2 = has2 ? A.slice_ptr[s2 + 1] : 0;
+        const int wd = (end - beg) >> 5, wd2 = (end2 - beg2) >> 5;
+        const int wmax = wd > wd2 ? wd : wd2;
         double sum = 0.0, sum2 = 0.0;
-        int k = beg + lane, k2 = beg2 + lane;
-        while (k < end || k2 < end2) {
-          if (k < end) {
-            const int j = A.col[k];
-            sum = fma(A.val[k], fma(beta, pold[j], A.z[j]), sum);
-            k += 32;
+        for (int w0 = 0; w0 < wmax; w0 += 4) {
+          int j[4], j2[4];
+          double v[4], v2[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const bool on = w0 + u < wd, on2 = w0 + u < wd2;
+            const int k = beg + ((w0 + u) << 5) + lane, k2 = beg2 + ((w0 + u) << 5) + lane;
+            j[u] = on ? A.col[k] : -1;
+            v[u] = on ? A.val[k] : 0.0;
+            j2[u] = on2 ? A.col[k2] : -1;
+            v2[u] = on2 ? A.val[k2] : 0.0;
           }
-          if (k2 < end2) {
-            const int j = A.col[k2];
-            sum2 = fma(A.val[k2], fma(beta, pold[j], A.z[j]), sum2);
-            k2 += 32;
+          double g[4], g2[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            g[u] = j[u] >= 0 ? fma(beta, pold[j[u]], A.z[j[u]]) : 0.0;
+            g2[u] = j2[u] >= 0 ? fma(beta, pold[j2[u]], A.z[j2[u]]) : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {   // same accumulation order as a column-by-column loop
+            if (j[u] >= 0) sum = fma(v[u], g[u], sum);
+            if (j2[u] >= 0) sum2 = fma(v2[u], g2[u], sum2);
           }
         }
         if (i < A.n) {
@@ -162,16 +177,29 @@ __global__ void __launch_bounds__(PT, 4) k_pcg(const PcgArgs A) {
       const double alpha = rz / pq;
       // ---- phase B
       double rz_new = 0.0, rr = 0.0;
-      for (int s = gw; s < A.n_slices; s += nwarps) {
-        const int i = 32 * s + lane;
-        if (i < A.n) {
-          A.x[i] = fma(alpha, pnew[i], A.x[i]);
-          const double ri = fma(-alpha, A.q[i], A.r[i]);
-          const double zi = A.dinv[i] * ri;
+      for (int s = gw; s < A.n_slices; s += 2 * nwarps) {   // two slices per trip: ten independent loads in flight
+        const int i = 32 * s + lane, i2 = i + 32 * nwarps;
+        const bool on = i < A.n, on2 = (s + nwarps < A.n_slices) && i2 < A.n;
+        double xi = 0, pi = 0, qi = 0, ri = 0, di = 0, xi2 = 0, pi2 = 0, qi2 = 0, ri2 = 0, di2 = 0;
+        if (on) { xi = A.x[i]; pi = pnew[i]; qi = A.q[i]; ri = A.r[i]; di = A.dinv[i]; }
+        if (on2) { xi2 = A.x[i2]; pi2 = pnew[i2]; qi2 = A.q[i2]; ri2 = A.r[i2]; di2 = A.dinv[i2]; }
+        if (on) {
+          A.x[i] = fma(alpha, pi, xi);
+          ri = fma(-alpha, qi, ri);
+          const double zi = di * ri;
           A.r[i] = ri;
           A.z[i] = zi;
           rz_new = fma(ri, zi, rz_new);
           rr = fma(ri, ri, rr);
+        }
+        if (on2) {
+          A.x[i2] = fma(alpha, pi2, xi2);
+          ri2 = fma(-alpha, qi2, ri2);
+          const double zi2 = di2 * ri2;
+          A.r[i2] = ri2;
+          A.z[i2] = zi2;
+          rz_new = fma(ri2, zi2, rz_new);
+          rr = fma(ri2, ri2, rr);
         }
       }
       // two independent reductions share one grid barrier
