@@ -479,6 +479,11 @@ int common_checks(const dfe_mesh* m, long long B, const void* a, const void* kap
     dfe::set_error("%s: mesh is not a 1-D chain with Dirichlet nodes at its ends; use the general path", who);
     return DFE_ERR_UNSUPPORTED;
   }
+  if (m->h_fault && *reinterpret_cast<volatile int*>(m->h_fault)) {
+    dfe::set_error("%s: an earlier fused 1-D launch on this mesh handle exceeded its wait bound (results of that call are "
+                   "invalid); destroy the handle", who);
+    return DFE_ERR_CUDA;
+  }
   DFE_REQUIRE(kappa_mode >= DFE_KAPPA_SCALAR && kappa_mode <= DFE_KAPPA_PER_SAMPLE_ELEMENT, "%s: bad kappa_mode %d", who,
               kappa_mode);
   size_t need = pl.total > dfe::split1d_workspace_bytes(m, B) ? pl.total : dfe::split1d_workspace_bytes(m, B);

@@ -57,7 +57,7 @@ struct PP {
   double gL, gR, Xtot;
   unsigned long long* part;   // [B][2][G][2] chunk totals (s, m) as bit patterns, pre-set to SENT
   double* gkpart;             // backward: [B][G+2] partial dL/dkappa (chunks, boundary terms of sweep 0 and 1)
-  int* err;                   // set to 1 if a poll timed out (never expected)
+  int* err;                   // mesh handle's fault word (mapped host memory): set to 1 if a wait exceeded its bound
   long long* gt;              // debug (trace build): [CTAs][32][8] globaltimer stamps
   long long* wstat;           // debug (trace build): [CTAs][12 categories][sum, max] wait cycles
   long long* trace;           // debug (DFE_PIPE_TRACE=1): [3 CTAs][16 iterations][4 roles][8 events] clock64 stamps
@@ -89,7 +89,7 @@ __device__ __forceinline__ double poll_word(const unsigned long long* p, unsigne
       if (*reinterpret_cast<volatile int*>(dead)) { v = 0; break; }
       if (++spins > (1 << 22)) {
         *reinterpret_cast<volatile int*>(dead) = 1;
-        atomicExch(err, 1);
+        *reinterpret_cast<volatile int*>(err) = 1;
         v = 0;
         break;
       }
@@ -158,7 +158,7 @@ __device__ __forceinline__ void poll_pair(const unsigned long long* p, unsigned 
       if (*reinterpret_cast<volatile int*>(dead)) { a = b = 0; break; }
       if (++spins > (1 << 22)) {
         *reinterpret_cast<volatile int*>(dead) = 1;
-        atomicExch(err, 1);
+        *reinterpret_cast<volatile int*>(err) = 1;
         a = b = 0;
         break;
       }
@@ -249,7 +249,7 @@ __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int*
       if (*reinterpret_cast<volatile int*>(dead)) return;
       if (clock64() - t0 > WAIT_LIMIT) {
         *reinterpret_cast<volatile int*>(dead) = 1;
-        atomicExch(err, 1);
+        *reinterpret_cast<volatile int*>(err) = 1;
         return;
       }
     }
@@ -861,7 +861,6 @@ int run_cfg(const dfe_mesh* m, PP p, cudaStream_t st, int gbound, int* G_used) {
   *G_used = g.G;
   // exchange buffer [B][2][G][2] <- "not yet published"
   DFE_CUDA_OK(cudaMemsetAsync(p.part, 0xFF, static_cast<size_t>(p.B) * 2 * g.G * 2 * sizeof(double), st));
-  DFE_CUDA_OK(cudaMemsetAsync(p.err, 0, sizeof(int), st));
   {
     const long long nk = p.per_sample ? p.B : 1;
     k1d_pipe_ck<<<static_cast<unsigned>((nk + 255) / 256), 256, 0, st>>>(p.kappa, nk, const_cast<double*>(p.ck));
@@ -932,7 +931,7 @@ int pipe1d_run(const dfe_mesh* m, long long B, bool bwd, const double* in0, long
   p.part = reinterpret_cast<unsigned long long*>(w);
   p.gkpart = reinterpret_cast<double*>(w + part_bytes);
   p.ck = reinterpret_cast<double*>(w + part_bytes + static_cast<size_t>(B) * (gmax + 2) * sizeof(double));
-  p.err = reinterpret_cast<int*>(w + part_bytes + static_cast<size_t>(B) * (gmax + 2 + 2) * sizeof(double));
+  p.err = m->d_fault;   // sticky, host-visible (checked at the next dfe_solve1d_* call on this handle)
   int rc, G = 0;
   const int id = cfg_id();
   static const bool want_trace = getenv("DFE_PIPE_TRACE") != nullptr;

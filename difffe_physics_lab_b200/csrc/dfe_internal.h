@@ -74,6 +74,10 @@ struct dfe_mesh {
   const double* d_rh = nullptr;  // chain: correctly rounded 1/(h_e/2), device, n_el
   const double* d_X = nullptr;   // chain: X_i = sum_{e<i} h_e/2, device, n_nodes
   double x_total = 0.0;          // chain: X_{n_nodes-1}
+  // sticky fault word of the fused 1-D kernels (pinned, device-mapped): a wait that exceeds its bound sets it to 1,
+  // every later dfe_solve1d_* call on this handle fails with DFE_ERR_CUDA
+  int* h_fault = nullptr;
+  int* d_fault = nullptr;
   // ---- device
   dfe::MeshDev dev{};
   std::vector<void*> allocs;  // every cudaMalloc owned by the handle

@@ -58,6 +58,7 @@ extern "C" void dfe_mesh_destroy(dfe_mesh* m) {
     cudaGetDevice(&cur);
     cudaSetDevice(m->info.device);
     for (void* p : m->allocs) cudaFree(p);
+    if (m->h_fault) cudaFreeHost(m->h_fault);
     if (cur >= 0) cudaSetDevice(cur);
   }
   delete m;
@@ -317,6 +318,20 @@ extern "C" int dfe_mesh_create(int dim, int64_t n_nodes, int64_t n_el, const dou
         if (i < ne) acc += static_cast<long double>(hsv[i]);
       }
       if (rc == DFE_OK) rc = upload(m, xv, &m->d_X);
+      if (rc == DFE_OK) {
+        void* hf = nullptr;
+        void* df = nullptr;
+        if (cudaHostAlloc(&hf, 64, cudaHostAllocMapped) == cudaSuccess && cudaHostGetDevicePointer(&df, hf, 0) == cudaSuccess) {
+          m->h_fault = static_cast<int*>(hf);
+          m->d_fault = static_cast<int*>(df);
+          *m->h_fault = 0;
+        } else {
+          cudaGetLastError();
+          if (hf) cudaFreeHost(hf);
+          set_error("dfe_mesh_create: cannot allocate the mapped fault word");
+          rc = DFE_ERR_CUDA;
+        }
+      }
       m->x_total = xv[n - 1];
     }
     cudaDeviceProp prop;
