@@ -76,6 +76,20 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_traffic(prefix):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernel whose name starts with
+    `prefix`, from the latest `ncu --set full` capture summarised under profiles/ (tools/make_profiles.py)."""
+    best = None
+    for fp in sorted((ROOT / "profiles").glob("r*_traffic.json")):
+        try:
+            for k, v in json.loads(fp.read_text()).items():
+                if prefix in k.replace(" ", ""):
+                    best = float(v)
+        except Exception:
+            pass
+    return best
+
+
 # ------------------------------------------------------------------------------- CPU baseline (oracle port)
 def cpu_port_rate(n_elements, seconds_target, steps=1, warmup=0, seed=0):
     """Time oracle/fem_port.c (fwd + adjoint, all host threads) on a bounded sample of the workload.
@@ -289,7 +303,11 @@ def run_b200(args):
                   "solve1d_bwd": "dfe_solve1d_bwd = k1d_pipe<bwd> (+ k1d_pipe_ck, k1d_pipe_gk, exchange-buffer memset)"}
         roofline = {"bound": "hbm", "kernel": knames[dom],
                     "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": kern[dom]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": kern[dom]["achieved_gbs"] / peak,
+                    "traffic": (measured_traffic("k1d_pipe<0" if dom == "solve1d_fwd" else "k1d_pipe<1")
+                                if args.workload == "c2" and not args.batch and not args.n_elements else None),
+                    "traffic_source": "profiles/r*_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel on this workload",
+                    "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": kern[dom]["algorithmic_bytes"],
                     "ms_per_launch": kern[dom]["ms_per_launch"], "kernels": kern,
                     "step_frac_of_peak": (40 * nn * B) / (ms_step * 1e-3) / 1e9 / peak}
@@ -445,7 +463,8 @@ def run_b200_2d(args, w, rank, local_rank, world, dev):
         ms_launch = ms_pcg / calls
         alg = bytes_iter * iters_step / 2.0                     # per PCG launch (forward and adjoint solves average)
         roofline = {"bound": "hbm", "kernel": "k_pcg (cooperative Jacobi-PCG)", "achieved": alg / (ms_launch * 1e-3) / 1e9,
-                    "peak": peak, "unit": "GB/s", "frac": alg / (ms_launch * 1e-3) / 1e9 / peak, "traffic": None,
+                    "peak": peak, "unit": "GB/s", "frac": alg / (ms_launch * 1e-3) / 1e9 / peak,
+                    "traffic": measured_traffic("k_pcg") if args.workload == "c4" and not args.n_elements else None,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "ms_per_launch": ms_launch,
                     "bytes_per_iteration": bytes_iter, "iterations": its, "us_per_iteration": 1e3 * ms_pcg / calls / (iters_step / 2.0),
                     "kernels": {k: {"calls": c, "ms_per_launch": m / c} for k, (c, m) in ksum.items()}}

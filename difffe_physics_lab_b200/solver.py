@@ -37,8 +37,8 @@ class KernelTimer:
     ``launches`` counts the kernels of libdfe_b200 launched while active."""
 
     _active: Optional["KernelTimer"] = None
-    # kernels of libdfe_b200 launched per ABI call (default split 1-D path: pass1 + fold + pass2 [+ gk_out])
-    KERNELS_PER_CALL = {"solve1d_fwd": 3, "solve1d_bwd": 4, "assemble": 1, "eliminate": 2, "pcg": 1, "scatter": 1,
+    # kernels of libdfe_b200 launched per ABI call (default pipelined 1-D path: k1d_pipe_ck + k1d_pipe [+ k1d_pipe_gk])
+    KERNELS_PER_CALL = {"solve1d_fwd": 2, "solve1d_bwd": 3, "assemble": 1, "eliminate": 2, "pcg": 1, "scatter": 1,
                         "gather": 1, "grad": 3}
 
     def __init__(self):
