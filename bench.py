@@ -47,6 +47,8 @@ WORKLOADS = {
     # 2-D configs (one mesh per GPU; N > 1 = replicas only).  Not the default bench line.
     "c3": dict(nx=128, kappa="scalar", scaling="weak",
                desc="2D unit-square P1 triangles 128x128 (16641 nodes), f=1, kappa=1, fwd+adjoint"),
+    "c5b": dict(nx=32, batch=65536, kappa="shared", scaling="strong", small=True,
+                desc="kappa inverse-problem sweep: 65536 2D solves on rectangle(32,32) (961 DOF), shared kappa, NCCL grad allreduce"),
     "c4": dict(nx=1024, kappa="per_element", scaling="weak",
                desc="2D heterogeneous per-element kappa 1024x1024 mesh, kappa_e ~ logU[1e-3,1], f=1, fwd+adjoint of sum(u)"),
 }
@@ -226,6 +228,8 @@ def run_b200(args):
     _native.build()
 
     w = dict(WORKLOADS[args.workload])
+    if w.get("small"):
+        return run_b200_small2d(args, w, rank, local_rank, world, dev)
     if "nx" in w:
         return run_b200_2d(args, w, rank, local_rank, world, dev)
     n_el = args.n_elements or w["n_elements"]
@@ -476,6 +480,92 @@ def run_b200_2d(args, w, rank, local_rank, world, dev):
                 "config": {"workload": w["desc"], "nx": nx, "n_free": int(N), "nnz_free": int(nnz), "pcg_tol": 1e-13,
                            "l2": "config 4 working set ~0.2 GB > L2; config 3 (3 MB) is L2/latency-bound by construction",
                            "mesh_setup_s": t_setup, "parallelism": f"replicas only x{world} (a single mesh stays on one GPU)"},
+                "roofline": roofline, "cpu_baseline": None, "e2e": None, "gpu_launches": kt.launches, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_b200_small2d(args, w, rank, local_rank, world, dev):
+    """Config 5b: many small 2-D systems with a shared kappa, one CTA per sample (dfe_batch_fwd / dfe_batch_bwd);
+    the batch is sharded over the ranks, the only collective is the all-reduce of [dL/dkappa, loss]."""
+    import torch
+    import torch.distributed as dist
+
+    from difffe_physics_lab_b200 import DifferentiableFESolver, FEMesh
+    from difffe_physics_lab_b200.solver import KernelTimer
+
+    nx = args.n_elements or w["nx"]
+    B = (args.batch or w["batch"]) // world
+    mesh = FEMesh.rectangle(nx, nx)
+    nn = mesh.n_nodes
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    f = torch.rand((B, nn), dtype=torch.float64, device=dev, generator=gen) + 0.5
+    gbar = torch.randn((B, nn), dtype=torch.float64, device=dev, generator=gen)
+    kappa = torch.tensor(1.0, dtype=torch.float64, device=dev)
+    red = torch.zeros(2, dtype=torch.float64, device=dev)
+    its = {}
+
+    def step():
+        fr = f.requires_grad_(True)
+        fr.grad = None
+        kr = kappa.detach().requires_grad_(True)
+        s = DifferentiableFESolver(mesh, kappa=kr)
+        u = s(fr)
+        u.backward(gbar)
+        its["fwd"] = s.last_pcg[0][0]
+        its["adj"] = s._opts["last_pcg_adjoint"][0][0]
+        if world > 1:
+            red[0] = kr.grad
+            dist.all_reduce(red)
+        return kr.grad
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with KernelTimer() as kt:
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    ksum = kt.summary()
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t[0])
+    ms_step = ms_total / args.steps
+    value = B * world * args.steps / (ms_total * 1e-3)
+    peak, peak_src = measured_peak()
+    kern = {k: {"calls": c, "ms_per_launch": m / c} for k, (c, m) in ksum.items()}
+    roofline = None
+    if "batch_bwd" in kern:
+        alg = 24 * nn * B                                     # read gbar, read u, write dL/df
+        ms = kern["batch_bwd"]["ms_per_launch"]
+        roofline = {"bound": "hbm", "kernel": "k_batch<adjoint> (one CTA per sample, matrix in shared memory)",
+                    "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak,
+                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "ms_per_launch": ms,
+                    "note": "shared-memory resident PCG: bound by the per-iteration latency inside a CTA, not by HBM",
+                    "max_iterations": its, "kernels": kern}
+    if rank == 0:
+        I = mesh._native(dev.index).info
+        line = {"metric": "fem_fwd_adjoint_solves_per_s", "value": value, "unit": "solves/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "dof_per_s": value * int(I.n_free),
+                "config": {"workload": w["desc"], "nx": nx, "n_free": int(I.n_free), "batch_per_gpu": B, "global_batch": B * world,
+                           "kappa": "shared", "pcg_tol": 1e-13, "l2": "inputs 0.57 GB/array larger than L2; no flush",
+                           "parallelism": f"batch-sharded x{world}, mesh replicated" + (", NCCL allreduce of [dL/dkappa, loss]" if world > 1 else "")},
                 "roofline": roofline, "cpu_baseline": None, "e2e": None, "gpu_launches": kt.launches, "clocks": clocks}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -19,7 +19,7 @@ import subprocess
 PKG = pathlib.Path(__file__).resolve().parent
 ROOT = PKG.parent
 LIB_PATH = PKG / "libdfe_b200.so"
-SOURCES = ["dfe_mesh.cu", "dfe_1d.cu", "dfe_1d_split.cu", "dfe_1d_pipe.cu", "dfe_general.cu", "dfe_pcg.cu"]
+SOURCES = ["dfe_mesh.cu", "dfe_1d.cu", "dfe_1d_split.cu", "dfe_1d_pipe.cu", "dfe_general.cu", "dfe_pcg.cu", "dfe_batch.cu"]
 HEADERS = [PKG / "csrc" / "dfe_internal.h", PKG / "csrc" / "dfe_1d_common.cuh", ROOT / "include" / "dfe.h"]
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOT_CONVERGED, ERR_BREAKDOWN, ERR_WORKSPACE = range(7)
@@ -32,6 +32,7 @@ SYMBOLS = [
     "dfe_solve1d_workspace_bytes", "dfe_solve1d_fwd", "dfe_solve1d_bwd",
     "dfe_assemble", "dfe_eliminate", "dfe_pcg_workspace_bytes", "dfe_pcg", "dfe_scatter", "dfe_gather_free",
     "dfe_grad_workspace_bytes", "dfe_grad",
+    "dfe_batch_supported", "dfe_batch_fwd", "dfe_batch_bwd",
 ]
 
 
@@ -146,6 +147,12 @@ def lib() -> C.CDLL:
     L.dfe_grad_workspace_bytes.argtypes = [vp]
     L.dfe_grad.restype = ci
     L.dfe_grad.argtypes = [vp, vp, vp, vp, ci, vp, vp, vp, sz, vp]
+    L.dfe_batch_supported.restype = ci
+    L.dfe_batch_supported.argtypes = [vp]
+    L.dfe_batch_fwd.restype = ci
+    L.dfe_batch_fwd.argtypes = [vp, i64, vp, i64, vp, vp, vp, vp, i64, dbl, i64, vp, vp, vp, vp]
+    L.dfe_batch_bwd.restype = ci
+    L.dfe_batch_bwd.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, ci, vp, i64, vp, dbl, i64, vp, vp, vp, vp]
     if L.dfe_abi_version() != 1:
         raise RuntimeError("libdfe_b200.so ABI version mismatch")
     _lib = L

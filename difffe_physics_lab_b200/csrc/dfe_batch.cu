@@ -1,0 +1,420 @@
+// Batched solve / adjoint of MANY small systems that share one matrix (kappa shared by the batch: a scalar or a
+// per-element field) on a general mesh — BASELINE config 5b: 65 536 forcing samples on rectangle(32, 32).
+//
+// Replaces, for every sample b, solver.py:143-145 (load), :165-169 (lifting), :174 (torch.linalg.solve),
+// :177-181 (scatter) and the autograd backward of those.  The per-sample route
+// (dfe_assemble + dfe_eliminate + dfe_pcg, one cooperative whole-GPU kernel and a stream synchronisation per
+// system) is latency-bound at this size; here ONE CTA owns a sample: the SELL-32 copy of K_free (values and
+// columns) and the search direction p live in shared memory, x / r / q / 1/diag in registers (a thread owns the
+// same rows for the whole solve), the dot products are fixed-order block reductions (bit-reproducible, no float
+// atomics), and a CTA loops over samples b = blockIdx, blockIdx + grid, ...  The matrix is loaded once per CTA.
+//
+//   forward   F_b (node-centred gather in ascending element order, the arithmetic of k_assemble) -> lifting in
+//             dict order (the arithmetic of k_eliminate) -> Jacobi-PCG to the recursive tolerance -> scatter
+//   adjoint   lambda_b = K_free^{-1} gbar_b[free] -> dL/dkappa (per element, or summed per sample) and dL/df_b
+#include "dfe_internal.h"
+
+namespace {
+
+using dfe::MeshDev;
+constexpr double AREA_EPS = 1e-15;  // solver.py:120
+constexpr int BT = 256;             // threads per CTA (few warps: the per-warp scalar work of CG — reductions, alpha,
+                                    // beta — is replicated in every warp, and this kernel is bound by instruction issue)
+constexpr int BNW = BT / 32;
+constexpr int RPT_MAX = 8;          // SELL slices per warp  =>  n_free <= 32 * BNW * RPT_MAX = 2048
+constexpr int WMAX = 8;             // SELL slice widths up to WMAX are unrolled (wider slices take the generic loop)
+
+struct BArgs {
+  MeshDev M;
+  long long B;
+  const double* in;        // forward: f (B, n_nodes); adjoint: gbar (B, n_nodes)
+  long long ldin;
+  const double* u;         // adjoint: forward solution (B, n_nodes)
+  long long ldu;
+  const double* vals_full; // forward: assembled K on the full pattern (lifting terms)
+  const double* sell_vals;
+  const double* dinv;
+  double* out;             // forward: u ; adjoint: dL/df (may be null)
+  long long ldout;
+  double* gk;              // adjoint: (B) [scalar kappa] or (B, n_el) [per-element kappa]
+  int gk_per_elem;
+  double tol;
+  int maxit;
+  int* iters;              // (B)
+  double* relres;          // (B)
+  int* status;             // (B): 0 ok, 4 not converged, 5 breakdown
+};
+
+struct Elem2D {
+  double area, b[3], c[3];
+};
+// solver.py:114-134 in the reference's operation order (same as dfe_general.cu)
+__device__ __forceinline__ Elem2D elem2d(const MeshDev& M, int e, int n[3]) {
+  n[0] = M.elems[3 * e + 0];
+  n[1] = M.elems[3 * e + 1];
+  n[2] = M.elems[3 * e + 2];
+  const double xi = M.nodes[2 * n[0]], yi = M.nodes[2 * n[0] + 1];
+  const double xj = M.nodes[2 * n[1]], yj = M.nodes[2 * n[1] + 1];
+  const double xk = M.nodes[2 * n[2]], yk = M.nodes[2 * n[2] + 1];
+  Elem2D E;
+  const double cr = __dsub_rn(__dmul_rn(__dsub_rn(xj, xi), __dsub_rn(yk, yi)), __dmul_rn(__dsub_rn(xk, xi), __dsub_rn(yj, yi)));
+  E.area = __dmul_rn(0.5, fabs(cr));
+  E.b[0] = __dsub_rn(yj, yk);
+  E.b[1] = __dsub_rn(yk, yi);
+  E.b[2] = __dsub_rn(yi, yj);
+  E.c[0] = __dsub_rn(xk, xj);
+  E.c[1] = __dsub_rn(xi, xk);
+  E.c[2] = __dsub_rn(xj, xi);
+  return E;
+}
+
+// F_p of one node (solver.py:95-96 / :143-145), accumulated over the adjacent elements in ascending element order
+__device__ __forceinline__ double load_at(const MeshDev& M, const double* f, int p) {
+  double Fp = 0.0;
+  for (int a = M.adj_ptr[p]; a < M.adj_ptr[p + 1]; ++a) {
+    const int e = M.adj_elem[a];
+    if (M.dim == 1) {
+      const int i = M.elems[2 * e], j = M.elems[2 * e + 1];
+      const double h = __dsub_rn(M.nodes[j], M.nodes[i]);
+      Fp = __dadd_rn(Fp, __dmul_rn(__ddiv_rn(h, 2.0), f[p]));
+    } else {
+      int n[3];
+      const Elem2D E = elem2d(M, e, n);
+      if (E.area < AREA_EPS) continue;
+      const double fc = __ddiv_rn(__dadd_rn(__dadd_rn(f[n[0]], f[n[1]]), f[n[2]]), 3.0);
+      Fp = __dadd_rn(Fp, __dmul_rn(__ddiv_rn(E.area, 3.0), fc));
+    }
+  }
+  return Fp;
+}
+
+// fixed-order block sums of up to two values; every thread returns the same bits
+__device__ __forceinline__ void block_sum2(double& a, double& b, double* sh, int lane, int warp) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, d);
+    b += __shfl_xor_sync(0xffffffffu, b, d);
+  }
+  if (lane == 0) { sh[2 * warp] = a; sh[2 * warp + 1] = b; }
+  __syncthreads();
+  // every warp folds the BNW partials with the same butterfly (lane l holds partial l mod BNW): same bits everywhere
+  double x = sh[2 * (lane & (BNW - 1))], y = sh[2 * (lane & (BNW - 1)) + 1];
+#pragma unroll
+  for (int d = BNW / 2; d > 0; d >>= 1) {
+    x += __shfl_xor_sync(0xffffffffu, x, d);
+    y += __shfl_xor_sync(0xffffffffu, y, d);
+  }
+  a = x;
+  b = y;
+}
+
+template <bool BWD, int RPT>
+__global__ void __launch_bounds__(BT, (RPT <= 4 ? 2 : 1)) k_batch(const BArgs A) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const MeshDev& M = A.M;
+  const int n = M.n_free, nsl = M.n_slices;
+  double* sval = reinterpret_cast<double*>(smem);                 // [sell_nnz]
+  double* sp = sval + M.sell_nnz;                                  // [32 * n_slices] search direction
+  double* sred = sp + 32 * nsl;                                    // [3][2 * BNW]
+  double* slam = sred + 6 * BNW;                                   // adjoint: [n_nodes] lambda on all nodes
+  int* scol = reinterpret_cast<int*>(slam + (BWD ? M.n_nodes : 0));   // [sell_nnz]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  for (int k = tid; k < M.sell_nnz; k += BT) {
+    sval[k] = A.sell_vals[k];
+    scol[k] = M.sell_col[k];
+  }
+  // rows owned by this thread: slice warp + BNW * j, lane
+  int row[RPT], beg[RPT], wd[RPT];
+  double dinv[RPT];
+#pragma unroll
+  for (int j = 0; j < RPT; ++j) {
+    const int s = warp + BNW * j;
+    const bool on = s < nsl && 32 * s + lane < n;
+    row[j] = on ? 32 * s + lane : -1;
+    beg[j] = s < nsl ? M.slice_ptr[s] : 0;
+    wd[j] = s < nsl ? (M.slice_ptr[s + 1] - M.slice_ptr[s]) >> 5 : 0;
+    dinv[j] = on ? A.dinv[row[j]] : 0.0;
+  }
+  __syncthreads();
+
+  for (long long b = blockIdx.x; b < A.B; b += gridDim.x) {
+    const double* in = A.in + b * A.ldin;
+    // ---- right-hand side
+    double x[RPT], r[RPT], z[RPT], p[RPT], q[RPT];
+    double bb = 0.0, rz = 0.0;
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      x[j] = r[j] = z[j] = p[j] = q[j] = 0.0;
+      if (row[j] >= 0) {
+        const int node = M.free_nodes[row[j]];
+        double Fr;
+        if (BWD) {
+          Fr = in[node];                                           // gbar restricted to the free rows
+        } else {
+          Fr = load_at(M, in, node);
+          for (int t = M.lift_ptr[row[j]]; t < M.lift_ptr[row[j] + 1]; ++t)
+            Fr = __dsub_rn(Fr, __dmul_rn(A.vals_full[M.lift_src[t]], M.lift_g[t]));   // solver.py:169
+        }
+        r[j] = Fr;
+        z[j] = dinv[j] * Fr;
+        p[j] = z[j];
+        bb = fma(Fr, Fr, bb);
+        rz = fma(Fr, z[j], rz);
+      }
+      if (warp + BNW * j < nsl) sp[32 * (warp + BNW * j) + lane] = p[j];
+    }
+    block_sum2(bb, rz, sred, lane, warp);   // (its barrier also publishes sp)
+    const double tol2bb = (A.tol * A.tol) * bb;
+    int status = 0, it = 0;
+    double rr_last = 0.0;
+    if (!(bb > 0.0)) {
+      if (bb != 0.0) status = 5;            // non-finite right-hand side
+    } else {
+      status = 4;
+      while (it < A.maxit) {
+        // ---- q = K p (SELL-32 from shared memory), p.q
+        double pq = 0.0, dummy = 0.0;
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+          double sum = 0.0;
+          if (wd[j] <= WMAX) {   // all loads of the row first (independent), then the fma chain in column order
+            double v[WMAX], g[WMAX];
+#pragma unroll
+            for (int w = 0; w < WMAX; ++w) {
+              const int k = beg[j] + (w << 5) + lane;
+              const bool on = w < wd[j];
+              v[w] = on ? sval[k] : 0.0;
+              g[w] = on ? sp[scol[k]] : 0.0;
+            }
+#pragma unroll
+            for (int w = 0; w < WMAX; ++w)
+              if (w < wd[j]) sum = fma(v[w], g[w], sum);
+          } else {
+            for (int w = 0; w < wd[j]; ++w) {
+              const int k = beg[j] + (w << 5) + lane;
+              sum = fma(sval[k], sp[scol[k]], sum);
+            }
+          }
+          q[j] = sum;
+          if (row[j] >= 0) pq = fma(p[j], sum, pq);
+        }
+        block_sum2(pq, dummy, sred + 2 * BNW, lane, warp);
+        if (!(pq > 0.0) || !isfinite(pq)) { status = 5; break; }
+        const double alpha = rz / pq;
+        // ---- x, r, z, r.z, r.r
+        double rzn = 0.0, rr = 0.0;
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+          if (row[j] >= 0) {
+            x[j] = fma(alpha, p[j], x[j]);
+            r[j] = fma(-alpha, q[j], r[j]);
+            z[j] = dinv[j] * r[j];
+            rzn = fma(r[j], z[j], rzn);
+            rr = fma(r[j], r[j], rr);
+          }
+        }
+        block_sum2(rzn, rr, sred + 4 * BNW, lane, warp);
+        ++it;
+        rr_last = rr;
+        if (!isfinite(rr)) { status = 5; break; }
+        if (rr <= tol2bb) { status = 0; break; }      // ||r|| <= tol ||b||, squared: no sqrt / division in the loop
+        const double beta = rzn / rz;
+        rz = rzn;
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+          if (row[j] >= 0) {
+            p[j] = fma(beta, p[j], z[j]);
+            sp[row[j]] = p[j];
+          }
+        }
+        __syncthreads();
+      }
+    }
+    if (tid == 0) {
+      A.iters[b] = it;
+      A.relres[b] = bb > 0.0 ? sqrt(rr_last / bb) : 0.0;
+      A.status[b] = status;
+    }
+    if (!BWD) {
+      // ---- u = 0; u[d] = g; u[free] = x   (solver.py:177-181)
+      double* u = A.out + b * A.ldout;
+#pragma unroll
+      for (int j = 0; j < RPT; ++j)
+        if (row[j] >= 0) u[M.free_nodes[row[j]]] = x[j];
+      for (int i = tid; i < M.n_dir; i += BT) u[M.dir_idx[i]] = M.dir_val[i];
+    } else {
+      // ---- lambda on all nodes (0 on Dirichlet nodes), then the closed-form backward of the assembly
+      __syncthreads();   // every thread left the solve loop: slam / sred are free
+      for (int i = tid; i < M.n_nodes; i += BT) slam[i] = 0.0;
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < RPT; ++j)
+        if (row[j] >= 0) slam[M.free_nodes[row[j]]] = x[j];
+      __syncthreads();
+      const double* u = A.u + b * A.ldu;
+      double gsum = 0.0, dummy = 0.0;
+      for (int e = tid; e < M.n_el; e += BT) {
+        double g = 0.0;
+        if (M.dim == 1) {
+          const int i = M.elems[2 * e], j = M.elems[2 * e + 1];
+          const double h = M.nodes[j] - M.nodes[i];
+          g = -(slam[j] - slam[i]) * (u[j] - u[i]) / h;
+        } else {
+          int nd[3];
+          const Elem2D E = elem2d(M, e, nd);
+          if (!(E.area < AREA_EPS)) {
+            double bl = 0, bu = 0, cl = 0, cu = 0;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const double l = slam[nd[c]], uu = u[nd[c]];
+              bl = fma(E.b[c], l, bl);
+              bu = fma(E.b[c], uu, bu);
+              cl = fma(E.c[c], l, cl);
+              cu = fma(E.c[c], uu, cu);
+            }
+            g = -(bl * bu + cl * cu) / (4.0 * E.area);
+          }
+        }
+        if (A.gk_per_elem) A.gk[b * M.n_el + e] = g;
+        else gsum += g;
+      }
+      if (!A.gk_per_elem) {
+        block_sum2(gsum, dummy, sred, lane, warp);
+        if (tid == 0) A.gk[b] = gsum;
+      }
+      if (A.out) {
+        double* gf = A.out + b * A.ldout;
+        for (int pn = tid; pn < M.n_nodes; pn += BT) {
+          double g = 0.0;
+          for (int a = M.adj_ptr[pn]; a < M.adj_ptr[pn + 1]; ++a) {
+            const int e = M.adj_elem[a];
+            if (M.dim == 1) {
+              const int i = M.elems[2 * e], j = M.elems[2 * e + 1];
+              g = fma((M.nodes[j] - M.nodes[i]) * 0.5, slam[pn], g);
+            } else {
+              int nd[3];
+              const Elem2D E = elem2d(M, e, nd);
+              if (E.area < AREA_EPS) continue;
+              g = fma(E.area / 9.0, (slam[nd[0]] + slam[nd[1]]) + slam[nd[2]], g);
+            }
+          }
+          gf[pn] = g;
+        }
+      }
+    }
+    __syncthreads();   // sp / sred / slam are reused by the next sample
+  }
+}
+
+size_t batch_smem(const dfe_mesh* m, bool bwd) {
+  const size_t snz = static_cast<size_t>(m->dev.sell_nnz);
+  size_t d = snz + 32ull * m->dev.n_slices + 6 * BNW + (bwd ? static_cast<size_t>(m->dev.n_nodes) : 0);
+  return d * sizeof(double) + snz * sizeof(int) + 16;
+}
+
+bool batch_fits(const dfe_mesh* m) {
+  if (!m || m->info.device < 0 || m->dev.n_free < 1) return false;
+  if (m->dev.n_slices > BNW * RPT_MAX) return false;
+  return batch_smem(m, true) <= 200 * 1024;
+}
+
+template <bool BWD, int RPT>
+int launch(const dfe_mesh* m, const BArgs& A, cudaStream_t st) {
+  auto kern = k_batch<BWD, RPT>;
+  const size_t smem = batch_smem(m, BWD);
+  DFE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  int occ = 0;
+  DFE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BT, smem));
+  if (occ < 1) {
+    dfe::set_error("dfe_batch: kernel does not fit (shared memory %zu bytes)", smem);
+    return DFE_ERR_UNSUPPORTED;
+  }
+  long long grid = static_cast<long long>(occ) * m->sm_count;
+  if (grid > A.B) grid = A.B;
+  kern<<<static_cast<unsigned>(grid), BT, smem, st>>>(A);
+  DFE_CUDA_OK(cudaGetLastError());
+  return DFE_OK;
+}
+
+template <bool BWD>
+int dispatch(const dfe_mesh* m, const BArgs& A, cudaStream_t st) {
+  const int rpt = (m->dev.n_slices + BNW - 1) / BNW;
+  switch (rpt) {
+    case 1: return launch<BWD, 1>(m, A, st);
+    case 2: return launch<BWD, 2>(m, A, st);
+    case 3: return launch<BWD, 3>(m, A, st);
+    case 4: return launch<BWD, 4>(m, A, st);
+    case 5: case 6: return launch<BWD, 6>(m, A, st);
+    default: return launch<BWD, 8>(m, A, st);
+  }
+}
+
+int enter(const dfe_mesh* m, const char* who, int* prev) {
+  if (!m) {
+    dfe::set_error("%s: mesh is null", who);
+    return DFE_ERR_INVALID;
+  }
+  if (m->info.device < 0) {
+    dfe::set_error("%s: mesh handle is host-only; no CUDA device (this library has no CPU path)", who);
+    return DFE_ERR_CUDA;
+  }
+  if (!batch_fits(m)) {
+    dfe::set_error("%s: mesh too large for the shared-memory resident batched solver (n_free %lld > %d or matrix > 200 KB); "
+                   "use dfe_assemble / dfe_eliminate / dfe_pcg per sample", who, static_cast<long long>(m->info.n_free),
+                   32 * BNW * RPT_MAX);
+    return DFE_ERR_UNSUPPORTED;
+  }
+  DFE_CUDA_OK(cudaGetDevice(prev));
+  if (*prev != m->info.device) DFE_CUDA_OK(cudaSetDevice(m->info.device));
+  return DFE_OK;
+}
+
+}  // namespace
+
+extern "C" int dfe_batch_supported(const dfe_mesh* m) { return batch_fits(m) ? 1 : 0; }
+
+extern "C" int dfe_batch_fwd(const dfe_mesh* m, int64_t B, const double* f, int64_t ldf, const double* vals_full,
+                             const double* sell_vals, const double* dinv, double* u, int64_t ldu, double tol,
+                             int64_t maxit, int32_t* iters, double* relres, int32_t* status, void* stream) {
+  int prev;
+  int rc = enter(m, "dfe_batch_fwd", &prev);
+  if (rc) return rc;
+  if (!f || !vals_full || !sell_vals || !dinv || !u || !iters || !relres || !status || B < 1 || !(tol > 0.0) || maxit < 1) {
+    dfe::set_error("dfe_batch_fwd: null / invalid argument");
+    rc = DFE_ERR_INVALID;
+  } else {
+    BArgs A{};
+    A.M = m->dev; A.B = B; A.in = f; A.ldin = ldf; A.vals_full = vals_full; A.sell_vals = sell_vals; A.dinv = dinv;
+    A.out = u; A.ldout = ldu; A.tol = tol; A.maxit = static_cast<int>(maxit > 2000000000 ? 2000000000 : maxit);
+    A.iters = iters; A.relres = relres; A.status = status;
+    rc = dispatch<false>(m, A, static_cast<cudaStream_t>(stream));
+  }
+  if (prev != m->info.device) cudaSetDevice(prev);
+  return rc;
+}
+
+extern "C" int dfe_batch_bwd(const dfe_mesh* m, int64_t B, const double* gbar, int64_t ldg, const double* u, int64_t ldu,
+                             const double* sell_vals, const double* dinv, int kappa_mode, double* gf, int64_t ldgf,
+                             double* gkappa, double tol, int64_t maxit, int32_t* iters, double* relres, int32_t* status,
+                             void* stream) {
+  int prev;
+  int rc = enter(m, "dfe_batch_bwd", &prev);
+  if (rc) return rc;
+  if (!gbar || !u || !sell_vals || !dinv || !gkappa || !iters || !relres || !status || B < 1 || !(tol > 0.0) || maxit < 1) {
+    dfe::set_error("dfe_batch_bwd: null / invalid argument");
+    rc = DFE_ERR_INVALID;
+  } else if (kappa_mode != DFE_KAPPA_SCALAR && kappa_mode != DFE_KAPPA_PER_ELEMENT) {
+    dfe::set_error("dfe_batch_bwd: kappa_mode must be SCALAR or PER_ELEMENT (the batch shares one matrix)");
+    rc = DFE_ERR_INVALID;
+  } else {
+    BArgs A{};
+    A.M = m->dev; A.B = B; A.in = gbar; A.ldin = ldg; A.u = u; A.ldu = ldu; A.sell_vals = sell_vals; A.dinv = dinv;
+    A.out = gf; A.ldout = ldgf; A.gk = gkappa; A.gk_per_elem = kappa_mode == DFE_KAPPA_PER_ELEMENT;
+    A.tol = tol; A.maxit = static_cast<int>(maxit > 2000000000 ? 2000000000 : maxit);
+    A.iters = iters; A.relres = relres; A.status = status;
+    rc = dispatch<true>(m, A, static_cast<cudaStream_t>(stream));
+  }
+  if (prev != m->info.device) cudaSetDevice(prev);
+  return rc;
+}

@@ -38,7 +38,7 @@ class KernelTimer:
 
     _active: Optional["KernelTimer"] = None
     # kernels of libdfe_b200 launched per ABI call (default pipelined 1-D path: k1d_pipe_ck + k1d_pipe [+ k1d_pipe_gk])
-    KERNELS_PER_CALL = {"solve1d_fwd": 2, "solve1d_bwd": 3, "assemble": 1, "eliminate": 2, "pcg": 1, "scatter": 1,
+    KERNELS_PER_CALL = {"solve1d_fwd": 2, "solve1d_bwd": 3, "batch_fwd": 1, "batch_bwd": 1, "assemble": 1, "eliminate": 2, "pcg": 1, "scatter": 1,
                         "gather": 1, "grad": 3}
 
     def __init__(self):
@@ -134,9 +134,14 @@ class _FESolve(torch.autograd.Function):
                                                     int(opts["n_refine"]), u.data_ptr(), u.stride(0), ws.data_ptr(),
                                                     ws.numel(), _stream(dev)))
             else:
-                saved_mats = _general_forward(L, nm, f, kappa, mode, u, opts)
+                # many samples, one matrix, small mesh: one CTA per sample (config 5b)
+                ctx.batch = (B >= int(opts.get("batch_min", 2)) and mode in (_native.KAPPA_SCALAR, _native.KAPPA_PER_ELEMENT)
+                             and bool(L.dfe_batch_supported(nm.handle)))
+                saved_mats = (_batch_forward if ctx.batch else _general_forward)(L, nm, f, kappa, mode, u, opts)
         ctx.mesh, ctx.mode, ctx.opts, ctx.fused = mesh, mode, opts, fused
         ctx.mats = saved_mats
+        if fused:
+            ctx.batch = False
         ctx.save_for_backward(u, kappa)
         return u
 
@@ -160,9 +165,83 @@ class _FESolve(torch.autograd.Function):
                                                     u.stride(0), kappa.data_ptr(), ctx.mode, int(ctx.opts["n_refine"]),
                                                     _ptr(gf), gf.stride(0) if gf is not None else n, gk.data_ptr(),
                                                     ws.data_ptr(), ws.numel(), _stream(dev)))
+            elif ctx.batch:
+                _batch_backward(L, nm, gbar, u, kappa, ctx.mode, ctx.mats, gf, gk, ctx.opts)
             else:
                 _general_backward(L, nm, gbar, u, kappa, ctx.mode, ctx.mats, gf, gk, ctx.opts)
         return gf, (gk if need_k else None), None, None, None
+
+
+def _raise_batch_status(status, iters, relres, tol, what):
+    """Turn the per-sample status array of the batched solver into the exceptions of the per-sample path."""
+    worst = int(status.max())          # one synchronisation per call
+    if worst == 0:
+        return
+    b = int(torch.argmax(status))
+    if worst == 4:
+        raise _native.NotConvergedError(_native.ERR_NOT_CONVERGED,
+                                        f"{what}: sample {b} not converged after {int(iters[b])} iterations "
+                                        f"(relative residual {float(relres[b]):.3e}, tol {tol:.3e})")
+    raise _native.BreakdownError(_native.ERR_BREAKDOWN,
+                                 f"{what}: breakdown in sample {b} at iteration {int(iters[b])} (p^T K p <= 0 or non-finite): "
+                                 "K_free is not SPD — does the mesh have a Dirichlet node?")
+
+
+def _batch_forward(L, nm, f, kappa, mode, u, opts):
+    """Shared matrix, many right-hand sides, small mesh: assemble / eliminate ONCE, then one CTA per sample
+    (dfe_batch_fwd).  Returns the saved (sell, dinv) like the per-sample path."""
+    dev = f.device
+    I = nm.info
+    B = f.shape[0]
+    st = _stream(dev)
+    amode = _native.KAPPA_SCALAR if mode == _native.KAPPA_SCALAR else _native.KAPPA_PER_ELEMENT
+    vals = torch.empty(max(I.nnz_full, 1), dtype=torch.float64, device=dev)
+    F0 = torch.empty(I.n_nodes, dtype=torch.float64, device=dev)
+    sell = torch.empty(max(I.sell_nnz, 1), dtype=torch.float64, device=dev)
+    dinv = torch.empty(max(I.n_free, 1), dtype=torch.float64, device=dev)
+    Ff0 = torch.empty(max(I.n_free, 1), dtype=torch.float64, device=dev)
+    with _timed("assemble", dev):
+        _native.check(L.dfe_assemble(nm.handle, kappa.reshape(-1).data_ptr(), amode, f[0].data_ptr(), vals.data_ptr(),
+                                     F0.data_ptr(), st))
+    with _timed("eliminate", dev):
+        _native.check(L.dfe_eliminate(nm.handle, vals.data_ptr(), F0.data_ptr(), None, sell.data_ptr(), Ff0.data_ptr(),
+                                      dinv.data_ptr(), st))
+    iters = torch.empty(B, dtype=torch.int32, device=dev)
+    relres = torch.empty(B, dtype=torch.float64, device=dev)
+    status = torch.empty(B, dtype=torch.int32, device=dev)
+    tol = float(opts["pcg_tol"])
+    with _timed("batch_fwd", dev):
+        _native.check(L.dfe_batch_fwd(nm.handle, B, f.data_ptr(), f.stride(0), vals.data_ptr(), sell.data_ptr(),
+                                      dinv.data_ptr(), u.data_ptr(), u.stride(0), tol,
+                                      int(opts["pcg_maxit"] or max(10 * I.n_free, 1000)), iters.data_ptr(),
+                                      relres.data_ptr(), status.data_ptr(), st))
+    _raise_batch_status(status, iters, relres, tol, "dfe_batch_fwd")
+    opts["last_pcg"] = [(int(iters.max()), float(relres.max()))]
+    return [(sell, dinv)]
+
+
+def _batch_backward(L, nm, gbar, u, kappa, mode, mats, gf, gk, opts):
+    dev = u.device
+    I = nm.info
+    B = u.shape[0]
+    st = _stream(dev)
+    sell, dinv = mats[0]
+    gmode = _native.KAPPA_SCALAR if mode == _native.KAPPA_SCALAR else _native.KAPPA_PER_ELEMENT
+    nk = 1 if gmode == _native.KAPPA_SCALAR else I.n_elements
+    gk_b = torch.empty((B, nk), dtype=torch.float64, device=dev)
+    iters = torch.empty(B, dtype=torch.int32, device=dev)
+    relres = torch.empty(B, dtype=torch.float64, device=dev)
+    status = torch.empty(B, dtype=torch.int32, device=dev)
+    tol = float(opts["pcg_tol"])
+    with _timed("batch_bwd", dev):
+        _native.check(L.dfe_batch_bwd(nm.handle, B, gbar.data_ptr(), gbar.stride(0), u.data_ptr(), u.stride(0),
+                                      sell.data_ptr(), dinv.data_ptr(), gmode, _ptr(gf),
+                                      gf.stride(0) if gf is not None else I.n_nodes, gk_b.data_ptr(), tol,
+                                      int(opts["pcg_maxit"] or max(10 * I.n_free, 1000)), iters.data_ptr(),
+                                      relres.data_ptr(), status.data_ptr(), st))
+    _raise_batch_status(status, iters, relres, tol, "dfe_batch_bwd")
+    opts["last_pcg_adjoint"] = [(int(iters.max()), float(relres.max()))]
+    gk.copy_(gk_b.sum(dim=0).reshape(gk.shape))   # torch.sum on CUDA is deterministic (no atomics)
 
 
 def _general_forward(L, nm, f, kappa, mode, u, opts):

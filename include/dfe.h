@@ -148,6 +148,29 @@ size_t dfe_grad_workspace_bytes(const dfe_mesh* m);
 int dfe_grad(const dfe_mesh* m, const double* lam_full, const double* u, const double* kappa,
              int kappa_mode, double* gkappa, double* gf, void* ws, size_t ws_bytes, void* stream);
 
+/* ---------------------------------------------------------------- batched small systems sharing one matrix
+ * (BASELINE config 5b: many forcing samples, shared kappa, small 2-D mesh).  Replaces, for every sample b of the
+ * batch, solver.py:143-145 (load), :165-169 (lifting), :174 (solve), :177-181 (scatter) and their autograd
+ * backward — the per-sample sequence dfe_assemble/dfe_eliminate/dfe_pcg/dfe_scatter/dfe_grad above, which is
+ * latency-bound for meshes of ~1e3 unknowns.  ONE CTA owns a sample: K_free (SELL-32, from dfe_eliminate) and the
+ * search direction live in shared memory, Jacobi-PCG to the recursive tolerance, fixed-order reductions.
+ *   dfe_batch_supported  1 if the mesh fits (n_free <= 2048 and matrix + vectors <= 200 KB of shared memory)
+ *   dfe_batch_fwd        f, u: (B, n_nodes) with row strides ldf / ldu; vals_full: K on the full pattern
+ *                        (dfe_assemble, any f), sell_vals / dinv from dfe_eliminate
+ *   dfe_batch_bwd        gbar, u, gf: (B, n_nodes); gkappa: SCALAR -> (B) per-sample sums (the caller adds them up
+ *                        for the shared parameter), PER_ELEMENT -> (B, n_el); gf may be NULL
+ *   iters / relres / status: device arrays of length B (status 0 ok, 4 not converged, 5 breakdown); the calls are
+ *                        asynchronous on `stream`.
+ */
+int dfe_batch_supported(const dfe_mesh* m);
+int dfe_batch_fwd(const dfe_mesh* m, int64_t B, const double* f, int64_t ldf, const double* vals_full,
+                  const double* sell_vals, const double* dinv, double* u, int64_t ldu, double tol, int64_t maxit,
+                  int32_t* iters, double* relres, int32_t* status, void* stream);
+int dfe_batch_bwd(const dfe_mesh* m, int64_t B, const double* gbar, int64_t ldg, const double* u, int64_t ldu,
+                  const double* sell_vals, const double* dinv, int kappa_mode, double* gf, int64_t ldgf,
+                  double* gkappa, double tol, int64_t maxit, int32_t* iters, double* relres, int32_t* status,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -432,6 +432,79 @@ def test_2d_batched_and_determinism():
         assert relerr(u[b], uo) <= TOL2D and abs(gk[b, 0] - gko.sum()) <= TOL2D * np.abs(gko).sum()
 
 
+def test_2d_batched_small_systems_kernel():
+    """dfe_batch_fwd / dfe_batch_bwd (one CTA per sample, shared matrix): against the oracle, against the per-sample
+    route (dfe_assemble / dfe_eliminate / dfe_pcg per system), more samples than CTAs, per-element shared kappa,
+    the largest mesh the kernel takes, and a 1-D mesh that is not a chain."""
+    L = _native.lib()
+    rng = np.random.default_rng(11)
+    # (a) more samples than resident CTAs, non-zero Dirichlet data, scalar shared kappa
+    m = FEMesh.rectangle(9, 7, x_range=(0.0, 1.3), y_range=(-0.4, 0.5), bc_value=0.3)
+    assert L.dfe_batch_supported(m._native(torch.cuda.current_device()).handle) == 1
+    B = 700
+    f = rng.uniform(0, 1, (B, m.n_nodes))
+    gbar = rng.standard_normal((B, m.n_nodes))
+    u, gk, gf, s = run(m, 0.8, f, gbar)
+    assert s.last_pcg[0][0] > 0
+    tot, mag = 0.0, 0.0
+    for b in list(range(0, B, 97)) + [B - 1]:
+        uo, gko, gfo = oracle_run(m, 0.8, f[b], gbar[b])
+        assert relerr(u[b], uo) <= TOL2D and np.abs(gf[b] - gfo).max() <= TOL2D * np.abs(gfo).max()
+    # (b) batched route == per-sample route (same arithmetic for F, lifting, SpMV; different reduction trees)
+    B = 6
+    k = torch.tensor(1.7, dtype=torch.float64, device="cuda", requires_grad=True)
+    ft = torch.tensor(f[:B], device="cuda", requires_grad=True)
+    s1 = DifferentiableFESolver(m, kappa=k)
+    u1 = s1(ft)
+    (u1 * torch.tensor(gbar[:B], device="cuda")).sum().backward()
+    gk1, gf1 = k.grad.clone(), ft.grad.clone()
+    k.grad = None
+    ft.grad = None
+    s2 = DifferentiableFESolver(m, kappa=k)
+    s2._opts["batch_min"] = 10 ** 9          # force one cooperative PCG per sample
+    u2 = s2(ft)
+    (u2 * torch.tensor(gbar[:B], device="cuda")).sum().backward()
+    assert float((u1 - u2).abs().max()) <= 1e-12 * float(u2.abs().max())
+    assert abs(float(gk1 - k.grad)) <= 1e-11 * abs(float(k.grad)) + 1e-14
+    assert float((gf1 - ft.grad).abs().max()) <= 1e-12 * float(ft.grad.abs().max())
+    # (c) shared per-element field
+    m = FEMesh.rectangle(13, 11, bc_value=-0.2)
+    kap = np.exp(rng.uniform(np.log(1e-2), 0.0, m.n_elements))
+    B = 4
+    f = rng.uniform(0, 1, (B, m.n_nodes))
+    gbar = rng.standard_normal((B, m.n_nodes))
+    u, gk, gf, _ = run(m, kap, f, gbar)
+    gsum = np.zeros(m.n_elements)
+    for b in range(B):
+        uo, gko, gfo = oracle_run(m, kap, f[b], gbar[b])
+        assert relerr(u[b], uo) <= TOL2D and np.abs(gf[b] - gfo).max() <= TOL2D * np.abs(gfo).max()
+        gsum += gko
+    assert np.abs(gk - gsum).max() <= TOL2D * np.abs(gsum).max()
+    # (d) largest mesh the kernel takes (4 slices per warp), and one beyond it (per-sample route)
+    m = FEMesh.rectangle(45, 44)
+    assert m.n_nodes - len(m.dirichlet_nodes) == 44 * 43
+    assert L.dfe_batch_supported(m._native(torch.cuda.current_device()).handle) == 1
+    f = rng.uniform(0, 1, (3, m.n_nodes))
+    gbar = rng.standard_normal((3, m.n_nodes))
+    u, gk, gf, _ = run(m, 1.1, f, gbar)
+    uo, gko, gfo = oracle_run(m, 1.1, f[2], gbar[2])
+    assert relerr(u[2], uo) <= TOL2D and np.abs(gf[2] - gfo).max() <= TOL2D * np.abs(gfo).max()
+    assert L.dfe_batch_supported(FEMesh.rectangle(60, 60)._native(torch.cuda.current_device()).handle) == 0
+    # (e) 1-D mesh that is not a chain (interior Dirichlet node): general path, batched
+    m = FEMesh.line(50, bc_left=0.1, bc_right=0.4)
+    m.dirichlet_nodes[20] = -0.3
+    f = rng.uniform(0, 1, (5, 51))
+    gbar = rng.standard_normal((5, 51))
+    u, gk, gf, _ = run(m, 2.2, f, gbar)
+    tot, mag = 0.0, 0.0
+    for b in range(5):
+        uo, gko, gfo = oracle_run(m, 2.2, f[b], gbar[b])
+        assert relerr(u[b], uo) <= TOL2D and np.abs(gf[b] - gfo).max() <= TOL2D * max(np.abs(gfo).max(), 1e-300)
+        tot += gko.sum()
+        mag += np.abs(gko).sum()
+    assert abs(float(gk) - tot) <= TOL2D * mag
+
+
 def test_general_path_for_non_chain_1d_meshes():
     """1-D meshes the fused kernel does not take: interior Dirichlet node, permuted elements, per-element kappa."""
     rng = np.random.default_rng(8)
@@ -460,6 +533,8 @@ def test_pcg_error_reporting():
     f = torch.ones(m.n_nodes, dtype=torch.float64, device="cuda")
     with pytest.raises(_native.NotConvergedError):
         DifferentiableFESolver(m, pcg_maxit=3)(f)
+    with pytest.raises(_native.NotConvergedError):          # the batched one-CTA-per-sample kernel reports it too
+        DifferentiableFESolver(m, pcg_maxit=3)(torch.ones((4, m.n_nodes), dtype=torch.float64, device="cuda"))
     m = FEMesh.rectangle(6, 6)
     m.dirichlet_nodes = {}              # singular K: the reference silently returns garbage
     with pytest.raises(_native.DfeError):

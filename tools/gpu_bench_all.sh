@@ -1,7 +1,7 @@
 #!/bin/bash
 # Bench lines for the non-default workloads (1 GPU): c5a (shared kappa sweep), c3, c4; plus pipe config alternatives.
 mkdir -p gpurun_out
-for w in c5a c3 c4; do
+for w in c5a c5b c3 c4; do
   timeout -s KILL 600 python bench.py --workload $w --steps ${STEPS:-3} --no-cpu --no-e2e > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err; echo "$w rc=$?"
   python - $w <<'PY'
 import json,sys

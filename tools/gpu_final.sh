@@ -10,7 +10,7 @@ timeout -s KILL 1500 python -m pytest tests -m gpu -q --timeout 900 --timeout-me
 tail -6 gpurun_out/check.log
 timeout -s KILL 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
 timeout -s KILL 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"
-for w in c5a c3 c4; do
+for w in c5a c5b c3 c4; do
   timeout -s KILL 600 python bench.py --workload $w --steps 3 --no-cpu --no-e2e > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err; echo "$w rc=$?"
 done
 SHORT="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu"
