@@ -58,6 +58,7 @@ struct PP {
   unsigned long long* part;   // [B][2][G][2] chunk totals (s, m) as bit patterns, pre-set to SENT
   double* gkpart;             // backward: [B][G+2] partial dL/dkappa (chunks, boundary terms of sweep 0 and 1)
   int* err;                   // mesh handle's fault word (mapped host memory): set to 1 if a wait exceeded its bound
+  int backoff;                // cycles a fold-warp lane waits between two polls of a chunk total (DFE_PIPE_BACKOFF)
   long long* gt;              // debug (trace build): [CTAs][32][8] globaltimer stamps
   long long* wstat;           // debug (trace build): [CTAs][12 categories][sum, max] wait cycles
   long long* trace;           // debug (DFE_PIPE_TRACE=1): [3 CTAs][16 iterations][4 roles][8 events] clock64 stamps
@@ -149,7 +150,7 @@ __device__ __forceinline__ void ld_pair(const unsigned long long* p, unsigned lo
   asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
 __device__ __forceinline__ void poll_pair(const unsigned long long* p, unsigned long long a, unsigned long long b,
-                                          double& s, double& m, int* err, int* dead) {
+                                          double& s, double& m, int* err, int* dead, int backoff) {
   if (a == SENT || b == SENT) {
     int spins = 0;
     while (true) {
@@ -161,6 +162,10 @@ __device__ __forceinline__ void poll_pair(const unsigned long long* p, unsigned 
         *reinterpret_cast<volatile int*>(err) = 1;
         a = b = 0;
         break;
+      }
+      if (backoff > 0) {   // busy wait on the clock: keeps the spinning lanes off the L2 lines the publishers store to
+        const long long t0 = clock64();
+        while (clock64() - t0 < backoff) {}
       }
       // no __nanosleep here: measured on B200, a sleeping poller occasionally oversleeps by ~4.5 us, and every such
       // hiccup stalls the whole group of CTAs two iterations later (1.7x on the config-2 step); the L2 round trip of
@@ -450,7 +455,7 @@ __device__ __forceinline__ void fold_warp(const PP& p, Ctl<W, NR>* ctl, int lane
         const int ci = lane + 32 * l;
         if (ci < G) {
           double sv, mv;
-          poll_pair(base + 2 * ci, ra[l], rb[l], sv, mv, p.err, &ctl->dead);
+          poll_pair(base + 2 * ci, ra[l], rb[l], sv, mv, p.err, &ctl->dead, p.backoff);
           St += sv; Mt += mv;
           if (ci < c) { Sx += sv; Mx += mv; }
         }
@@ -459,7 +464,7 @@ __device__ __forceinline__ void fold_warp(const PP& p, Ctl<W, NR>* ctl, int lane
         const int ci = lane + l0;
         if (ci < G) {
           double sv, mv;
-          poll_pair(base + 2 * ci, SENT, SENT, sv, mv, p.err, &ctl->dead);
+          poll_pair(base + 2 * ci, SENT, SENT, sv, mv, p.err, &ctl->dead, p.backoff);
           St += sv; Mt += mv;
           if (ci < c) { Sx += sv; Mx += mv; }
         }
@@ -934,6 +939,8 @@ int pipe1d_run(const dfe_mesh* m, long long B, bool bwd, const double* in0, long
   p.err = m->d_fault;   // sticky, host-visible (checked at the next dfe_solve1d_* call on this handle)
   int rc, G = 0;
   const int id = cfg_id();
+  static const int backoff = [] { const char* e = getenv("DFE_PIPE_BACKOFF"); return e ? atoi(e) : 0; }();
+  p.backoff = backoff;
   static const bool want_trace = getenv("DFE_PIPE_TRACE") != nullptr;
   const size_t trace_n = 3 * 16 * 4 * 8;
   if (want_trace) {

@@ -13,25 +13,23 @@
 // Dot products are reduced in a fixed order (lane-strided sum + xor-shuffle tree over the per-CTA
 // partials), identically on every CTA: results are bit-reproducible and no float atomics are used.
 // Stops when the recursive residual satisfies ||r||_2 <= tol ||rhs||_2.
+#include <cstdlib>
+
 #include "dfe_internal.h"
 
 namespace {
 
-// Grid-wide barrier for a cooperative (co-resident) launch: one release-increment per CTA on a monotonically
-// increasing counter, acquire-polling by one thread per CTA.  `epoch` counts the barriers this CTA has passed.
-__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& epoch) {
-  __syncthreads();
-  ++epoch;
-  if (threadIdx.x == 0) {
-    const unsigned int target = epoch * gridDim.x;
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
-    unsigned int v;
-    do {   // relaxed polling (no L1 invalidation per poll), one acquire fence once the count is reached
-      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-    } while (v < target);
-    asm volatile("fence.acq_rel.gpu;" ::: "memory");
-  }
-  __syncthreads();
+// Grid-wide fixed-order sum of two values for a cooperative (co-resident) launch, fused with the grid barrier the
+// CG phases need anyway: *data-as-flag* — every CTA release-stores its two partial sums into its slot of the epoch's
+// buffer (pre-set to an all-ones sentinel), warp 0 of every CTA polls all G slots with relaxed loads and adds them in
+// a fixed order (lane-strided, then a butterfly), one acquire fence, one CTA barrier.  No atomic, no separate counter,
+// no second read of a partials array: one L2 round trip after the last CTA arrives.  Three buffers rotate; a CTA
+// resets its own slot of epoch E-2 just before it publishes epoch E (everybody finished reading E-2 before
+// publishing E-1, which this CTA has seen complete), and the release orders the reset before the publication.
+constexpr unsigned long long SENTQ = 0xFFFFFFFFFFFFFFFFull;
+__device__ __forceinline__ unsigned long long as_bits(double v) {
+  const unsigned long long u = static_cast<unsigned long long>(__double_as_longlong(v));
+  return u == SENTQ ? 0x7FF8000000000000ull : u;   // a NaN that happens to carry the sentinel payload
 }
 
 constexpr int PT = 768;  // threads per CTA: one CTA per SM (148 arrivals per grid barrier instead of 444)
@@ -51,42 +49,80 @@ struct PcgArgs {
   double* p1;
   double* q;
   unsigned int* barrier;  // grid barrier counter (zeroed before launch)
-  double* part;   // [3][gridDim.x]
+  double* part;   // [3 epochs][gridDim.x][2] exchange slots, pre-set to the sentinel
   double* out;    // [0]=iterations, [1]=relres, [2]=status (0 ok, 4 not converged, 5 breakdown)
   double tol;
   long long maxit;
+  int backoff;    // cycles an early arriver waits between two polls of a slot
 };
 
-// Sum of `v` over the whole grid; every thread of every CTA returns the same bits.
-__device__ __forceinline__ double grid_sum(unsigned int* bar, unsigned int& epoch, double v, double* part, double* sh) {
+// Sums of `v0` and `v1` over the whole grid; every thread of every CTA returns the same bits.  Doubles as the grid
+// barrier between the CG phases (all global writes of every CTA before the call are visible after it).
+__device__ __forceinline__ void grid_sum2(double* slots, unsigned int& epoch, double& v0, double& v1, double* sh,
+                                          const int backoff) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int G = gridDim.x;
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-  if (lane == 0) sh[warp] = v;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double a = 0.0;
-    for (int w = 0; w < PW; ++w) a += sh[w];
-    part[blockIdx.x] = a;
+  for (int d = 16; d > 0; d >>= 1) {
+    v0 += __shfl_xor_sync(0xffffffffu, v0, d);
+    v1 += __shfl_xor_sync(0xffffffffu, v1, d);
   }
-  grid_barrier(bar, epoch);
-  double a = 0.0;
-  for (int i = lane; i < static_cast<int>(gridDim.x); i += 32) a += __ldcg(part + i);
+  if (lane == 0) { sh[2 * warp] = v0; sh[2 * warp + 1] = v1; }
+  __syncthreads();
+  ++epoch;
+  if (warp == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = lane; w < PW; w += 32) { a += sh[2 * w]; b += sh[2 * w + 1]; }
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
-  return a;
+    for (int d = 16; d > 0; d >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, d);
+      b += __shfl_xor_sync(0xffffffffu, b, d);
+    }
+    double* cur = slots + static_cast<size_t>(epoch % 3) * 2 * G;
+    if (lane == 0) {
+      unsigned long long* old = reinterpret_cast<unsigned long long*>(slots + static_cast<size_t>((epoch + 1) % 3) * 2 * G) + 2 * blockIdx.x;
+      asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(old), "l"(SENTQ), "l"(SENTQ) : "memory");
+      asm volatile("st.release.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(cur + 2 * blockIdx.x), "l"(as_bits(a)), "l"(as_bits(b)) : "memory");
+    }
+    double sa = 0.0, sb = 0.0;
+    for (int i = lane; i < G; i += 32) {
+      unsigned long long ua, ub;
+      while (true) {
+        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(ua), "=l"(ub) : "l"(cur + 2 * i) : "memory");
+        if (ua != SENTQ && ub != SENTQ) break;
+        // early arrivers back off for ~250 cycles (a busy wait on the clock, not __nanosleep, which oversleeps by
+        // microseconds on B200): hundreds of spinning lanes on a handful of L2 lines delay the stores they wait for
+        const long long t0 = clock64();
+        while (clock64() - t0 < backoff) {}
+      }
+      sa += __longlong_as_double(static_cast<long long>(ua));
+      sb += __longlong_as_double(static_cast<long long>(ub));
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      sa += __shfl_xor_sync(0xffffffffu, sa, d);
+      sb += __shfl_xor_sync(0xffffffffu, sb, d);
+    }
+    // (the butterfly above made every lane's polls complete; one fence, then the CTA barrier, as a grid barrier does)
+    __syncwarp();
+    if (lane == 0) {
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      sh[2 * PW] = sa;
+      sh[2 * PW + 1] = sb;
+    }
+  }
+  __syncthreads();
+  v0 = sh[2 * PW];
+  v1 = sh[2 * PW + 1];
 }
 
 __global__ void __launch_bounds__(PT, 1) k_pcg(const PcgArgs A) {
   unsigned int epoch = 0;
-  __shared__ double sh[3][PW];
+  __shared__ double sh[2 * PW + 2];
   const int lane = threadIdx.x & 31;
   const int gw = (blockIdx.x * PT + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * PT) >> 5;
   const int G = gridDim.x;
-  double* partA = A.part;
-  double* partB = A.part + G;
-  double* partC = A.part + 2 * G;
 
   // ---- init: x = 0, r = b, z = D^{-1} r, p buffers = 0
   double bb = 0.0, rz = 0.0;
@@ -104,8 +140,7 @@ __global__ void __launch_bounds__(PT, 1) k_pcg(const PcgArgs A) {
       rz = fma(bi, zi, rz);
     }
   }
-  bb = grid_sum(A.barrier, epoch, bb, partA, sh[0]);
-  rz = grid_sum(A.barrier, epoch, rz, partB, sh[1]);
+  grid_sum2(A.part, epoch, bb, rz, sh, A.backoff);
   const double bnorm = sqrt(bb);
   double status = 0.0, relres = 0.0;
   long long it = 0;
@@ -169,7 +204,8 @@ __global__ void __launch_bounds__(PT, 1) k_pcg(const PcgArgs A) {
           pq = fma(pi, sum2, pq);
         }
       }
-      pq = grid_sum(A.barrier, epoch, pq, partA, sh[0]);
+      double unused = 0.0;
+      grid_sum2(A.part, epoch, pq, unused, sh, A.backoff);
       if (!(pq > 0.0) || !isfinite(pq)) {
         status = 5.0;
         break;
@@ -202,42 +238,7 @@ __global__ void __launch_bounds__(PT, 1) k_pcg(const PcgArgs A) {
           rr = fma(ri2, ri2, rr);
         }
       }
-      // two independent reductions share one grid barrier
-      {
-        const int warp = threadIdx.x >> 5;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-          rz_new += __shfl_xor_sync(0xffffffffu, rz_new, d);
-          rr += __shfl_xor_sync(0xffffffffu, rr, d);
-        }
-        if (lane == 0) {
-          sh[1][warp] = rz_new;
-          sh[2][warp] = rr;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-          double a = 0.0, c = 0.0;
-          for (int w = 0; w < PW; ++w) {
-            a += sh[1][w];
-            c += sh[2][w];
-          }
-          partB[blockIdx.x] = a;
-          partC[blockIdx.x] = c;
-        }
-        grid_barrier(A.barrier, epoch);
-        double a = 0.0, c = 0.0;
-        for (int i = lane; i < G; i += 32) {
-          a += __ldcg(partB + i);
-          c += __ldcg(partC + i);
-        }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-          a += __shfl_xor_sync(0xffffffffu, a, d);
-          c += __shfl_xor_sync(0xffffffffu, c, d);
-        }
-        rz_new = a;
-        rr = c;
-      }
+      grid_sum2(A.part, epoch, rz_new, rr, sh, A.backoff);   // two independent reductions share one exchange
       ++it;
       relres = sqrt(rr) / bnorm;
       if (!isfinite(rr)) {
@@ -288,7 +289,7 @@ int plan_pcg(const dfe_mesh* m, PcgPlan* pl, bool query_device) {
   pl->off_p0 = off; off += vec;
   pl->off_p1 = off; off += vec;
   pl->off_q = off; off += vec;
-  pl->off_part = off; off += 3 * static_cast<size_t>(max_grid) * sizeof(double);
+  pl->off_part = off; off += 6 * static_cast<size_t>(max_grid) * sizeof(double);
   pl->off_out = off; off += 256;
   pl->off_bar = off; off += 256;
   pl->total = off;
@@ -347,9 +348,11 @@ extern "C" int dfe_pcg(const dfe_mesh* m, const double* sell_vals, const double*
     A.barrier = reinterpret_cast<unsigned int*>(w + pl.off_bar);
     A.tol = tol;
     A.maxit = maxit;
+    static const int backoff = [] { const char* e = getenv("DFE_PCG_BACKOFF"); return e ? atoi(e) : 250; }();
+    A.backoff = backoff;
     void* args[] = {&A};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaError_t e = cudaMemsetAsync(A.barrier, 0, sizeof(unsigned int), st);
+    cudaError_t e = cudaMemsetAsync(A.part, 0xFF, 6 * static_cast<size_t>(pl.grid) * sizeof(double), st);
     if (e == cudaSuccess) e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_pcg), dim3(pl.grid), dim3(PT), args, 0, st);
     if (e != cudaSuccess) {
       dfe::set_error("dfe_pcg: cooperative launch failed: %s", cudaGetErrorString(e));
