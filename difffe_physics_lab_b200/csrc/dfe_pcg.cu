@@ -174,10 +174,11 @@ __global__ void __launch_bounds__(PT, 1) k_pcg(const PcgArgs A) {
           for (int u = 0; u < 4; ++u) {
             const bool on = w0 + u < wd, on2 = w0 + u < wd2;
             const int k = beg + ((w0 + u) << 5) + lane, k2 = beg2 + ((w0 + u) << 5) + lane;
-            j[u] = on ? A.col[k] : -1;
-            v[u] = on ? A.val[k] : 0.0;
-            j2[u] = on2 ? A.col[k2] : -1;
-            v2[u] = on2 ? A.val[k2] : 0.0;
+            // the matrix streams through once per iteration (evict-first), the vectors it is applied to stay in L2
+            j[u] = on ? __ldcs(A.col + k) : -1;
+            v[u] = on ? __ldcs(A.val + k) : 0.0;
+            j2[u] = on2 ? __ldcs(A.col + k2) : -1;
+            v2[u] = on2 ? __ldcs(A.val + k2) : 0.0;
           }
           double g[4], g2[4];
 #pragma unroll
@@ -217,10 +218,11 @@ __global__ void __launch_bounds__(PT, 1) k_pcg(const PcgArgs A) {
         const int i = 32 * s + lane, i2 = i + 32 * nwarps;
         const bool on = i < A.n, on2 = (s + nwarps < A.n_slices) && i2 < A.n;
         double xi = 0, pi = 0, qi = 0, ri = 0, di = 0, xi2 = 0, pi2 = 0, qi2 = 0, ri2 = 0, di2 = 0;
-        if (on) { xi = A.x[i]; pi = pnew[i]; qi = A.q[i]; ri = A.r[i]; di = A.dinv[i]; }
-        if (on2) { xi2 = A.x[i2]; pi2 = pnew[i2]; qi2 = A.q[i2]; ri2 = A.r[i2]; di2 = A.dinv[i2]; }
+        // x is touched once per iteration and never gathered: streamed (evict-first) like the matrix
+        if (on) { xi = __ldcs(A.x + i); pi = pnew[i]; qi = A.q[i]; ri = A.r[i]; di = A.dinv[i]; }
+        if (on2) { xi2 = __ldcs(A.x + i2); pi2 = pnew[i2]; qi2 = A.q[i2]; ri2 = A.r[i2]; di2 = A.dinv[i2]; }
         if (on) {
-          A.x[i] = fma(alpha, pi, xi);
+          __stcs(A.x + i, fma(alpha, pi, xi));
           ri = fma(-alpha, qi, ri);
           const double zi = di * ri;
           A.r[i] = ri;
@@ -229,7 +231,7 @@ __global__ void __launch_bounds__(PT, 1) k_pcg(const PcgArgs A) {
           rr = fma(ri, ri, rr);
         }
         if (on2) {
-          A.x[i2] = fma(alpha, pi2, xi2);
+          __stcs(A.x + i2, fma(alpha, pi2, xi2));
           ri2 = fma(-alpha, qi2, ri2);
           const double zi2 = di2 * ri2;
           A.r[i2] = ri2;
