@@ -469,6 +469,8 @@ def run_b200_2d(args, w, rank, local_rank, world, dev):
         roofline = {"bound": "hbm", "kernel": "k_pcg (cooperative Jacobi-PCG)", "achieved": alg / (ms_launch * 1e-3) / 1e9,
                     "peak": peak, "unit": "GB/s", "frac": alg / (ms_launch * 1e-3) / 1e9 / peak,
                     "traffic": measured_traffic("k_pcg") if args.workload == "c4" and not args.n_elements else None,
+                    "note": "achieved = SURVEY 8(d) accounting bytes / time; the gathered vectors stay in the 126 MB L2 "
+                            "(matrix loads are evict-first), so the DRAM traffic in `traffic` is lower than the accounting",
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "ms_per_launch": ms_launch,
                     "bytes_per_iteration": bytes_iter, "iterations": its, "us_per_iteration": 1e3 * ms_pcg / calls / (iters_step / 2.0),
                     "kernels": {k: {"calls": c, "ms_per_launch": m / c} for k, (c, m) in ksum.items()}}

@@ -120,13 +120,19 @@ __global__ void __launch_bounds__(PT, 1) k_pcg(const PcgArgs A) {
   unsigned int epoch = 0;
   __shared__ double sh[2 * PW + 2];
   const int lane = threadIdx.x & 31;
-  const int gw = (blockIdx.x * PT + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * PT) >> 5;
+  // A CTA owns a CONTIGUOUS block of SELL slices and walks it front to back, PW slices at a time: the neighbours a
+  // row gathers (rows +-1 and, on a structured mesh, +- one mesh line) were touched by this SM a trip or two ago and
+  // are served by its L1 instead of travelling from L2 to two or three different SMs.
+  const int per_cta = (A.n_slices + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int s_lo = blockIdx.x * per_cta;
+  const int s_hi = s_lo + per_cta < A.n_slices ? s_lo + per_cta : A.n_slices;
+  const int gw = s_lo + (threadIdx.x >> 5);
+  constexpr int nwarps = PW;
   const int G = gridDim.x;
 
   // ---- init: x = 0, r = b, z = D^{-1} r, p buffers = 0
   double bb = 0.0, rz = 0.0;
-  for (int s = gw; s < A.n_slices; s += nwarps) {
+  for (int s = gw; s < s_hi; s += nwarps) {
     const int i = 32 * s + lane;
     if (i < A.n) {
       const double bi = A.b[i];
@@ -155,12 +161,12 @@ __global__ void __launch_bounds__(PT, 1) k_pcg(const PcgArgs A) {
     while (it < A.maxit) {
       // ---- phase A
       double pq = 0.0;
-      for (int s = gw; s < A.n_slices; s += 2 * nwarps) {
+      for (int s = gw; s < s_hi; s += 2 * nwarps) {
         // two slices per trip, four columns of each per batch: all column / value loads of a batch are issued
         // before the first dependent gather, so ~16 gathers per thread are in flight (the kernel is bound by
         // memory latency, not bandwidth: ncu long_scoreboard 73 % with one column at a time)
         const int s2 = s + nwarps;
-        const bool has2 = s2 < A.n_slices;
+        const bool has2 = s2 < s_hi;
         const int i = 32 * s + lane, i2 = 32 * s2 + lane;
         const int beg = A.slice_ptr[s], end = A.slice_ptr[s + 1];
         const int beg2 = has2 ? A.slice_ptr[s2] : 0, end2 = has2 ? A.slice_ptr[s2 + 1] : 0;
@@ -214,9 +220,9 @@ __global__ void __launch_bounds__(PT, 1) k_pcg(const PcgArgs A) {
       const double alpha = rz / pq;
       // ---- phase B
       double rz_new = 0.0, rr = 0.0;
-      for (int s = gw; s < A.n_slices; s += 2 * nwarps) {   // two slices per trip: ten independent loads in flight
+      for (int s = gw; s < s_hi; s += 2 * nwarps) {   // two slices per trip: ten independent loads in flight
         const int i = 32 * s + lane, i2 = i + 32 * nwarps;
-        const bool on = i < A.n, on2 = (s + nwarps < A.n_slices) && i2 < A.n;
+        const bool on = i < A.n, on2 = (s + nwarps < s_hi) && i2 < A.n;
         double xi = 0, pi = 0, qi = 0, ri = 0, di = 0, xi2 = 0, pi2 = 0, qi2 = 0, ri2 = 0, di2 = 0;
         // x is touched once per iteration and never gathered: streamed (evict-first) like the matrix
         if (on) { xi = __ldcs(A.x + i); pi = pnew[i]; qi = A.q[i]; ri = A.r[i]; di = A.dinv[i]; }
