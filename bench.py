@@ -551,14 +551,18 @@ def run_b200_small2d(args, w, rank, local_rank, world, dev):
     peak, peak_src = measured_peak()
     kern = {k: {"calls": c, "ms_per_launch": m / c} for k, (c, m) in ksum.items()}
     roofline = None
-    if "batch_bwd" in kern:
-        alg = 24 * nn * B                                     # read gbar, read u, write dL/df
-        ms = kern["batch_bwd"]["ms_per_launch"]
-        roofline = {"bound": "hbm", "kernel": "k_batch<adjoint> (one CTA per sample, matrix in shared memory)",
-                    "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak,
-                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "ms_per_launch": ms,
-                    "note": "shared-memory resident PCG: bound by the per-iteration latency inside a CTA, not by HBM",
-                    "max_iterations": its, "kernels": kern}
+    for key, kname, note in (("band_bwd", "dfe_band_bwd = k_band_rhs + k_band_solve + k_band_grad (banded Cholesky, a warp per 4 samples)",
+                              "two banded triangular solves per sample; bound by instruction issue / L2 reads of the shared factor, not by HBM"),
+                             ("batch_bwd", "k_batch<adjoint> (one CTA per sample, matrix in shared memory)",
+                              "shared-memory resident PCG: bound by the SpMV's shared-memory traffic, not by HBM")):
+        if key in kern:
+            alg = 24 * nn * B                                     # read gbar, read u, write dL/df
+            ms = kern[key]["ms_per_launch"]
+            roofline = {"bound": "hbm", "kernel": kname, "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": alg, "ms_per_launch": ms, "note": note, "max_iterations": its,
+                        "kernels": kern}
+            break
     if rank == 0:
         I = mesh._native(dev.index).info
         line = {"metric": "fem_fwd_adjoint_solves_per_s", "value": value, "unit": "solves/s", "n_gpus": world,

@@ -33,6 +33,7 @@ SYMBOLS = [
     "dfe_assemble", "dfe_eliminate", "dfe_pcg_workspace_bytes", "dfe_pcg", "dfe_scatter", "dfe_gather_free",
     "dfe_grad_workspace_bytes", "dfe_grad",
     "dfe_batch_supported", "dfe_batch_fwd", "dfe_batch_bwd",
+    "dfe_band_supported", "dfe_band_factor_bytes", "dfe_band_workspace_bytes", "dfe_band_factor", "dfe_band_fwd", "dfe_band_bwd",
 ]
 
 
@@ -153,6 +154,18 @@ def lib() -> C.CDLL:
     L.dfe_batch_fwd.argtypes = [vp, i64, vp, i64, vp, vp, vp, vp, i64, dbl, i64, vp, vp, vp, vp]
     L.dfe_batch_bwd.restype = ci
     L.dfe_batch_bwd.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, ci, vp, i64, vp, dbl, i64, vp, vp, vp, vp]
+    L.dfe_band_supported.restype = ci
+    L.dfe_band_supported.argtypes = [vp]
+    L.dfe_band_factor_bytes.restype = sz
+    L.dfe_band_factor_bytes.argtypes = [vp]
+    L.dfe_band_workspace_bytes.restype = sz
+    L.dfe_band_workspace_bytes.argtypes = [vp, i64]
+    L.dfe_band_factor.restype = ci
+    L.dfe_band_factor.argtypes = [vp, vp, vp, vp, vp]
+    L.dfe_band_fwd.restype = ci
+    L.dfe_band_fwd.argtypes = [vp, i64, vp, i64, vp, vp, vp, i64, vp, sz, vp]
+    L.dfe_band_bwd.restype = ci
+    L.dfe_band_bwd.argtypes = [vp, i64, vp, i64, vp, i64, vp, ci, vp, i64, vp, vp, sz, vp]
     if L.dfe_abi_version() != 1:
         raise RuntimeError("libdfe_b200.so ABI version mismatch")
     _lib = L

@@ -307,6 +307,250 @@ __global__ void __launch_bounds__(BT, (RPT <= 4 ? 2 : 1)) k_batch(const BArgs A)
   }
 }
 
+// =====================================================================================================================
+// Banded direct solver for the same job when the half bandwidth of K_free is <= 32 (rectangle(nx, ny) with nx <= 32
+// in the reference's node numbering): K_free = L L^T once per call (the batch shares the matrix), then two banded
+// triangular solves per sample.  That is ~13x fewer flops than ~120 Jacobi-PCG iterations at 961 unknowns and has
+// no reductions: a WARP owns BS samples, lane k holds the pending right-hand side of the rows = k (mod 32) of the
+// sliding 32-row window, and a step is  y = W[head] / L_ii  (one shuffle),  W -= L[.., i] y  (one coalesced 256 B
+// load of the column shared by the BS samples, one fma per sample).  Replaces solver.py:174 (LU with partial
+// pivoting on the dense K_free) more literally than PCG does.
+constexpr int BW = 32;   // half bandwidth supported: one lane per sub-diagonal
+constexpr int BS = 4;    // samples per warp (the factor is loaded once per BS samples)
+
+// One CTA: right-looking banded Cholesky with the active (BW+1) x (BW+1) window in shared memory.
+//   invd[i] = 1 / L_ii,  Lc[i*32 + d-1] = L[i+d][i],  Lr[i*32 + d-1] = L[i][i-d]   (d = 1..32; rows >= n: identity)
+__global__ void __launch_bounds__(512) k_band_factor(const MeshDev M, const double* __restrict__ vals_full, int npad,
+                                                     double* __restrict__ invd, double* __restrict__ Lc,
+                                                     double* __restrict__ Lr, int* __restrict__ status) {
+  __shared__ double sA[BW + 1][BW + 2];   // sA[r % 33][k] = A[r][r-k], rows j..j+32 of the trailing matrix
+  __shared__ double sl[BW + 1];
+  __shared__ double sd0[BW + 1];          // diagonal entries of the window's rows before elimination
+  __shared__ int sbad;
+  const int n = M.n_free, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < npad; i += 512) invd[i] = 1.0;
+  for (int i = tid; i < npad * BW; i += 512) { Lc[i] = 0.0; Lr[i] = 0.0; }
+  if (tid == 0) sbad = 0;
+  auto load_row = [&](int r) {   // by one warp
+    double* row = sA[r % (BW + 1)];
+    row[lane] = 0.0;
+    if (lane == 0) row[BW] = 0.0;
+    __syncwarp();
+    if (r < n)
+      for (int k = M.rowptr_f[r] + lane; k < M.rowptr_f[r + 1]; k += 32) {
+        const int c = M.col_f[k];
+        if (c <= r) row[r - c] = vals_full[M.src_f[k]];
+      }
+    __syncwarp();
+    if (lane == 0) sd0[r % (BW + 1)] = row[0];
+  };
+  for (int r = warp; r <= BW; r += 16) load_row(r);
+  __syncthreads();
+  for (int j = 0; j < n; ++j) {
+    const double d = sA[j % (BW + 1)][0];
+    // SPD check: a pivot that lost 12 digits against its diagonal entry means K_free is (numerically) singular — the
+    // reference returns garbage silently there, this library reports a breakdown
+    const bool ok = d > 1e-12 * sd0[j % (BW + 1)];
+    const double inv = ok ? 1.0 / sqrt(d) : 1.0;
+    if (!ok && tid == 0) sbad = 1;
+    if (tid == 0) invd[j] = inv;
+    if (tid >= 1 && tid <= BW) {
+      const int a = tid, r = j + a;
+      const double l = r < n ? sA[r % (BW + 1)][a] * inv : 0.0;
+      sl[a] = l;
+      if (r < n) {
+        Lc[static_cast<size_t>(j) * BW + a - 1] = l;
+        Lr[static_cast<size_t>(r) * BW + a - 1] = l;
+      }
+    }
+    __syncthreads();
+    for (int q = tid; q < BW * BW; q += 512) {   // A[j+a][j+b] -= l_a l_b,  1 <= b <= a <= 32
+      const int a = (q >> 5) + 1, b = (q & 31) + 1;
+      if (b <= a && j + a < n) sA[(j + a) % (BW + 1)][a - b] -= sl[a] * sl[b];
+    }
+    __syncthreads();
+    if (warp == 0) load_row(j + BW + 1);   // row j leaves the window, row j+33 takes its slot
+    __syncthreads();
+  }
+  if (tid == 0) *status = sbad ? 5 : 0;
+}
+
+// right-hand sides of the whole batch, (B, npad) row-major, rows >= n_free zero
+template <bool BWD>
+__global__ void k_band_rhs(const MeshDev M, long long B, int npad, const double* __restrict__ in, long long ldin,
+                           const double* __restrict__ vals_full, double* __restrict__ X) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= B * npad) return;
+  const long long b = idx / npad;
+  const int r = static_cast<int>(idx - b * npad);
+  double v = 0.0;
+  if (r < M.n_free) {
+    const int node = M.free_nodes[r];
+    const double* src = in + b * ldin;
+    if (BWD) {
+      v = src[node];
+    } else {
+      v = load_at(M, src, node);
+      for (int t = M.lift_ptr[r]; t < M.lift_ptr[r + 1]; ++t)
+        v = __dsub_rn(v, __dmul_rn(vals_full[M.lift_src[t]], M.lift_g[t]));   // solver.py:169
+    }
+  }
+  X[idx] = v;
+}
+
+// L y = b, then L^T x = y, in place on X; one warp per BS samples
+__global__ void __launch_bounds__(128) k_band_solve(int npad, long long B, const double* __restrict__ invd,
+                                                    const double* __restrict__ Lc, const double* __restrict__ Lr,
+                                                    double* __restrict__ X) {
+  const int lane = threadIdx.x & 31;
+  const long long b0 = (blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5)) * BS;
+  if (b0 >= B) return;
+  double* x[BS];
+  bool valid[BS];
+#pragma unroll
+  for (int s = 0; s < BS; ++s) {
+    valid[s] = b0 + s < B;
+    x[s] = X + (valid[s] ? b0 + s : b0) * npad;
+  }
+  const int nb = npad >> 5;
+  double W[BS], nxt[BS], keep[BS];
+  // ---- forward substitution, rows ascending
+#pragma unroll
+  for (int s = 0; s < BS; ++s) W[s] = x[s][lane];
+  for (int t = 0; t < nb; ++t) {
+#pragma unroll
+    for (int s = 0; s < BS; ++s) { nxt[s] = t + 1 < nb ? x[s][32 * (t + 1) + lane] : 0.0; keep[s] = 0.0; }
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+      const int i = 32 * t + q;
+      const double inv = invd[i];
+      const double lc = Lc[static_cast<size_t>(i) * BW + ((lane - q - 1) & 31)];   // L[i+d][i], d = ((lane-q-1)&31)+1
+#pragma unroll
+      for (int s = 0; s < BS; ++s) {
+        const double y = __shfl_sync(0xffffffffu, W[s], q) * inv;
+        if (lane == q) { keep[s] = y; W[s] = nxt[s]; }   // row i is done; this lane takes row i+32
+        W[s] = fma(-lc, y, W[s]);
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < BS; ++s)
+      if (valid[s]) x[s][32 * t + lane] = keep[s];
+  }
+  __syncwarp();
+  // ---- backward substitution, rows descending
+#pragma unroll
+  for (int s = 0; s < BS; ++s) W[s] = x[s][32 * (nb - 1) + lane];
+  for (int t = nb - 1; t >= 0; --t) {
+#pragma unroll
+    for (int s = 0; s < BS; ++s) { nxt[s] = t > 0 ? x[s][32 * (t - 1) + lane] : 0.0; keep[s] = 0.0; }
+#pragma unroll
+    for (int q = 31; q >= 0; --q) {
+      const int i = 32 * t + q;
+      const double inv = invd[i];
+      const double lr = Lr[static_cast<size_t>(i) * BW + ((q - lane - 1) & 31)];   // L[i][i-d], d = ((q-lane-1)&31)+1
+#pragma unroll
+      for (int s = 0; s < BS; ++s) {
+        const double xv = __shfl_sync(0xffffffffu, W[s], q) * inv;
+        if (lane == q) { keep[s] = xv; W[s] = nxt[s]; }   // row i is done; this lane takes row i-32
+        W[s] = fma(-lr, xv, W[s]);
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < BS; ++s)
+      if (valid[s]) x[s][32 * t + lane] = keep[s];
+  }
+}
+
+// forward: u = 0; u[d] = g; u[free] = x   (solver.py:177-181)
+__global__ void k_band_scatter(const MeshDev M, long long B, int npad, const double* __restrict__ X, double* __restrict__ u,
+                               long long ldu) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const int per = M.n_free + M.n_dir;
+  if (idx >= B * per) return;
+  const long long b = idx / per;
+  const int r = static_cast<int>(idx - b * per);
+  if (r < M.n_free) u[b * ldu + M.free_nodes[r]] = X[b * npad + r];
+  else u[b * ldu + M.dir_idx[r - M.n_free]] = M.dir_val[r - M.n_free];
+}
+
+// adjoint: dL/dkappa (per element, or summed per sample in a fixed order) and dL/df from lambda = X (0 on Dirichlet nodes)
+__global__ void __launch_bounds__(BT) k_band_grad(const MeshDev M, long long B, int npad, const double* __restrict__ X,
+                                                  const double* __restrict__ ufull, long long ldu, double* __restrict__ gk,
+                                                  int gk_per_elem, double* __restrict__ gf, long long ldgf) {
+  __shared__ double sred[2 * BNW];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (long long b = blockIdx.x; b < B; b += gridDim.x) {
+    const double* lamf = X + b * npad;
+    const double* u = ufull + b * ldu;
+    auto lam = [&](int node) { const int rk = M.free_rank[node]; return rk >= 0 ? lamf[rk] : 0.0; };
+    double gsum = 0.0, dummy = 0.0;
+    for (int e = tid; e < M.n_el; e += BT) {
+      double g = 0.0;
+      if (M.dim == 1) {
+        const int i = M.elems[2 * e], j = M.elems[2 * e + 1];
+        const double h = M.nodes[j] - M.nodes[i];
+        g = -(lam(j) - lam(i)) * (u[j] - u[i]) / h;
+      } else {
+        int nd[3];
+        const Elem2D E = elem2d(M, e, nd);
+        if (!(E.area < AREA_EPS)) {
+          double bl = 0, bu = 0, cl = 0, cu = 0;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const double l = lam(nd[c]), uu = u[nd[c]];
+            bl = fma(E.b[c], l, bl);
+            bu = fma(E.b[c], uu, bu);
+            cl = fma(E.c[c], l, cl);
+            cu = fma(E.c[c], uu, cu);
+          }
+          g = -(bl * bu + cl * cu) / (4.0 * E.area);
+        }
+      }
+      if (gk_per_elem) gk[b * M.n_el + e] = g;
+      else gsum += g;
+    }
+    if (!gk_per_elem) {
+      block_sum2(gsum, dummy, sred, lane, warp);
+      if (tid == 0) gk[b] = gsum;
+      __syncthreads();
+    }
+    if (gf) {
+      for (int pn = tid; pn < M.n_nodes; pn += BT) {
+        double g = 0.0;
+        for (int a = M.adj_ptr[pn]; a < M.adj_ptr[pn + 1]; ++a) {
+          const int e = M.adj_elem[a];
+          if (M.dim == 1) {
+            const int i = M.elems[2 * e], j = M.elems[2 * e + 1];
+            g = fma((M.nodes[j] - M.nodes[i]) * 0.5, lam(pn), g);
+          } else {
+            int nd[3];
+            const Elem2D E = elem2d(M, e, nd);
+            if (E.area < AREA_EPS) continue;
+            g = fma(E.area / 9.0, (lam(nd[0]) + lam(nd[1])) + lam(nd[2]), g);
+          }
+        }
+        gf[b * ldgf + pn] = g;
+      }
+    }
+  }
+}
+
+int band_width(const dfe_mesh* m) {   // max |row - col| over the pattern of K_free
+  long long w = 0;
+  const long long n = static_cast<long long>(m->h_rowptr_f.size()) - 1;
+  for (long long r = 0; r < n; ++r)
+    for (long long k = m->h_rowptr_f[r]; k < m->h_rowptr_f[r + 1]; ++k) {
+      const long long d = r > m->h_col_f[k] ? r - m->h_col_f[k] : m->h_col_f[k] - r;
+      if (d > w) w = d;
+    }
+  return static_cast<int>(w);
+}
+bool band_fits(const dfe_mesh* m) {
+  if (!m || m->info.device < 0 || m->dev.n_free < 1 || m->dev.n_free > (1 << 20)) return false;
+  return band_width(m) <= BW;
+}
+int band_npad(const dfe_mesh* m) { return ((m->dev.n_free + 31) / 32) * 32; }
+
 size_t batch_smem(const dfe_mesh* m, bool bwd) {
   const size_t snz = static_cast<size_t>(m->dev.sell_nnz);
   size_t d = snz + 32ull * m->dev.n_slices + 6 * BNW + (bwd ? static_cast<size_t>(m->dev.n_nodes) : 0);
@@ -414,6 +658,143 @@ extern "C" int dfe_batch_bwd(const dfe_mesh* m, int64_t B, const double* gbar, i
     A.tol = tol; A.maxit = static_cast<int>(maxit > 2000000000 ? 2000000000 : maxit);
     A.iters = iters; A.relres = relres; A.status = status;
     rc = dispatch<true>(m, A, static_cast<cudaStream_t>(stream));
+  }
+  if (prev != m->info.device) cudaSetDevice(prev);
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------------- banded direct ABI
+extern "C" int dfe_band_supported(const dfe_mesh* m) { return band_fits(m) ? 1 : 0; }
+
+extern "C" size_t dfe_band_factor_bytes(const dfe_mesh* m) {
+  if (!m) return 0;
+  const size_t np = static_cast<size_t>(band_npad(m));
+  return (np + 2 * np * BW) * sizeof(double) + 256;
+}
+extern "C" size_t dfe_band_workspace_bytes(const dfe_mesh* m, int64_t B) {
+  if (!m || B < 1) return 0;
+  return static_cast<size_t>(B) * band_npad(m) * sizeof(double);
+}
+
+namespace {
+struct BandPtrs {
+  double *invd, *Lc, *Lr;
+  int* status;
+};
+BandPtrs band_ptrs(const dfe_mesh* m, void* factor) {
+  const size_t np = static_cast<size_t>(band_npad(m));
+  BandPtrs p;
+  p.invd = static_cast<double*>(factor);
+  p.Lc = p.invd + np;
+  p.Lr = p.Lc + np * BW;
+  p.status = reinterpret_cast<int*>(p.Lr + np * BW);
+  return p;
+}
+int band_enter(const dfe_mesh* m, const char* who, int* prev) {
+  if (!m) {
+    dfe::set_error("%s: mesh is null", who);
+    return DFE_ERR_INVALID;
+  }
+  if (m->info.device < 0) {
+    dfe::set_error("%s: mesh handle is host-only; no CUDA device (this library has no CPU path)", who);
+    return DFE_ERR_CUDA;
+  }
+  if (!band_fits(m)) {
+    dfe::set_error("%s: half bandwidth of K_free is %d > %d; use dfe_batch_* (PCG) or the per-sample path", who, band_width(m), BW);
+    return DFE_ERR_UNSUPPORTED;
+  }
+  DFE_CUDA_OK(cudaGetDevice(prev));
+  if (*prev != m->info.device) DFE_CUDA_OK(cudaSetDevice(m->info.device));
+  return DFE_OK;
+}
+inline unsigned nblk(long long n, int t) { return static_cast<unsigned>((n + t - 1) / t > 0 ? (n + t - 1) / t : 1); }
+}  // namespace
+
+// K_free = L L^T from the assembled matrix (dfe_assemble); `factor` holds dfe_band_factor_bytes(m) bytes.  The status
+// word (0 ok, 5 = a pivot <= 0: K_free is not SPD) is the int at the end of the buffer; *status_dev (optional, device)
+// receives a copy.  Asynchronous.
+extern "C" int dfe_band_factor(const dfe_mesh* m, const double* vals_full, void* factor, int32_t* status_dev, void* stream) {
+  int prev;
+  int rc = band_enter(m, "dfe_band_factor", &prev);
+  if (rc) return rc;
+  if (!vals_full || !factor) {
+    dfe::set_error("dfe_band_factor: null argument");
+    rc = DFE_ERR_INVALID;
+  } else {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const BandPtrs p = band_ptrs(m, factor);
+    k_band_factor<<<1, 512, 0, st>>>(m->dev, vals_full, band_npad(m), p.invd, p.Lc, p.Lr, p.status);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && status_dev) e = cudaMemcpyAsync(status_dev, p.status, sizeof(int), cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) {
+      dfe::set_error("dfe_band_factor: %s", cudaGetErrorString(e));
+      rc = DFE_ERR_CUDA;
+    }
+  }
+  if (prev != m->info.device) cudaSetDevice(prev);
+  return rc;
+}
+
+extern "C" int dfe_band_fwd(const dfe_mesh* m, int64_t B, const double* f, int64_t ldf, const double* vals_full,
+                            const void* factor, double* u, int64_t ldu, void* ws, size_t ws_bytes, void* stream) {
+  int prev;
+  int rc = band_enter(m, "dfe_band_fwd", &prev);
+  if (rc) return rc;
+  if (!f || !vals_full || !factor || !u || !ws || B < 1) {
+    dfe::set_error("dfe_band_fwd: null / invalid argument");
+    rc = DFE_ERR_INVALID;
+  } else if (ws_bytes < dfe_band_workspace_bytes(m, B)) {
+    dfe::set_error("dfe_band_fwd: workspace %zu bytes < required %zu", ws_bytes, dfe_band_workspace_bytes(m, B));
+    rc = DFE_ERR_WORKSPACE;
+  } else {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int np = band_npad(m);
+    const BandPtrs p = band_ptrs(m, const_cast<void*>(factor));
+    double* X = static_cast<double*>(ws);
+    k_band_rhs<false><<<nblk(B * np, 256), 256, 0, st>>>(m->dev, B, np, f, ldf, vals_full, X);
+    k_band_solve<<<nblk((B + BS - 1) / BS, 4), 128, 0, st>>>(np, B, p.invd, p.Lc, p.Lr, X);
+    k_band_scatter<<<nblk(B * (m->dev.n_free + m->dev.n_dir), 256), 256, 0, st>>>(m->dev, B, np, X, u, ldu);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      dfe::set_error("dfe_band_fwd: kernel launch failed: %s", cudaGetErrorString(e));
+      rc = DFE_ERR_CUDA;
+    }
+  }
+  if (prev != m->info.device) cudaSetDevice(prev);
+  return rc;
+}
+
+extern "C" int dfe_band_bwd(const dfe_mesh* m, int64_t B, const double* gbar, int64_t ldg, const double* u, int64_t ldu,
+                            const void* factor, int kappa_mode, double* gf, int64_t ldgf, double* gkappa, void* ws,
+                            size_t ws_bytes, void* stream) {
+  int prev;
+  int rc = band_enter(m, "dfe_band_bwd", &prev);
+  if (rc) return rc;
+  if (!gbar || !u || !factor || !gkappa || !ws || B < 1) {
+    dfe::set_error("dfe_band_bwd: null / invalid argument");
+    rc = DFE_ERR_INVALID;
+  } else if (kappa_mode != DFE_KAPPA_SCALAR && kappa_mode != DFE_KAPPA_PER_ELEMENT) {
+    dfe::set_error("dfe_band_bwd: kappa_mode must be SCALAR or PER_ELEMENT (the batch shares one matrix)");
+    rc = DFE_ERR_INVALID;
+  } else if (ws_bytes < dfe_band_workspace_bytes(m, B)) {
+    dfe::set_error("dfe_band_bwd: workspace %zu bytes < required %zu", ws_bytes, dfe_band_workspace_bytes(m, B));
+    rc = DFE_ERR_WORKSPACE;
+  } else {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int np = band_npad(m);
+    const BandPtrs p = band_ptrs(m, const_cast<void*>(factor));
+    double* X = static_cast<double*>(ws);
+    k_band_rhs<true><<<nblk(B * np, 256), 256, 0, st>>>(m->dev, B, np, gbar, ldg, nullptr, X);
+    k_band_solve<<<nblk((B + BS - 1) / BS, 4), 128, 0, st>>>(np, B, p.invd, p.Lc, p.Lr, X);
+    long long grid = 8LL * m->sm_count;
+    if (grid > B) grid = B;
+    k_band_grad<<<static_cast<unsigned>(grid), BT, 0, st>>>(m->dev, B, np, X, u, ldu, gkappa,
+                                                             kappa_mode == DFE_KAPPA_PER_ELEMENT, gf, ldgf);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      dfe::set_error("dfe_band_bwd: kernel launch failed: %s", cudaGetErrorString(e));
+      rc = DFE_ERR_CUDA;
+    }
   }
   if (prev != m->info.device) cudaSetDevice(prev);
   return rc;

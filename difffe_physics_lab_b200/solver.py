@@ -38,7 +38,8 @@ class KernelTimer:
 
     _active: Optional["KernelTimer"] = None
     # kernels of libdfe_b200 launched per ABI call (default pipelined 1-D path: k1d_pipe_ck + k1d_pipe [+ k1d_pipe_gk])
-    KERNELS_PER_CALL = {"solve1d_fwd": 2, "solve1d_bwd": 3, "batch_fwd": 1, "batch_bwd": 1, "assemble": 1, "eliminate": 2, "pcg": 1, "scatter": 1,
+    KERNELS_PER_CALL = {"solve1d_fwd": 2, "solve1d_bwd": 3, "batch_fwd": 1, "batch_bwd": 1, "band_factor": 1,
+                        "band_fwd": 3, "band_bwd": 3, "assemble": 1, "eliminate": 2, "pcg": 1, "scatter": 1,
                         "gather": 1, "grad": 3}
 
     def __init__(self):
@@ -135,13 +136,16 @@ class _FESolve(torch.autograd.Function):
                                                     ws.numel(), _stream(dev)))
             else:
                 # many samples, one matrix, small mesh: one CTA per sample (config 5b)
-                ctx.batch = (B >= int(opts.get("batch_min", 2)) and mode in (_native.KAPPA_SCALAR, _native.KAPPA_PER_ELEMENT)
-                             and bool(L.dfe_batch_supported(nm.handle)))
-                saved_mats = (_batch_forward if ctx.batch else _general_forward)(L, nm, f, kappa, mode, u, opts)
+                # many samples, one matrix: banded direct solver or one-CTA-per-sample PCG (config 5b)
+                ctx.batch = None
+                if B >= int(opts.get("batch_min", 2)) and mode in (_native.KAPPA_SCALAR, _native.KAPPA_PER_ELEMENT):
+                    ctx.batch = _batch_solver(L, nm, opts)
+                fwd = {"band": _band_forward, "pcg": _batch_forward, None: _general_forward}[ctx.batch]
+                saved_mats = fwd(L, nm, f, kappa, mode, u, opts)
         ctx.mesh, ctx.mode, ctx.opts, ctx.fused = mesh, mode, opts, fused
         ctx.mats = saved_mats
         if fused:
-            ctx.batch = False
+            ctx.batch = None
         ctx.save_for_backward(u, kappa)
         return u
 
@@ -165,7 +169,9 @@ class _FESolve(torch.autograd.Function):
                                                     u.stride(0), kappa.data_ptr(), ctx.mode, int(ctx.opts["n_refine"]),
                                                     _ptr(gf), gf.stride(0) if gf is not None else n, gk.data_ptr(),
                                                     ws.data_ptr(), ws.numel(), _stream(dev)))
-            elif ctx.batch:
+            elif ctx.batch == "band":
+                _band_backward(L, nm, gbar, u, kappa, ctx.mode, ctx.mats, gf, gk, ctx.opts)
+            elif ctx.batch == "pcg":
                 _batch_backward(L, nm, gbar, u, kappa, ctx.mode, ctx.mats, gf, gk, ctx.opts)
             else:
                 _general_backward(L, nm, gbar, u, kappa, ctx.mode, ctx.mats, gf, gk, ctx.opts)
@@ -185,6 +191,62 @@ def _raise_batch_status(status, iters, relres, tol, what):
     raise _native.BreakdownError(_native.ERR_BREAKDOWN,
                                  f"{what}: breakdown in sample {b} at iteration {int(iters[b])} (p^T K p <= 0 or non-finite): "
                                  "K_free is not SPD — does the mesh have a Dirichlet node?")
+
+
+def _batch_solver(L, nm, opts):
+    """Which batched route a shared-matrix batch takes: 'band' (direct, half bandwidth <= 32), 'pcg' (one CTA per
+    sample, matrix in shared memory) or None (per-sample cooperative PCG)."""
+    want = opts.get("batch_solver", "auto")
+    if want in ("auto", "band") and L.dfe_band_supported(nm.handle):
+        return "band"
+    if want in ("auto", "pcg") and L.dfe_batch_supported(nm.handle):
+        return "pcg"
+    return None
+
+
+def _band_forward(L, nm, f, kappa, mode, u, opts):
+    """Shared matrix with half bandwidth <= 32: K_free = L L^T once, two banded triangular solves per sample."""
+    dev = f.device
+    I = nm.info
+    B = f.shape[0]
+    st = _stream(dev)
+    amode = _native.KAPPA_SCALAR if mode == _native.KAPPA_SCALAR else _native.KAPPA_PER_ELEMENT
+    vals = torch.empty(max(I.nnz_full, 1), dtype=torch.float64, device=dev)
+    F0 = torch.empty(I.n_nodes, dtype=torch.float64, device=dev)
+    with _timed("assemble", dev):
+        _native.check(L.dfe_assemble(nm.handle, kappa.reshape(-1).data_ptr(), amode, f[0].data_ptr(), vals.data_ptr(),
+                                     F0.data_ptr(), st))
+    factor = _ws(L.dfe_band_factor_bytes(nm.handle), dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    with _timed("band_factor", dev):
+        _native.check(L.dfe_band_factor(nm.handle, vals.data_ptr(), factor.data_ptr(), status.data_ptr(), st))
+    ws = _ws(L.dfe_band_workspace_bytes(nm.handle, B), dev)
+    with _timed("band_fwd", dev):
+        _native.check(L.dfe_band_fwd(nm.handle, B, f.data_ptr(), f.stride(0), vals.data_ptr(), factor.data_ptr(),
+                                     u.data_ptr(), u.stride(0), ws.data_ptr(), ws.numel(), st))
+    if int(status) != 0:              # one synchronisation per call
+        raise _native.BreakdownError(_native.ERR_BREAKDOWN, "dfe_band_factor: a pivot of the Cholesky factorisation is <= 0: "
+                                     "K_free is not SPD — does the mesh have a Dirichlet node?")
+    opts["last_pcg"] = [(0, 0.0)]     # direct solve: no iterations
+    return [("band", factor)]
+
+
+def _band_backward(L, nm, gbar, u, kappa, mode, mats, gf, gk, opts):
+    dev = u.device
+    I = nm.info
+    B = u.shape[0]
+    st = _stream(dev)
+    factor = mats[0][1]
+    gmode = _native.KAPPA_SCALAR if mode == _native.KAPPA_SCALAR else _native.KAPPA_PER_ELEMENT
+    nk = 1 if gmode == _native.KAPPA_SCALAR else I.n_elements
+    gk_b = torch.empty((B, nk), dtype=torch.float64, device=dev)
+    ws = _ws(L.dfe_band_workspace_bytes(nm.handle, B), dev)
+    with _timed("band_bwd", dev):
+        _native.check(L.dfe_band_bwd(nm.handle, B, gbar.data_ptr(), gbar.stride(0), u.data_ptr(), u.stride(0),
+                                     factor.data_ptr(), gmode, _ptr(gf), gf.stride(0) if gf is not None else I.n_nodes,
+                                     gk_b.data_ptr(), ws.data_ptr(), ws.numel(), st))
+    opts["last_pcg_adjoint"] = [(0, 0.0)]
+    gk.copy_(gk_b.sum(dim=0).reshape(gk.shape))   # torch.sum on CUDA is deterministic (no atomics)
 
 
 def _batch_forward(L, nm, f, kappa, mode, u, opts):

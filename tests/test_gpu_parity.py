@@ -444,12 +444,24 @@ def test_2d_batched_small_systems_kernel():
     B = 700
     f = rng.uniform(0, 1, (B, m.n_nodes))
     gbar = rng.standard_normal((B, m.n_nodes))
-    u, gk, gf, s = run(m, 0.8, f, gbar)
-    assert s.last_pcg[0][0] > 0
-    tot, mag = 0.0, 0.0
-    for b in list(range(0, B, 97)) + [B - 1]:
-        uo, gko, gfo = oracle_run(m, 0.8, f[b], gbar[b])
-        assert relerr(u[b], uo) <= TOL2D and np.abs(gf[b] - gfo).max() <= TOL2D * np.abs(gfo).max()
+    assert L.dfe_band_supported(m._native(torch.cuda.current_device()).handle) == 1
+    for route in ("band", "pcg"):            # banded Cholesky (default for this mesh) and one-CTA-per-sample PCG
+        k = torch.tensor(0.8, dtype=torch.float64, device="cuda", requires_grad=True)
+        ft = torch.tensor(f, device="cuda", requires_grad=True)
+        s = DifferentiableFESolver(m, kappa=k)
+        s._opts["batch_solver"] = route
+        ut = s(ft)
+        (ut * torch.tensor(gbar, device="cuda")).sum().backward()
+        assert (s.last_pcg[0][0] > 0) == (route == "pcg")
+        u, gf = ut.detach().cpu().numpy(), ft.grad.cpu().numpy()
+        tot, mag = 0.0, 0.0
+        for b in list(range(0, B, 97)) + [B - 1]:
+            uo, gko, gfo = oracle_run(m, 0.8, f[b], gbar[b])
+            assert relerr(u[b], uo) <= TOL2D and np.abs(gf[b] - gfo).max() <= TOL2D * np.abs(gfo).max()
+        if route == "band":
+            u_band, gk_band = u, float(k.grad)
+        else:
+            assert relerr(u, u_band) <= 1e-11 and abs(float(k.grad) - gk_band) <= 1e-10 * abs(gk_band)
     # (b) batched route == per-sample route (same arithmetic for F, lifting, SpMV; different reduction trees)
     B = 6
     k = torch.tensor(1.7, dtype=torch.float64, device="cuda", requires_grad=True)
@@ -480,16 +492,31 @@ def test_2d_batched_small_systems_kernel():
         assert relerr(u[b], uo) <= TOL2D and np.abs(gf[b] - gfo).max() <= TOL2D * np.abs(gfo).max()
         gsum += gko
     assert np.abs(gk - gsum).max() <= TOL2D * np.abs(gsum).max()
-    # (d) largest mesh the kernel takes (4 slices per warp), and one beyond it (per-sample route)
+    # (d) largest mesh the shared-memory PCG kernel takes (bandwidth 46 > 32: no banded route), and one beyond it
     m = FEMesh.rectangle(45, 44)
     assert m.n_nodes - len(m.dirichlet_nodes) == 44 * 43
     assert L.dfe_batch_supported(m._native(torch.cuda.current_device()).handle) == 1
+    assert L.dfe_band_supported(m._native(torch.cuda.current_device()).handle) == 0
     f = rng.uniform(0, 1, (3, m.n_nodes))
     gbar = rng.standard_normal((3, m.n_nodes))
     u, gk, gf, _ = run(m, 1.1, f, gbar)
     uo, gko, gfo = oracle_run(m, 1.1, f[2], gbar[2])
     assert relerr(u[2], uo) <= TOL2D and np.abs(gf[2] - gfo).max() <= TOL2D * np.abs(gfo).max()
     assert L.dfe_batch_supported(FEMesh.rectangle(60, 60)._native(torch.cuda.current_device()).handle) == 0
+    # long thin mesh: too many unknowns for the shared-memory kernel, but banded (half bandwidth 9): direct route
+    m = FEMesh.rectangle(8, 400, y_range=(0.0, 30.0), bc_value=0.05)
+    assert L.dfe_batch_supported(m._native(torch.cuda.current_device()).handle) == 0
+    assert L.dfe_band_supported(m._native(torch.cuda.current_device()).handle) == 1
+    f = rng.uniform(0, 1, (5, m.n_nodes))
+    gbar = rng.standard_normal((5, m.n_nodes))
+    u, gk, gf, _ = run(m, 0.6, f, gbar)
+    tot, mag = 0.0, 0.0
+    for b in range(5):
+        uo, gko, gfo = oracle_run(m, 0.6, f[b], gbar[b])
+        assert relerr(u[b], uo) <= TOL2D and np.abs(gf[b] - gfo).max() <= TOL2D * np.abs(gfo).max()
+        tot += gko.sum()
+        mag += np.abs(gko).sum()
+    assert abs(float(gk) - tot) <= TOL2D * mag
     # (e) 1-D mesh that is not a chain (interior Dirichlet node): general path, batched
     m = FEMesh.line(50, bc_left=0.1, bc_right=0.4)
     m.dirichlet_nodes[20] = -0.3
@@ -534,7 +561,14 @@ def test_pcg_error_reporting():
     with pytest.raises(_native.NotConvergedError):
         DifferentiableFESolver(m, pcg_maxit=3)(f)
     with pytest.raises(_native.NotConvergedError):          # the batched one-CTA-per-sample kernel reports it too
-        DifferentiableFESolver(m, pcg_maxit=3)(torch.ones((4, m.n_nodes), dtype=torch.float64, device="cuda"))
+        sb = DifferentiableFESolver(m, pcg_maxit=3)
+        sb._opts["batch_solver"] = "pcg"
+        sb(torch.ones((4, m.n_nodes), dtype=torch.float64, device="cuda"))
+    m = FEMesh.rectangle(6, 6)
+    m.dirichlet_nodes = {}
+    with pytest.raises(_native.DfeError):                   # banded Cholesky: zero pivot of the singular K
+        DfeS = DifferentiableFESolver(m)
+        DfeS(torch.ones((3, 49), dtype=torch.float64, device="cuda"))
     m = FEMesh.rectangle(6, 6)
     m.dirichlet_nodes = {}              # singular K: the reference silently returns garbage
     with pytest.raises(_native.DfeError):
