@@ -320,7 +320,7 @@ constexpr int BS = 4;    // samples per warp (the factor is loaded once per BS s
 
 // One CTA: right-looking banded Cholesky with the active (BW+1) x (BW+1) window in shared memory.
 //   invd[i] = 1 / L_ii,  Lc[i*32 + d-1] = L[i+d][i],  Lr[i*32 + d-1] = L[i][i-d]   (d = 1..32; rows >= n: identity)
-__global__ void __launch_bounds__(512) k_band_factor(const MeshDev M, const double* __restrict__ vals_full, int npad,
+__global__ void __launch_bounds__(256) k_band_factor(const MeshDev M, const double* __restrict__ vals_full, int npad,
                                                      double* __restrict__ invd, double* __restrict__ Lc,
                                                      double* __restrict__ Lr, int* __restrict__ status) {
   __shared__ double sA[BW + 1][BW + 2];   // sA[r % 33][k] = A[r][r-k], rows j..j+32 of the trailing matrix
@@ -328,8 +328,8 @@ __global__ void __launch_bounds__(512) k_band_factor(const MeshDev M, const doub
   __shared__ double sd0[BW + 1];          // diagonal entries of the window's rows before elimination
   __shared__ int sbad;
   const int n = M.n_free, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < npad; i += 512) invd[i] = 1.0;
-  for (int i = tid; i < npad * BW; i += 512) { Lc[i] = 0.0; Lr[i] = 0.0; }
+  for (int i = tid; i < npad; i += 256) invd[i] = 1.0;
+  for (int i = tid; i < npad * BW; i += 256) { Lc[i] = 0.0; Lr[i] = 0.0; }
   if (tid == 0) sbad = 0;
   auto load_row = [&](int r) {   // by one warp
     double* row = sA[r % (BW + 1)];
@@ -344,14 +344,14 @@ __global__ void __launch_bounds__(512) k_band_factor(const MeshDev M, const doub
     __syncwarp();
     if (lane == 0) sd0[r % (BW + 1)] = row[0];
   };
-  for (int r = warp; r <= BW; r += 16) load_row(r);
+  for (int r = warp; r <= BW; r += 8) load_row(r);
   __syncthreads();
   for (int j = 0; j < n; ++j) {
     const double d = sA[j % (BW + 1)][0];
     // SPD check: a pivot that lost 12 digits against its diagonal entry means K_free is (numerically) singular — the
     // reference returns garbage silently there, this library reports a breakdown
     const bool ok = d > 1e-12 * sd0[j % (BW + 1)];
-    const double inv = ok ? 1.0 / sqrt(d) : 1.0;
+    const double inv = ok ? rsqrt(d) : 1.0;
     if (!ok && tid == 0) sbad = 1;
     if (tid == 0) invd[j] = inv;
     if (tid >= 1 && tid <= BW) {
@@ -364,41 +364,104 @@ __global__ void __launch_bounds__(512) k_band_factor(const MeshDev M, const doub
       }
     }
     __syncthreads();
-    for (int q = tid; q < BW * BW; q += 512) {   // A[j+a][j+b] -= l_a l_b,  1 <= b <= a <= 32
-      const int a = (q >> 5) + 1, b = (q & 31) + 1;
-      if (b <= a && j + a < n) sA[(j + a) % (BW + 1)][a - b] -= sl[a] * sl[b];
+    // warps 1..7: A[j+a][j+b] -= l_a l_b, 1 <= b <= a <= 32; warp 0 meanwhile loads row j+33 into the slot of row j
+    // (whose pivot was read before the barrier; the update never touches that slot)
+    if (warp == 0) {
+      load_row(j + BW + 1);
+    } else {
+      for (int q = tid - 32; q < BW * BW; q += 224) {
+        const int a = (q >> 5) + 1, b = (q & 31) + 1;
+        if (b <= a && j + a < n) sA[(j + a) % (BW + 1)][a - b] -= sl[a] * sl[b];
+      }
     }
-    __syncthreads();
-    if (warp == 0) load_row(j + BW + 1);   // row j leaves the window, row j+33 takes its slot
     __syncthreads();
   }
   if (tid == 0) *status = sbad ? 5 : 0;
 }
 
-// right-hand sides of the whole batch, (B, npad) row-major, rows >= n_free zero
-template <bool BWD>
-__global__ void k_band_rhs(const MeshDev M, long long B, int npad, const double* __restrict__ in, long long ldin,
-                           const double* __restrict__ vals_full, double* __restrict__ X) {
+// Per-element constants shared by every sample of the batch (8 doubles per element):
+//   [0] area/3 (load weight, solver.py:143-145; -1 marks a skipped / degenerate element)   [1] area/9 (dL/df weight)
+//   [2..4] b_p   [5..7] c_p  (2-D);   1-D: [0] h/2 as the reference rounds it  [1] h/2  [2] h
+__global__ void k_band_geom(const MeshDev M, double* __restrict__ geom) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= M.n_el) return;
+  const size_t ne = static_cast<size_t>(M.n_el);   // structure of arrays: component k of element e at geom[k * n_el + e]
+  double g[8];
+  if (M.dim == 1) {
+    const int i = M.elems[2 * e], j = M.elems[2 * e + 1];
+    const double h = __dsub_rn(M.nodes[j], M.nodes[i]);
+    g[0] = __ddiv_rn(h, 2.0);
+    g[1] = (M.nodes[j] - M.nodes[i]) * 0.5;
+    g[2] = M.nodes[j] - M.nodes[i];
+    g[3] = g[4] = g[5] = g[6] = g[7] = 0.0;
+  } else {
+    int nd[3];
+    const Elem2D E = elem2d(M, e, nd);
+    const bool skip = E.area < AREA_EPS;
+    g[0] = skip ? -1.0 : __ddiv_rn(E.area, 3.0);
+    g[1] = skip ? -1.0 : E.area / 9.0;
+    g[2] = E.b[0]; g[3] = E.b[1]; g[4] = E.b[2];
+    g[5] = E.c[0]; g[6] = E.c[1]; g[7] = E.c[2];
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) geom[k * ne + e] = g[k];
+}
+
+// right-hand sides of the whole batch, (B, npad) row-major, rows >= n_free zero.
+// adjoint: gbar restricted to the free rows
+__global__ void k_band_rhs_bwd(const MeshDev M, long long B, int npad, const double* __restrict__ gbar, long long ldg,
+                               double* __restrict__ X) {
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (idx >= B * npad) return;
   const long long b = idx / npad;
   const int r = static_cast<int>(idx - b * npad);
-  double v = 0.0;
-  if (r < M.n_free) {
-    const int node = M.free_nodes[r];
-    const double* src = in + b * ldin;
-    if (BWD) {
-      v = src[node];
-    } else {
-      v = load_at(M, src, node);
-      for (int t = M.lift_ptr[r]; t < M.lift_ptr[r + 1]; ++t)
-        v = __dsub_rn(v, __dmul_rn(vals_full[M.lift_src[t]], M.lift_g[t]));   // solver.py:169
+  X[idx] = r < M.n_free ? gbar[b * ldg + M.free_nodes[r]] : 0.0;
+}
+// forward: one CTA per sample — f_b and the per-element terms (area/3) * (f_i+f_j+f_k)/3 (solver.py:143-145) in shared
+// memory, then every free row adds the terms of its adjacent elements in ascending element order and applies the
+// lifting in dict order (solver.py:165-169): the arithmetic of k_assemble / k_eliminate, bit for bit
+__global__ void __launch_bounds__(BT) k_band_rhs_fwd(const MeshDev M, long long B, int npad, const double* __restrict__ f,
+                                                     long long ldf, const double* __restrict__ vals_full,
+                                                     const double* __restrict__ geom, double* __restrict__ X) {
+  extern __shared__ double sg[];
+  double* sf = sg;               // [n_nodes]
+  double* st = sf + M.n_nodes;   // [n_el]
+  const int tid = threadIdx.x;
+  for (long long b = blockIdx.x; b < B; b += gridDim.x) {
+    const double* fb = f + b * ldf;
+    for (int p = tid; p < M.n_nodes; p += BT) sf[p] = fb[p];
+    __syncthreads();
+    if (M.dim == 2)
+      for (int e = tid; e < M.n_el; e += BT) {
+        const double w = geom[e];
+        const int n0 = M.elems[3 * e], n1 = M.elems[3 * e + 1], n2 = M.elems[3 * e + 2];
+        const double fc = __ddiv_rn(__dadd_rn(__dadd_rn(sf[n0], sf[n1]), sf[n2]), 3.0);
+        st[e] = w >= 0.0 ? __dmul_rn(w, fc) : 0.0;   // a skipped element adds nothing
+      }
+    __syncthreads();
+    for (int r = tid; r < npad; r += BT) {
+      double v = 0.0;
+      if (r < M.n_free) {
+        const int node = M.free_nodes[r];
+        for (int a = M.adj_ptr[node]; a < M.adj_ptr[node + 1]; ++a) {
+          const int e = M.adj_elem[a];
+          v = __dadd_rn(v, M.dim == 1 ? __dmul_rn(geom[e], sf[node]) : st[e]);
+        }
+        for (int t = M.lift_ptr[r]; t < M.lift_ptr[r + 1]; ++t)
+          v = __dsub_rn(v, __dmul_rn(vals_full[M.lift_src[t]], M.lift_g[t]));   // solver.py:169
+      }
+      X[b * npad + r] = v;
     }
+    __syncthreads();
   }
-  X[idx] = v;
 }
 
-// L y = b, then L^T x = y, in place on X; one warp per BS samples
+// L y = b, then L^T x = y, in place on X; one warp per BS samples.
+// Lane k holds two pending right-hand sides per sample: C = row k of the current 32-row block, N = row k of the next
+// one.  Step q (row i = 32 t + q): y = C[lane q] / L_ii (one shuffle, one multiply), then every lane subtracts
+// L[row][i] * y from the row it holds at distance d = 1..32 — lanes k > q from C (same block), lanes k <= q from N
+// (next block) — one coalesced 256 B load of column i for all BS samples.  C[lane q] is never touched after step q,
+// so the block's 32 results are C * (1 / L_ii) at the end of the block: no per-step capture.
 __global__ void __launch_bounds__(128) k_band_solve(int npad, long long B, const double* __restrict__ invd,
                                                     const double* __restrict__ Lc, const double* __restrict__ Lr,
                                                     double* __restrict__ X) {
@@ -413,51 +476,61 @@ __global__ void __launch_bounds__(128) k_band_solve(int npad, long long B, const
     x[s] = X + (valid[s] ? b0 + s : b0) * npad;
   }
   const int nb = npad >> 5;
-  double W[BS], nxt[BS], keep[BS];
+  double C[BS], N[BS];
   // ---- forward substitution, rows ascending
 #pragma unroll
-  for (int s = 0; s < BS; ++s) W[s] = x[s][lane];
+  for (int s = 0; s < BS; ++s) C[s] = x[s][lane];
   for (int t = 0; t < nb; ++t) {
 #pragma unroll
-    for (int s = 0; s < BS; ++s) { nxt[s] = t + 1 < nb ? x[s][32 * (t + 1) + lane] : 0.0; keep[s] = 0.0; }
+    for (int s = 0; s < BS; ++s) N[s] = t + 1 < nb ? x[s][32 * (t + 1) + lane] : 0.0;
+    const double invl = invd[32 * t + lane];
 #pragma unroll
     for (int q = 0; q < 32; ++q) {
       const int i = 32 * t + q;
-      const double inv = invd[i];
+      const double inv = invd[i];                                                    // uniform
       const double lc = Lc[static_cast<size_t>(i) * BW + ((lane - q - 1) & 31)];   // L[i+d][i], d = ((lane-q-1)&31)+1
+      // the coefficient is routed once per step (shared by the BS samples): two unconditional fmas per sample, one of
+      // which subtracts an exact zero
+      const double lcC = lane > q ? -lc : 0.0, lcN = lane > q ? 0.0 : -lc;
 #pragma unroll
       for (int s = 0; s < BS; ++s) {
-        const double y = __shfl_sync(0xffffffffu, W[s], q) * inv;
-        if (lane == q) { keep[s] = y; W[s] = nxt[s]; }   // row i is done; this lane takes row i+32
-        W[s] = fma(-lc, y, W[s]);
+        const double y = __shfl_sync(0xffffffffu, C[s], q) * inv;
+        C[s] = fma(lcC, y, C[s]);
+        N[s] = fma(lcN, y, N[s]);
       }
     }
 #pragma unroll
-    for (int s = 0; s < BS; ++s)
-      if (valid[s]) x[s][32 * t + lane] = keep[s];
+    for (int s = 0; s < BS; ++s) {
+      if (valid[s]) x[s][32 * t + lane] = C[s] * invl;
+      C[s] = N[s];
+    }
   }
   __syncwarp();
-  // ---- backward substitution, rows descending
+  // ---- backward substitution, rows descending (N = the block below)
 #pragma unroll
-  for (int s = 0; s < BS; ++s) W[s] = x[s][32 * (nb - 1) + lane];
+  for (int s = 0; s < BS; ++s) C[s] = x[s][32 * (nb - 1) + lane];
   for (int t = nb - 1; t >= 0; --t) {
 #pragma unroll
-    for (int s = 0; s < BS; ++s) { nxt[s] = t > 0 ? x[s][32 * (t - 1) + lane] : 0.0; keep[s] = 0.0; }
+    for (int s = 0; s < BS; ++s) N[s] = t > 0 ? x[s][32 * (t - 1) + lane] : 0.0;
+    const double invl = invd[32 * t + lane];
 #pragma unroll
     for (int q = 31; q >= 0; --q) {
       const int i = 32 * t + q;
       const double inv = invd[i];
       const double lr = Lr[static_cast<size_t>(i) * BW + ((q - lane - 1) & 31)];   // L[i][i-d], d = ((q-lane-1)&31)+1
+      const double lrC = lane < q ? -lr : 0.0, lrN = lane < q ? 0.0 : -lr;
 #pragma unroll
       for (int s = 0; s < BS; ++s) {
-        const double xv = __shfl_sync(0xffffffffu, W[s], q) * inv;
-        if (lane == q) { keep[s] = xv; W[s] = nxt[s]; }   // row i is done; this lane takes row i-32
-        W[s] = fma(-lr, xv, W[s]);
+        const double xv = __shfl_sync(0xffffffffu, C[s], q) * inv;
+        C[s] = fma(lrC, xv, C[s]);
+        N[s] = fma(lrN, xv, N[s]);
       }
     }
 #pragma unroll
-    for (int s = 0; s < BS; ++s)
-      if (valid[s]) x[s][32 * t + lane] = keep[s];
+    for (int s = 0; s < BS; ++s) {
+      if (valid[s]) x[s][32 * t + lane] = C[s] * invl;
+      C[s] = N[s];
+    }
   }
 }
 
@@ -473,37 +546,49 @@ __global__ void k_band_scatter(const MeshDev M, long long B, int npad, const dou
   else u[b * ldu + M.dir_idx[r - M.n_free]] = M.dir_val[r - M.n_free];
 }
 
-// adjoint: dL/dkappa (per element, or summed per sample in a fixed order) and dL/df from lambda = X (0 on Dirichlet nodes)
+// adjoint: dL/dkappa (per element, or summed per sample in a fixed order) and dL/df from lambda = X (0 on Dirichlet
+// nodes).  One CTA per sample: lambda on all nodes and the per-element sums lambda_i+lambda_j+lambda_k in shared memory.
 __global__ void __launch_bounds__(BT) k_band_grad(const MeshDev M, long long B, int npad, const double* __restrict__ X,
-                                                  const double* __restrict__ ufull, long long ldu, double* __restrict__ gk,
+                                                  const double* __restrict__ ufull, long long ldu,
+                                                  const double* __restrict__ geom, double* __restrict__ gk,
                                                   int gk_per_elem, double* __restrict__ gf, long long ldgf) {
-  __shared__ double sred[2 * BNW];
+  extern __shared__ double sg[];
+  double* slam = sg;                 // [n_nodes]
+  double* su = slam + M.n_nodes;     // [n_nodes]
+  double* ssum = su + M.n_nodes;     // [n_el]
+  double* sred = ssum + M.n_el;      // [2 * BNW]
+  const size_t ne = static_cast<size_t>(M.n_el);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (long long b = blockIdx.x; b < B; b += gridDim.x) {
     const double* lamf = X + b * npad;
-    const double* u = ufull + b * ldu;
-    auto lam = [&](int node) { const int rk = M.free_rank[node]; return rk >= 0 ? lamf[rk] : 0.0; };
+    const double* ug = ufull + b * ldu;
+    for (int p = tid; p < M.n_nodes; p += BT) {
+      const int rk = M.free_rank[p];
+      slam[p] = rk >= 0 ? lamf[rk] : 0.0;
+      su[p] = ug[p];
+    }
+    const double* u = su;
+    __syncthreads();
     double gsum = 0.0, dummy = 0.0;
     for (int e = tid; e < M.n_el; e += BT) {
+      double ge[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) ge[k] = (k == 1) ? 0.0 : geom[k * ne + e];
       double g = 0.0;
       if (M.dim == 1) {
         const int i = M.elems[2 * e], j = M.elems[2 * e + 1];
-        const double h = M.nodes[j] - M.nodes[i];
-        g = -(lam(j) - lam(i)) * (u[j] - u[i]) / h;
+        g = -(slam[j] - slam[i]) * (u[j] - u[i]) / ge[2];
       } else {
-        int nd[3];
-        const Elem2D E = elem2d(M, e, nd);
-        if (!(E.area < AREA_EPS)) {
-          double bl = 0, bu = 0, cl = 0, cu = 0;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const double l = lam(nd[c]), uu = u[nd[c]];
-            bl = fma(E.b[c], l, bl);
-            bu = fma(E.b[c], uu, bu);
-            cl = fma(E.c[c], l, cl);
-            cu = fma(E.c[c], uu, cu);
-          }
-          g = -(bl * bu + cl * cu) / (4.0 * E.area);
+        const int n0 = M.elems[3 * e], n1 = M.elems[3 * e + 1], n2 = M.elems[3 * e + 2];
+        const double l0 = slam[n0], l1 = slam[n1], l2 = slam[n2];
+        ssum[e] = (l0 + l1) + l2;
+        if (ge[0] >= 0.0) {
+          const double u0 = u[n0], u1 = u[n1], u2 = u[n2];
+          const double bl = fma(ge[4], l2, fma(ge[3], l1, fma(ge[2], l0, 0.0)));
+          const double bu = fma(ge[4], u2, fma(ge[3], u1, fma(ge[2], u0, 0.0)));
+          const double cl = fma(ge[7], l2, fma(ge[6], l1, fma(ge[5], l0, 0.0)));
+          const double cu = fma(ge[7], u2, fma(ge[6], u1, fma(ge[5], u0, 0.0)));
+          g = -(bl * bu + cl * cu) / (12.0 * ge[0]);   // 4 area = 12 (area/3)
         }
       }
       if (gk_per_elem) gk[b * M.n_el + e] = g;
@@ -512,26 +597,21 @@ __global__ void __launch_bounds__(BT) k_band_grad(const MeshDev M, long long B, 
     if (!gk_per_elem) {
       block_sum2(gsum, dummy, sred, lane, warp);
       if (tid == 0) gk[b] = gsum;
-      __syncthreads();
     }
+    __syncthreads();   // ssum complete
     if (gf) {
       for (int pn = tid; pn < M.n_nodes; pn += BT) {
         double g = 0.0;
         for (int a = M.adj_ptr[pn]; a < M.adj_ptr[pn + 1]; ++a) {
           const int e = M.adj_elem[a];
-          if (M.dim == 1) {
-            const int i = M.elems[2 * e], j = M.elems[2 * e + 1];
-            g = fma((M.nodes[j] - M.nodes[i]) * 0.5, lam(pn), g);
-          } else {
-            int nd[3];
-            const Elem2D E = elem2d(M, e, nd);
-            if (E.area < AREA_EPS) continue;
-            g = fma(E.area / 9.0, (lam(nd[0]) + lam(nd[1])) + lam(nd[2]), g);
-          }
+          const double w9 = geom[ne + e];
+          if (M.dim == 1) g = fma(w9, slam[pn], g);
+          else if (w9 >= 0.0) g = fma(w9, ssum[e], g);
         }
         gf[b * ldgf + pn] = g;
       }
     }
+    __syncthreads();   // slam / ssum are reused by the next sample
   }
 }
 
@@ -546,7 +626,9 @@ int band_width(const dfe_mesh* m) {   // max |row - col| over the pattern of K_f
   return static_cast<int>(w);
 }
 bool band_fits(const dfe_mesh* m) {
-  if (!m || m->info.device < 0 || m->dev.n_free < 1 || m->dev.n_free > (1 << 20)) return false;
+  if (!m || m->info.device < 0 || m->dev.n_free < 1) return false;
+  // the gradient kernel keeps lambda (all nodes) and one sum per element in shared memory
+  if ((2 * static_cast<size_t>(m->dev.n_nodes) + m->dev.n_el + 2 * BNW) * sizeof(double) > 200 * 1024) return false;
   return band_width(m) <= BW;
 }
 int band_npad(const dfe_mesh* m) { return ((m->dev.n_free + 31) / 32) * 32; }
@@ -669,7 +751,7 @@ extern "C" int dfe_band_supported(const dfe_mesh* m) { return band_fits(m) ? 1 :
 extern "C" size_t dfe_band_factor_bytes(const dfe_mesh* m) {
   if (!m) return 0;
   const size_t np = static_cast<size_t>(band_npad(m));
-  return (np + 2 * np * BW) * sizeof(double) + 256;
+  return (np + 2 * np * BW + 8 * static_cast<size_t>(m->dev.n_el)) * sizeof(double) + 256;
 }
 extern "C" size_t dfe_band_workspace_bytes(const dfe_mesh* m, int64_t B) {
   if (!m || B < 1) return 0;
@@ -678,7 +760,7 @@ extern "C" size_t dfe_band_workspace_bytes(const dfe_mesh* m, int64_t B) {
 
 namespace {
 struct BandPtrs {
-  double *invd, *Lc, *Lr;
+  double *invd, *Lc, *Lr, *geom;
   int* status;
 };
 BandPtrs band_ptrs(const dfe_mesh* m, void* factor) {
@@ -687,7 +769,8 @@ BandPtrs band_ptrs(const dfe_mesh* m, void* factor) {
   p.invd = static_cast<double*>(factor);
   p.Lc = p.invd + np;
   p.Lr = p.Lc + np * BW;
-  p.status = reinterpret_cast<int*>(p.Lr + np * BW);
+  p.geom = p.Lr + np * BW;
+  p.status = reinterpret_cast<int*>(p.geom + 8 * static_cast<size_t>(m->dev.n_el));
   return p;
 }
 int band_enter(const dfe_mesh* m, const char* who, int* prev) {
@@ -723,7 +806,8 @@ extern "C" int dfe_band_factor(const dfe_mesh* m, const double* vals_full, void*
   } else {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const BandPtrs p = band_ptrs(m, factor);
-    k_band_factor<<<1, 512, 0, st>>>(m->dev, vals_full, band_npad(m), p.invd, p.Lc, p.Lr, p.status);
+    k_band_factor<<<1, 256, 0, st>>>(m->dev, vals_full, band_npad(m), p.invd, p.Lc, p.Lr, p.status);
+    k_band_geom<<<nblk(m->dev.n_el, 128), 128, 0, st>>>(m->dev, p.geom);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess && status_dev) e = cudaMemcpyAsync(status_dev, p.status, sizeof(int), cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) {
@@ -751,7 +835,11 @@ extern "C" int dfe_band_fwd(const dfe_mesh* m, int64_t B, const double* f, int64
     const int np = band_npad(m);
     const BandPtrs p = band_ptrs(m, const_cast<void*>(factor));
     double* X = static_cast<double*>(ws);
-    k_band_rhs<false><<<nblk(B * np, 256), 256, 0, st>>>(m->dev, B, np, f, ldf, vals_full, X);
+    const size_t rsm = (static_cast<size_t>(m->dev.n_nodes) + m->dev.n_el) * sizeof(double);
+    cudaFuncSetAttribute(k_band_rhs_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rsm));
+    long long rgrid = 8LL * m->sm_count;
+    if (rgrid > B) rgrid = B;
+    k_band_rhs_fwd<<<static_cast<unsigned>(rgrid), BT, rsm, st>>>(m->dev, B, np, f, ldf, vals_full, p.geom, X);
     k_band_solve<<<nblk((B + BS - 1) / BS, 4), 128, 0, st>>>(np, B, p.invd, p.Lc, p.Lr, X);
     k_band_scatter<<<nblk(B * (m->dev.n_free + m->dev.n_dir), 256), 256, 0, st>>>(m->dev, B, np, X, u, ldu);
     cudaError_t e = cudaGetLastError();
@@ -784,12 +872,19 @@ extern "C" int dfe_band_bwd(const dfe_mesh* m, int64_t B, const double* gbar, in
     const int np = band_npad(m);
     const BandPtrs p = band_ptrs(m, const_cast<void*>(factor));
     double* X = static_cast<double*>(ws);
-    k_band_rhs<true><<<nblk(B * np, 256), 256, 0, st>>>(m->dev, B, np, gbar, ldg, nullptr, X);
+    k_band_rhs_bwd<<<nblk(B * np, 256), 256, 0, st>>>(m->dev, B, np, gbar, ldg, X);
     k_band_solve<<<nblk((B + BS - 1) / BS, 4), 128, 0, st>>>(np, B, p.invd, p.Lc, p.Lr, X);
-    long long grid = 8LL * m->sm_count;
-    if (grid > B) grid = B;
-    k_band_grad<<<static_cast<unsigned>(grid), BT, 0, st>>>(m->dev, B, np, X, u, ldu, gkappa,
-                                                             kappa_mode == DFE_KAPPA_PER_ELEMENT, gf, ldgf);
+    const size_t gsm = (2 * static_cast<size_t>(m->dev.n_nodes) + m->dev.n_el + 2 * BNW) * sizeof(double);
+    if (gsm > 200 * 1024) {
+      dfe::set_error("dfe_band_bwd: mesh too large for the gradient kernel (%zu bytes of shared memory)", gsm);
+      rc = DFE_ERR_UNSUPPORTED;
+    } else {
+      cudaFuncSetAttribute(k_band_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(gsm));
+      long long grid = 8LL * m->sm_count;
+      if (grid > B) grid = B;
+      k_band_grad<<<static_cast<unsigned>(grid), BT, gsm, st>>>(m->dev, B, np, X, u, ldu, p.geom, gkappa,
+                                                                 kappa_mode == DFE_KAPPA_PER_ELEMENT, gf, ldgf);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
       dfe::set_error("dfe_band_bwd: kernel launch failed: %s", cudaGetErrorString(e));
