@@ -318,56 +318,77 @@ __global__ void __launch_bounds__(BT, (RPT <= 4 ? 2 : 1)) k_batch(const BArgs A)
 constexpr int BW = 32;   // half bandwidth supported: one lane per sub-diagonal
 constexpr int BS = 4;    // samples per warp (the factor is loaded once per BS samples)
 
-// One CTA: right-looking banded Cholesky with the active (BW+1) x (BW+1) window in shared memory.
+// Lower band of K_free, Ab[r * 33 + k] = K_free[r][r - k] (k = 0..32), scattered from the assembled matrix in parallel.
+// Rows n_free .. n_free + 34 are zero (the factor kernel prefetches past the end).
+__global__ void k_band_gather(const MeshDev M, const double* __restrict__ vals_full, double* __restrict__ Ab) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= M.n_free) return;
+  for (int k = M.rowptr_f[r]; k < M.rowptr_f[r + 1]; ++k) {
+    const int c = M.col_f[k];
+    if (c <= r) Ab[static_cast<size_t>(r) * (BW + 1) + (r - c)] = vals_full[M.src_f[k]];
+  }
+}
+
+// One CTA: right-looking banded Cholesky with the active (BW+1) x (BW+1) window in shared memory; the row that enters
+// the window at step j is prefetched from Ab two steps earlier (one global latency per step would otherwise be the
+// critical path of the whole factorisation).
 //   invd[i] = 1 / L_ii,  Lc[i*32 + d-1] = L[i+d][i],  Lr[i*32 + d-1] = L[i][i-d]   (d = 1..32; rows >= n: identity)
-__global__ void __launch_bounds__(256) k_band_factor(const MeshDev M, const double* __restrict__ vals_full, int npad,
+__global__ void __launch_bounds__(256) k_band_factor(int n, int npad, const double* __restrict__ Ab,
                                                      double* __restrict__ invd, double* __restrict__ Lc,
                                                      double* __restrict__ Lr, int* __restrict__ status) {
   __shared__ double sA[BW + 1][BW + 2];   // sA[r % 33][k] = A[r][r-k], rows j..j+32 of the trailing matrix
   __shared__ double sl[BW + 1];
   __shared__ double sd0[BW + 1];          // diagonal entries of the window's rows before elimination
   __shared__ int sbad;
-  const int n = M.n_free, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < npad; i += 256) invd[i] = 1.0;
-  for (int i = tid; i < npad * BW; i += 256) { Lc[i] = 0.0; Lr[i] = 0.0; }
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = n + tid; i < npad; i += 256) invd[i] = 1.0;
   if (tid == 0) sbad = 0;
-  auto load_row = [&](int r) {   // by one warp
-    double* row = sA[r % (BW + 1)];
-    row[lane] = 0.0;
-    if (lane == 0) row[BW] = 0.0;
-    __syncwarp();
-    if (r < n)
-      for (int k = M.rowptr_f[r] + lane; k < M.rowptr_f[r + 1]; k += 32) {
-        const int c = M.col_f[k];
-        if (c <= r) row[r - c] = vals_full[M.src_f[k]];
-      }
-    __syncwarp();
-    if (lane == 0) sd0[r % (BW + 1)] = row[0];
-  };
-  for (int r = warp; r <= BW; r += 8) load_row(r);
+  for (int q = tid; q < (BW + 1) * (BW + 1); q += 256) {   // rows 0..32
+    const int r = q / (BW + 1), k = q - r * (BW + 1);
+    const double v = Ab[static_cast<size_t>(r) * (BW + 1) + k];
+    sA[r][k] = v;
+    if (k == 0) sd0[r] = v;
+  }
+  // warp 0 keeps the next two incoming rows in registers (lane k holds entry k, lane 0 also entry 32)
+  double pa = 0.0, pa32 = 0.0, pb = 0.0, pb32 = 0.0;
+  if (warp == 0) {
+    pa = Ab[static_cast<size_t>(BW + 1) * (BW + 1) + lane];
+    pb = Ab[static_cast<size_t>(BW + 2) * (BW + 1) + lane];
+    if (lane == 0) {
+      pa32 = Ab[static_cast<size_t>(BW + 1) * (BW + 1) + BW];
+      pb32 = Ab[static_cast<size_t>(BW + 2) * (BW + 1) + BW];
+    }
+  }
   __syncthreads();
   for (int j = 0; j < n; ++j) {
-    const double d = sA[j % (BW + 1)][0];
+    const int sj = j % (BW + 1);
+    const double d = sA[sj][0];
     // SPD check: a pivot that lost 12 digits against its diagonal entry means K_free is (numerically) singular — the
     // reference returns garbage silently there, this library reports a breakdown
-    const bool ok = d > 1e-12 * sd0[j % (BW + 1)];
+    const bool ok = d > 1e-12 * sd0[sj];
     const double inv = ok ? rsqrt(d) : 1.0;
     if (!ok && tid == 0) sbad = 1;
     if (tid == 0) invd[j] = inv;
+    double pc = 0.0, pc32 = 0.0;
+    if (warp == 0) {   // prefetch row j + 35 (consumed at step j + 2)
+      pc = Ab[static_cast<size_t>(j + BW + 3) * (BW + 1) + lane];
+      if (lane == 0) pc32 = Ab[static_cast<size_t>(j + BW + 3) * (BW + 1) + BW];
+    }
     if (tid >= 1 && tid <= BW) {
       const int a = tid, r = j + a;
       const double l = r < n ? sA[r % (BW + 1)][a] * inv : 0.0;
       sl[a] = l;
-      if (r < n) {
-        Lc[static_cast<size_t>(j) * BW + a - 1] = l;
-        Lr[static_cast<size_t>(r) * BW + a - 1] = l;
-      }
+      Lc[static_cast<size_t>(j) * BW + a - 1] = l;
+      if (r < n) Lr[static_cast<size_t>(r) * BW + a - 1] = l;
     }
     __syncthreads();
-    // warps 1..7: A[j+a][j+b] -= l_a l_b, 1 <= b <= a <= 32; warp 0 meanwhile loads row j+33 into the slot of row j
+    // warps 1..7: A[j+a][j+b] -= l_a l_b, 1 <= b <= a <= 32; warp 0 meanwhile puts row j+33 into the slot of row j
     // (whose pivot was read before the barrier; the update never touches that slot)
     if (warp == 0) {
-      load_row(j + BW + 1);
+      sA[sj][lane] = pa;
+      if (lane == 0) { sA[sj][BW] = pa32; sd0[sj] = pa; }
+      pa = pb; pa32 = pb32;
+      pb = pc; pb32 = pc32;
     } else {
       for (int q = tid - 32; q < BW * BW; q += 224) {
         const int a = (q >> 5) + 1, b = (q & 31) + 1;
@@ -751,7 +772,7 @@ extern "C" int dfe_band_supported(const dfe_mesh* m) { return band_fits(m) ? 1 :
 extern "C" size_t dfe_band_factor_bytes(const dfe_mesh* m) {
   if (!m) return 0;
   const size_t np = static_cast<size_t>(band_npad(m));
-  return (np + 2 * np * BW + 8 * static_cast<size_t>(m->dev.n_el)) * sizeof(double) + 256;
+  return (np + 2 * np * BW + 8 * static_cast<size_t>(m->dev.n_el) + (np + 40) * (BW + 1)) * sizeof(double) + 256;
 }
 extern "C" size_t dfe_band_workspace_bytes(const dfe_mesh* m, int64_t B) {
   if (!m || B < 1) return 0;
@@ -760,7 +781,7 @@ extern "C" size_t dfe_band_workspace_bytes(const dfe_mesh* m, int64_t B) {
 
 namespace {
 struct BandPtrs {
-  double *invd, *Lc, *Lr, *geom;
+  double *invd, *Lc, *Lr, *geom, *Ab;
   int* status;
 };
 BandPtrs band_ptrs(const dfe_mesh* m, void* factor) {
@@ -770,7 +791,8 @@ BandPtrs band_ptrs(const dfe_mesh* m, void* factor) {
   p.Lc = p.invd + np;
   p.Lr = p.Lc + np * BW;
   p.geom = p.Lr + np * BW;
-  p.status = reinterpret_cast<int*>(p.geom + 8 * static_cast<size_t>(m->dev.n_el));
+  p.Ab = p.geom + 8 * static_cast<size_t>(m->dev.n_el);
+  p.status = reinterpret_cast<int*>(p.Ab + (np + 40) * (BW + 1));
   return p;
 }
 int band_enter(const dfe_mesh* m, const char* who, int* prev) {
@@ -806,9 +828,14 @@ extern "C" int dfe_band_factor(const dfe_mesh* m, const double* vals_full, void*
   } else {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const BandPtrs p = band_ptrs(m, factor);
-    k_band_factor<<<1, 256, 0, st>>>(m->dev, vals_full, band_npad(m), p.invd, p.Lc, p.Lr, p.status);
+    const size_t np = static_cast<size_t>(band_npad(m));
+    // invd | Lc | Lr zeroed (rows >= n_free and entries outside the band stay zero), Ab zeroed, then gathered
+    cudaError_t e = cudaMemsetAsync(p.invd, 0, (np + 2 * np * BW) * sizeof(double), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(p.Ab, 0, (np + 40) * (BW + 1) * sizeof(double), st);
+    k_band_gather<<<nblk(m->dev.n_free, 128), 128, 0, st>>>(m->dev, vals_full, p.Ab);
+    k_band_factor<<<1, 256, 0, st>>>(m->dev.n_free, band_npad(m), p.Ab, p.invd, p.Lc, p.Lr, p.status);
     k_band_geom<<<nblk(m->dev.n_el, 128), 128, 0, st>>>(m->dev, p.geom);
-    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e == cudaSuccess && status_dev) e = cudaMemcpyAsync(status_dev, p.status, sizeof(int), cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) {
       dfe::set_error("dfe_band_factor: %s", cudaGetErrorString(e));
