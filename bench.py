@@ -206,6 +206,33 @@ class ClockSampler:
         return out
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank (and therefore the pinned host buffers it first-touches) to the CPUs of its GPU's NUMA node:
+    with one rank per GPU the host->device copies of the e2e leg otherwise cross the socket interconnect.  Best
+    effort (pynvml + sysfs); returns a short description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:          # nvml pads the PCI domain to 8 hex digits, sysfs uses 4
+            bus = bus[4:]
+        base = pathlib.Path("/sys/bus/pci/devices") / bus
+        node = int((base / "numa_node").read_text().strip())
+        cpus = set()
+        for part in (base / "local_cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"numa node {node}, {len(cpus)} cpus"
+    except Exception as exc:  # no NUMA information: leave the default placement
+        return f"unbound ({type(exc).__name__})"
+    return "unbound"
+
+
 # ------------------------------------------------------------------------------- GPU arm
 def run_b200(args):
     import torch
@@ -222,6 +249,7 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device — the B200 arm has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    host_binding = bind_to_gpu_numa_node(local_rank) if world > 1 else "single rank: default placement"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -371,7 +399,7 @@ def run_b200(args):
         e2e = {"value": B * world * n_e2e / (ms_e2e * 1e-3), "unit": "solves/s",
                "h2d_bytes_per_step": int(f_host.numel() * 8 + k_host.numel() * 8),
                "d2h_bytes_per_step": int(gk_host.numel() * 8), "steps": n_e2e, "ms_per_step": ms_e2e / n_e2e,
-               "pipeline": f"{nsub} sub-batches, copy stream + compute stream"}
+               "pipeline": f"{nsub} sub-batches, copy stream + compute stream", "host_binding": host_binding}
         del f_host, f_dev
 
     clocks = sampler.stop()
