@@ -64,11 +64,6 @@ struct PP {
   long long* trace;           // debug (DFE_PIPE_TRACE=1): [3 CTAs][16 iterations][4 roles][8 events] clock64 stamps
 };
 
-__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -79,24 +74,6 @@ __device__ __forceinline__ void publish(unsigned long long* slot, double s, doub
   if (b == SENT) b = 0x7FF8000000000000ull;
   st_relaxed_u64(slot, a);
   st_relaxed_u64(slot + 1, b);
-}
-// wait until the word is published; bounded (a stuck poll sets *err and returns 0 instead of hanging the GPU)
-__device__ __forceinline__ double poll_word(const unsigned long long* p, unsigned long long v, int* err, int* dead) {
-  if (v == SENT) {
-    int spins = 0;
-    while (true) {
-      v = ld_relaxed_u64(p);
-      if (v != SENT) break;
-      if (*reinterpret_cast<volatile int*>(dead)) { v = 0; break; }
-      if (++spins > (1 << 22)) {
-        *reinterpret_cast<volatile int*>(dead) = 1;
-        *reinterpret_cast<volatile int*>(err) = 1;
-        v = 0;
-        break;
-      }
-    }
-  }
-  return __longlong_as_double(static_cast<long long>(v));
 }
 __device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
@@ -111,10 +88,6 @@ __device__ __forceinline__ double two_sum_err(double a, double b) {
   const double bb = __dsub_rn(d, a);
   return __dadd_rn(__dsub_rn(a, __dsub_rn(d, bb)), __dsub_rn(b, bb));
 }
-__device__ __forceinline__ int mis_of(const double* g) {
-  return static_cast<int>((reinterpret_cast<uintptr_t>(g) >> 3) & 1);
-}
-
 // x += (value of lane - d), only where that lane exists: the shuffle's own predicate guards the add (3 instructions)
 __device__ __forceinline__ void scan_step(double& x, int d) {
   asm volatile(
@@ -139,12 +112,6 @@ __device__ __forceinline__ void warp_scan2(double& is, double& im, double& es, d
   if (lane == 0) { es = 0.0; em = 0.0; }
 }
 
-__device__ __forceinline__ void named_arrive(int id, int count) {
-  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-__device__ __forceinline__ void named_sync(int id, int count) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
 // 16-byte poll of one (s, m) pair; tearing is harmless: each word is individually "sentinel or final"
 __device__ __forceinline__ void ld_pair(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
   asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");

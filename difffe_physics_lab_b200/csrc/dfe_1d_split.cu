@@ -133,7 +133,6 @@ __device__ __forceinline__ double two_sum_err(double a, double b) {
 // smem: bars | wt | red | hsS | rhS | rows
 template <bool BWD>
 __global__ void __launch_bounds__(ST, 2) k1d_pass1(const PS p) {
-  constexpr int NB = BWD ? 1 : 2;   // row buffers: forward prefetches the next sample
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);               // [2]
   Tri* wt = reinterpret_cast<Tri*>(smem_raw + 64);                     // [SNW]

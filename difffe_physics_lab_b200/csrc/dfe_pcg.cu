@@ -48,7 +48,6 @@ struct PcgArgs {
   double* p0;
   double* p1;
   double* q;
-  unsigned int* barrier;  // grid barrier counter (zeroed before launch)
   double* part;   // [3 epochs][gridDim.x][2] exchange slots, pre-set to the sentinel
   double* out;    // [0]=iterations, [1]=relres, [2]=status (0 ok, 4 not converged, 5 breakdown)
   double tol;
@@ -128,7 +127,6 @@ __global__ void __launch_bounds__(PT, 1) k_pcg(const PcgArgs A) {
   const int s_hi = s_lo + per_cta < A.n_slices ? s_lo + per_cta : A.n_slices;
   const int gw = s_lo + (threadIdx.x >> 5);
   constexpr int nwarps = PW;
-  const int G = gridDim.x;
 
   // ---- init: x = 0, r = b, z = D^{-1} r, p buffers = 0
   double bb = 0.0, rz = 0.0;
@@ -353,7 +351,6 @@ extern "C" int dfe_pcg(const dfe_mesh* m, const double* sell_vals, const double*
     A.q = reinterpret_cast<double*>(w + pl.off_q);
     A.part = reinterpret_cast<double*>(w + pl.off_part);
     A.out = reinterpret_cast<double*>(w + pl.off_out);
-    A.barrier = reinterpret_cast<unsigned int*>(w + pl.off_bar);
     A.tol = tol;
     A.maxit = maxit;
     static const int backoff = [] { const char* e = getenv("DFE_PCG_BACKOFF"); return e ? atoi(e) : 250; }();
