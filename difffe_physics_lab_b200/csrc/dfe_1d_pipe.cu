@@ -16,8 +16,11 @@
 //
 // Prefix sums are kept in MOMENT form: a block of nodes contributes (s, m) with m = w - s*X_end, which makes
 // every combine a plain addition: W_i = W^thread_i + sum_before(m) + X_i * sum_before(s).  Scans are therefore
-// two-component add-scans (warp shuffles), chunk folds are plain sums; the affine part a + b*X_i is carried along
-// the thread's nodes incrementally (X_i = coordinate in half element lengths, from the mesh handle).
+// two-component add-scans, chunk folds are plain sums; the affine part a + b*X_i is carried along the thread's nodes
+// incrementally (X_i = coordinate in half element lengths, from the mesh handle).  The scan over the threads of a CTA
+// is done by the fold warps: a compute thread stores its (s, m) in shared memory and reads its CTA-wide exclusive
+// prefix back one iteration later (ncu: the two warp-shuffle scans per iteration were 29 % of the compute warps'
+// stall samples).
 //
 // Roles inside a CTA: W compute warps (never touch global memory); one fold warp per sweep (publishes the CTA's
 // totals, polls/folds the other chunks' totals — data-as-flag: the exchange buffer is pre-set to an all-ones
@@ -100,18 +103,6 @@ __device__ __forceinline__ void scan_step(double& x, int d) {
       : "+d"(x)
       : "r"(d));
 }
-// two-component inclusive add-scan over the warp; returns the exclusive prefix in (es, em)
-__device__ __forceinline__ void warp_scan2(double& is, double& im, double& es, double& em, int lane) {
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    scan_step(is, d);
-    scan_step(im, d);
-  }
-  es = __shfl_up_sync(0xffffffffu, is, 1);
-  em = __shfl_up_sync(0xffffffffu, im, 1);
-  if (lane == 0) { es = 0.0; em = 0.0; }
-}
-
 // 16-byte poll of one (s, m) pair; tearing is harmless: each word is individually "sentinel or final"
 __device__ __forceinline__ void ld_pair(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
   asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
@@ -310,37 +301,34 @@ struct Ctl {
   uint64_t outr[NR];    // phase C finished writing ring slot k                 (W arrivals)   compute -> I/O
   uint64_t ufull[2];    // backward: u-row slot landed                          (tx bytes)     I/O -> compute
   uint64_t ufree[2];    // backward: phase B finished reading the u-row slot    (W arrivals)   compute -> I/O
-  uint64_t tot[2][2];   // [sweep][it & 1] per-warp totals of this iteration    (W arrivals)   compute -> fold warp
+  uint64_t tot[2][2];   // [sweep][it & 1] per-thread totals of this iteration  (W arrivals)   compute -> fold warp
   uint64_t cf[2][2];    // [sweep][it & 1] folded constants for iteration `it`  (1 arrival)    fold warp -> compute
-  double wt[2][2][W][2];    // [sweep][it & 1][warp] (s, m) totals
-  double cfw[2][2][W][2];   // [sweep][it & 1][warp] (A, B) constants
+  double cfa[2][2][2];      // [sweep][it & 1] (A, B) constants of the CTA
   double red[2][W];         // backward: [it & 1][warp] dot partials of phase B
   double sc[2][4];          // [it & 1] c0, kappa/2, c1
   int dead;
 };
 
 // One fold warp per sweep ST (0 or 1).  In iteration `it` it
-//   * waits for the compute warps' totals of this iteration's phase (A for sweep 0, B for sweep 1), scans them,
-//     publishes the CTA total of that sample and keeps the per-warp exclusive offsets (register queue);
+//   * waits for the compute threads' (s, m) totals of this iteration's phase (A for sweep 0, B for sweep 1), turns
+//     them IN PLACE into CTA-wide exclusive prefixes (lane l scans the W consecutive threads l*W .. l*W+W-1 serially,
+//     one shuffle scan over the 32 lane totals — the compute warps execute no shuffle at all) and publishes the CTA
+//     total of that sample;
 //   * folds the G chunk totals of the sample the NEXT iteration consumes (published about one iteration ago by
-//     every CTA of the group; its loads are issued before the wait): boundary constants -> per-warp (A, B) ->
+//     every CTA of the group; its loads are issued before the wait): boundary constants -> (A, B) of the CTA ->
 //     shared memory, then signals cf[ST][(it + 1) & 1].
 // ST is a run-time value: both fold warps share ONE copy of this code (instruction-cache footprint).
 template <bool BWD, int W, int NR, int LB, int LC>
-__device__ __forceinline__ void fold_warp(const PP& p, Ctl<W, NR>* ctl, int lane, int c, int grp, int nIt, int nTot,
-                                          const int ST) {
+__device__ __forceinline__ void fold_warp(const PP& p, Ctl<W, NR>* ctl, double2* pt, int lane, int c, int grp, int nIt,
+                                          int nTot, const int ST) {
+  constexpr int WP = W | 1;                     // odd row pitch: conflict-free 16-byte accesses from both sides
   const int LAG = ST == 0 ? LB : LB + LC;       // the sample folded in iteration it is it + 1 - LAG
-  constexpr int QD = LB > LC ? LB : LC;         // offsets queue depth; the folded sample's entry is qd - 1 deep
-  const int qd = ST == 0 ? LB : LC;
   const int G = p.G, GP = G + 2;
   const bool LR = p.bcL && p.bcR;
   const double rXtot = 1.0 / p.Xtot;
   const bool lift = (!BWD && ST == 0);   // harmonic interpolant of the Dirichlet data: forward, sweep 0 only
   const double ga = (lift && LR) ? (p.gR - p.gL) * rXtot : 0.0;
   const double gb = lift ? (p.bcL ? p.gL : p.gR) : 0.0;
-  double qs[QD], qm[QD];
-#pragma unroll
-  for (int k = 0; k < QD; ++k) qs[k] = qm[k] = 0.0;
   const long long sstep = p.NG;
   long long sF = grp + static_cast<long long>(1 - LAG) * sstep;   // sample folded in iteration 0 (may be negative)
   long long sP = grp + static_cast<long long>(ST == 0 ? 0 : -LB) * sstep;   // sample published in iteration 0
@@ -381,30 +369,38 @@ __device__ __forceinline__ void fold_warp(const PP& p, Ctl<W, NR>* ctl, int lane
       khnx = ck[1];
       if (ends) { uLnx = p.in1[sN * p.ld1]; uRnx = p.in1[sN * p.ld1 + p.nn - 1]; }
     }
-    // ---- totals of this iteration's phase: publish, keep the per-warp exclusive offsets
+    // ---- totals of this iteration's phase: exclusive prefixes in place, publish the CTA total
     if (lane == 0) tr(p, it, 1 + ST, 0);
     ws_tot.begin();
     mbar_wait_b(&ctl->tot[ST][par], ph, p.err, &ctl->dead);
     ws_tot.end();
     if (lane == 0) tr(p, it, 1 + ST, 1);
     {
-      double is = (lane < W) ? ctl->wt[ST][par][lane < W ? lane : 0][0] : 0.0;
-      double im = (lane < W) ? ctl->wt[ST][par][lane < W ? lane : 0][1] : 0.0;
+      double2* P = pt + static_cast<size_t>(ST * 2 + par) * (32 * WP) + lane * WP;
+      double es[W], em[W];
+      double rs = 0.0, rm = 0.0;
 #pragma unroll
-      for (int d = 1; d < W; d <<= 1) {
-        const double os = __shfl_up_sync(0xffffffffu, is, d), om = __shfl_up_sync(0xffffffffu, im, d);
-        if (lane >= d) { is += os; im += om; }
+      for (int k = 0; k < W; ++k) {
+        const double2 v = P[k];
+        es[k] = rs;
+        em[k] = rm;
+        rs += v.x;
+        rm += v.y;
       }
-      double es = __shfl_up_sync(0xffffffffu, is, 1);
-      double em = __shfl_up_sync(0xffffffffu, im, 1);
-      if (lane == 0) { es = 0.0; em = 0.0; }
-      const int jp = ST == 0 ? it : it - LB;
-      if (lane == W - 1 && jp >= 0 && jp < nIt) publish(p.part + ((sP * 2 + ST) * G + c) * 2, is, im);
-      if (lane == W - 1) gts(p, it, 6 + ST);
+      double is = rs, im = rm;
 #pragma unroll
-      for (int k = QD - 1; k > 0; --k) { qs[k] = qs[k - 1]; qm[k] = qm[k - 1]; }
-      qs[0] = es;
-      qm[0] = em;
+      for (int d = 1; d < 32; d <<= 1) {
+        scan_step(is, d);
+        scan_step(im, d);
+      }
+      double xs = __shfl_up_sync(0xffffffffu, is, 1);
+      double xm = __shfl_up_sync(0xffffffffu, im, 1);
+      if (lane == 0) { xs = 0.0; xm = 0.0; }
+#pragma unroll
+      for (int k = 0; k < W; ++k) P[k] = make_double2(es[k] + xs, em[k] + xm);
+      const int jp = ST == 0 ? it : it - LB;
+      if (lane == 31 && jp >= 0 && jp < nIt) publish(p.part + ((sP * 2 + ST) * G + c) * 2, is, im);
+      if (lane == 31) gts(p, it, 6 + ST);
       if (BWD && ST == 1) {   // dot partial of the sample phase B handled in this iteration
         double a = (lane < W) ? ctl->red[par][lane < W ? lane : 0] : 0.0;
 #pragma unroll
@@ -450,15 +446,9 @@ __device__ __forceinline__ void fold_warp(const PP& p, Ctl<W, NR>* ctl, int lane
       const double C = LR ? Wtot * rXtot : (p.bcL ? St : 0.0);    // flux constant fixed by the boundary conditions
       const double A = gb + (p.bcL ? 0.0 : cc * Wtot) - cc * Mx;
       const double Bc = ga + cc * (C - Sx);
-      if (lane < W) {
-        double qmo = qm[0], qso = qs[0];
-#pragma unroll
-        for (int k = 1; k < QD; ++k)
-          if (k == qd - 1) { qmo = qm[k]; qso = qs[k]; }
-        ctl->cfw[ST][nxt][lane][0] = fma(-cc, qmo, A);
-        ctl->cfw[ST][nxt][lane][1] = fma(-cc, qso, Bc);
-      }
       if (lane == 0) {
+        ctl->cfa[ST][nxt][0] = A;
+        ctl->cfa[ST][nxt][1] = Bc;
         ctl->sc[nxt][2 * ST] = cc;
         if (ST == 0) ctl->sc[nxt][1] = khcur;
         // backward, chunk 0: boundary terms of sum_e q_e (u_{e+1}-u_e) = C (u_R-u_L) - S_tot u_R + sum_i rhs_i u_i
@@ -484,8 +474,11 @@ __global__ void __launch_bounds__(32 * (W + 3), (W >= 8 ? 1 : 2)) k1d_pipe(const
   static_assert(sizeof(Ctl<W, NR>) <= MISC_BYTES, "misc region");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Ctl<W, NR>* ctl = reinterpret_cast<Ctl<W, NR>*>(smem_raw);
+  constexpr int WP = W | 1;
   double* ring = reinterpret_cast<double*>(smem_raw + MISC_BYTES);
   double* uring = ring + static_cast<size_t>(NR) * p.slotd;
+  // per-thread (s, m) totals -> exclusive prefixes, [sweep][it & 1][32 * WP]: thread t at (t / W) * WP + t % W
+  double2* pt = reinterpret_cast<double2*>(uring + static_cast<size_t>(BWD ? NRU : 0) * p.slotd);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = p.G, nn = p.nn;
@@ -535,11 +528,15 @@ __global__ void __launch_bounds__(32 * (W + 3), (W >= 8 ? 1 : 2)) k1d_pipe(const
     }
     const double X0 = p.X[min(n0 + tb, nn - 1)];
     const double Xe = p.X[min(n0 + min(tb + R, len), nn - 1)];   // where the block after this thread starts
-    double q0s[LB + 1], q0m[LB + 1], q1s[LC + 1], q1m[LC + 1];   // this thread's exclusive prefixes in flight
+    // this thread's CTA-wide exclusive prefixes in flight (computed by the fold warps, read back one iteration later)
+    double q0s[LB - 1], q0m[LB - 1], q1s[LC - 1], q1m[LC - 1];
 #pragma unroll
-    for (int k = 0; k <= LB; ++k) q0s[k] = q0m[k] = 0.0;
+    for (int k = 0; k < LB - 1; ++k) q0s[k] = q0m[k] = 0.0;
 #pragma unroll
-    for (int k = 0; k <= LC; ++k) q1s[k] = q1m[k] = 0.0;
+    for (int k = 0; k < LC - 1; ++k) q1s[k] = q1m[k] = 0.0;
+    const int pidx = (tid / W) * WP + tid % W;
+    double2* pt0 = pt + pidx;                 // [it & 1] at pt0 + par * 32 * WP
+    double2* pt1 = pt + 2 * 32 * WP + pidx;
 
     int slotA = 0, roundA = 0;   // ring slot of phase A's sample and its use count parity
     WStat ws_full, ws_cf0, ws_uf, ws_cf1;
@@ -560,17 +557,9 @@ __global__ void __launch_bounds__(32 * (W + 3), (W >= 8 ? 1 : 2)) k1d_pipe(const
           if (full) phase_a<BWD, R, true>(buf, hs, nin, nst, ownsL, S, Wc);
           else phase_a<BWD, R, false>(buf, hs, nin, nst, ownsL, S, Wc);
         }
-        double is = S, im = fma(-S, Xe, Wc), es, em;
-        warp_scan2(is, im, es, em, lane);
-#pragma unroll
-        for (int k = LB; k > 0; --k) { q0s[k] = q0s[k - 1]; q0m[k] = q0m[k - 1]; }
-        q0s[0] = es;
-        q0m[0] = em;
-        if (lane == 31) {
-          ctl->wt[0][par][warp][0] = is;
-          ctl->wt[0][par][warp][1] = im;
-          mbar_arrive(&ctl->tot[0][par]);
-        }
+        pt0[par * 32 * WP] = make_double2(S, fma(-S, Xe, Wc));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl->tot[0][par]);
       }
       // ---------------------------------------------------------------- phase B (sample it-LB)
       {
@@ -589,8 +578,8 @@ __global__ void __launch_bounds__(32 * (W + 3), (W >= 8 ? 1 : 2)) k1d_pipe(const
         if (act) {
           double* buf = ring + slotB * slotd + mis0_of(jB) + tb;
           const double c0 = ctl->sc[par][0], kaph = ctl->sc[par][1];
-          const double a0 = fma(-c0, q0m[LB], ctl->cfw[0][par][warp][0]);
-          const double b0 = fma(-c0, q0s[LB], ctl->cfw[0][par][warp][1]);
+          const double a0 = fma(-c0, q0m[LB - 2], ctl->cfa[0][par][0]);
+          const double b0 = fma(-c0, q0s[LB - 2], ctl->cfa[0][par][1]);
           const double* ub = nullptr;
           if (BWD) {
             const int us = jB & 1;
@@ -603,20 +592,22 @@ __global__ void __launch_bounds__(32 * (W + 3), (W >= 8 ? 1 : 2)) k1d_pipe(const
           if (full) phase_b<BWD, R, true>(buf, ub, hs, rh, X0, nin, nst, ownsL, c0, kaph, a0, b0, S1, W1, D);
           else phase_b<BWD, R, false>(buf, ub, hs, rh, X0, nin, nst, ownsL, c0, kaph, a0, b0, S1, W1, D);
         }
-        double is = S1, im = fma(-S1, Xe, W1), es, em;
-        warp_scan2(is, im, es, em, lane);
+        {   // the prefix of the sample phase A handled in the previous iteration is ready (cf[0] of this iteration
+            // is signalled after the fold warp finished that iteration): keep it for phase B of iteration it-1+LB
+          const double2 e0 = pt0[(par ^ 1) * 32 * WP];
 #pragma unroll
-        for (int k = LC; k > 0; --k) { q1s[k] = q1s[k - 1]; q1m[k] = q1m[k - 1]; }
-        q1s[0] = es;
-        q1m[0] = em;
+          for (int k = LB - 2; k > 0; --k) { q0s[k] = q0s[k - 1]; q0m[k] = q0m[k - 1]; }
+          q0s[0] = e0.x;
+          q0m[0] = e0.y;
+        }
+        pt1[par * 32 * WP] = make_double2(S1, fma(-S1, Xe, W1));
         if (BWD) {
 #pragma unroll
           for (int d = 16; d > 0; d >>= 1) D += __shfl_xor_sync(0xffffffffu, D, d);
+          if (lane == 0) ctl->red[par][warp] = D;
         }
-        if (lane == 31) {   // (the shuffles above order every lane's shared-memory reads of this phase before this point)
-          ctl->wt[1][par][warp][0] = is;
-          ctl->wt[1][par][warp][1] = im;
-          if (BWD) ctl->red[par][warp] = D;
+        __syncwarp();   // every lane's shared-memory accesses of this phase are done
+        if (lane == 0) {
           mbar_arrive(&ctl->tot[1][par]);
           if (BWD && act) mbar_arrive(&ctl->ufree[jB & 1]);
         }
@@ -637,8 +628,8 @@ __global__ void __launch_bounds__(32 * (W + 3), (W >= 8 ? 1 : 2)) k1d_pipe(const
           if (have_out) {
             double* buf = ring + slotC * slotd + mis0_of(jC) + tb;
             const double c1 = ctl->sc[par][2];
-            const double a1 = fma(-c1, q1m[LC], ctl->cfw[1][par][warp][0]);
-            const double b1 = fma(-c1, q1s[LC], ctl->cfw[1][par][warp][1]);
+            const double a1 = fma(-c1, q1m[LC - 2], ctl->cfa[1][par][0]);
+            const double b1 = fma(-c1, q1s[LC - 2], ctl->cfa[1][par][1]);
             if (full) {
               phase_c<BWD, R, true>(buf, hs, X0, nst, a1, b1);
             } else {
@@ -651,6 +642,14 @@ __global__ void __launch_bounds__(32 * (W + 3), (W >= 8 ? 1 : 2)) k1d_pipe(const
           __syncwarp();
           if (lane == 0) mbar_arrive(&ctl->outr[slotC]);
         }
+        {   // prefix of the sample phase B handled in the previous iteration (ready: cf[1] of this iteration was signalled
+            // after the fold warp finished that iteration): keep it for phase C of iteration it-1+LC
+          const double2 e1 = pt1[(par ^ 1) * 32 * WP];
+#pragma unroll
+          for (int k = LC - 2; k > 0; --k) { q1s[k] = q1s[k - 1]; q1m[k] = q1m[k - 1]; }
+          q1s[0] = e1.x;
+          q1m[0] = e1.y;
+        }
       }
       if (++slotA == NR) { slotA = 0; roundA ^= 1; }
       if (tid == 0) tr(p, it, 0, 7);
@@ -658,7 +657,7 @@ __global__ void __launch_bounds__(32 * (W + 3), (W >= 8 ? 1 : 2)) k1d_pipe(const
     }
     if (tid == 0) { ws_full.save(p, 0); ws_cf0.save(p, 1); ws_uf.save(p, 2); ws_cf1.save(p, 3); }
   } else if (warp <= W + 1) {
-    fold_warp<BWD, W, NR, LB, LC>(p, ctl, lane, c, grp, nIt, nTot, warp - W);
+    fold_warp<BWD, W, NR, LB, LC>(p, ctl, pt, lane, c, grp, nIt, nTot, warp - W);
   } else {
     // ============================================================================ I/O warp
     // Row chunks are loaded as the 16-byte aligned superset [g - mis, g + len rounded up): the element before /
@@ -815,7 +814,7 @@ int run_cfg(const dfe_mesh* m, PP p, cudaStream_t st, int gbound, int* G_used) {
       g.G = (nn + g.chg - 1) / g.chg;   // drop empty trailing chunks
       g.NG = static_cast<int>(NG);
       g.slotd = ((g.chg + 2) + 1) & ~1;
-      g.smem = MISC_BYTES + sizeof(double) * static_cast<size_t>(NR + NRU) * g.slotd;
+      g.smem = MISC_BYTES + sizeof(double) * static_cast<size_t>(NR + NRU) * g.slotd + 4 * 32 * (W | 1) * 16;
       if (g.smem > 227 * 1024) continue;
       int occ = 0;
       DFE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, g.smem));
