@@ -51,6 +51,16 @@ def test_compute_calls_fail_loudly_without_a_device():
     assert rc == _native.ERR_CUDA
     rc = L.dfe_assemble(nm.handle, 8, 0, 8, 8, 8, None)
     assert rc == _native.ERR_CUDA
+    # batched small-system routes: not offered for a host-only handle, and the entry points refuse
+    m2 = FEMesh.rectangle(5, 4)
+    n2 = m2._native(-1)
+    assert L.dfe_batch_supported(n2.handle) == 0 and L.dfe_band_supported(n2.handle) == 0
+    assert L.dfe_batch_fwd(n2.handle, 2, 8, 30, 8, 8, 8, 8, 30, 1e-13, 100, 8, 8, 8, None) == _native.ERR_CUDA
+    assert L.dfe_batch_bwd(n2.handle, 2, 8, 30, 8, 30, 8, 8, 0, 8, 30, 8, 1e-13, 100, 8, 8, 8, None) == _native.ERR_CUDA
+    assert L.dfe_band_factor(n2.handle, 8, 8, None, None) == _native.ERR_CUDA
+    assert L.dfe_band_fwd(n2.handle, 2, 8, 30, 8, 8, 8, 30, 8, 1 << 20, None) == _native.ERR_CUDA
+    assert L.dfe_band_bwd(n2.handle, 2, 8, 30, 8, 30, 8, 0, 8, 30, 8, 8, 1 << 20, None) == _native.ERR_CUDA
+    assert b"no CUDA device" in L.dfe_last_error()
 
 
 # ----------------------------------------------------------------- reference mesh tests (upstream tests/test_fem.py:44-72)
