@@ -243,12 +243,14 @@ __device__ __forceinline__ void phase_a(double* buf, const double (&hs)[R + 1], 
   }
 }
 
-template <bool BWD, int R, bool FULL>
+// SK (kappa shared by the batch): delta_i does not depend on the sample; it was computed once per thread and sits in
+// rh[i + 1] (the reciprocals are not needed any more), which takes 9 of the 15 flops per node out of this phase.
+template <bool BWD, int R, bool FULL, bool SK>
 __device__ __forceinline__ void phase_b(double* buf, const double* ub, const double (&hs)[R + 1], const double (&rh)[R + 1],
                                         double X0, int nin, int nst, bool ownsL, double c0, double kaph, double a0,
                                         double b0, double& S1, double& W1, double& D) {
   double S = 0.0, Wc = 0.0;
-  double kp = kdiv(kaph, hs[0], rh[0]);
+  double kp = SK ? 0.0 : kdiv(kaph, hs[0], rh[0]);
   double t = fma(b0, X0, a0);
 #pragma unroll
   for (int j = 0; j < R; ++j) {
@@ -266,9 +268,14 @@ __device__ __forceinline__ void phase_b(double* buf, const double* ub, const dou
     t = fma(b0, hs[j + 1], t);
     // k_i = fl(kappa/h_i) bit-exactly (solver.py:88); err = (k_{i-1}+k_i) - fl(k_{i-1}+k_i) is minus the rounding of
     // the reference's diagonal accumulation (solver.py:89-92); it is 0 on Dirichlet and padding rows.
-    const double ki = kdiv(kaph, hs[j + 1], rh[j + 1]);
-    const double v1 = __dmul_rn(two_sum_err(kp, ki), x0);
-    kp = ki;
+    double v1;
+    if (SK) {
+      v1 = __dmul_rn(rh[j + 1], x0);
+    } else {
+      const double ki = kdiv(kaph, hs[j + 1], rh[j + 1]);
+      v1 = __dmul_rn(two_sum_err(kp, ki), x0);
+      kp = ki;
+    }
     if (BWD) {
       const double uj = (FULL || j < nst) ? ub[j] : 0.0;
       D = fma(g + v1, uj, D);
@@ -466,7 +473,7 @@ __device__ __forceinline__ void fold_warp(const PP& p, Ctl<W, NR>* ctl, double2*
 }
 
 // Warps 0..W-1 compute; warp W / W+1 = fold warps of sweep 0 / 1; warp W+2 = I/O warp (TMA loads and stores).
-template <bool BWD, int R, int W, int LB, int LC>
+template <bool BWD, int R, int W, int LB, int LC, bool SK>
 __global__ void __launch_bounds__(32 * (W + 3), (W >= 8 ? 1 : 2)) k1d_pipe(const PP p) {
   constexpr int NR = LB + LC + 3;           // ring slots of the in-place chain: prefetch, A..C, store drain
   constexpr int NRU = 2;                    // ring slots of the u row (backward, used by phase B only)
@@ -525,6 +532,16 @@ __global__ void __launch_bounds__(32 * (W + 3), (W >= 8 ? 1 : 2)) k1d_pipe(const
       const bool ex = (e >= 0 && e < nn - 1 && tb + j <= len);
       hs[j] = ex ? p.hs[e] : 0.0;
       rh[j] = ex ? p.rh[e] : 0.0;
+    }
+    if (SK) {   // delta_i = (k_{i-1} + k_i) - fl(k_{i-1} + k_i) for the one kappa of the batch, kept in rh[i + 1]
+      const double kaph = 0.5 * p.kappa[0];
+      double kp = kdiv(kaph, hs[0], rh[0]);
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const double ki = kdiv(kaph, hs[j + 1], rh[j + 1]);
+        rh[j + 1] = two_sum_err(kp, ki);
+        kp = ki;
+      }
     }
     const double X0 = p.X[min(n0 + tb, nn - 1)];
     const double Xe = p.X[min(n0 + min(tb + R, len), nn - 1)];   // where the block after this thread starts
@@ -589,8 +606,8 @@ __global__ void __launch_bounds__(32 * (W + 3), (W >= 8 ? 1 : 2)) k1d_pipe(const
             ws_uf.end();
           }
           if (tid == 0) tr(p, it, 0, 4);
-          if (full) phase_b<BWD, R, true>(buf, ub, hs, rh, X0, nin, nst, ownsL, c0, kaph, a0, b0, S1, W1, D);
-          else phase_b<BWD, R, false>(buf, ub, hs, rh, X0, nin, nst, ownsL, c0, kaph, a0, b0, S1, W1, D);
+          if (full) phase_b<BWD, R, true, SK>(buf, ub, hs, rh, X0, nin, nst, ownsL, c0, kaph, a0, b0, S1, W1, D);
+          else phase_b<BWD, R, false, SK>(buf, ub, hs, rh, X0, nin, nst, ownsL, c0, kaph, a0, b0, S1, W1, D);
         }
         {   // the prefix of the sample phase A handled in the previous iteration is ready (cf[0] of this iteration
             // is signalled after the fold warp finished that iteration): keep it for phase B of iteration it-1+LB
@@ -777,11 +794,11 @@ struct Geo {
   size_t smem;
 };
 
-template <bool BWD, int R, int W, int LB, int LC>
+template <bool BWD, int R, int W, int LB, int LC, bool SK = false>
 int run_cfg(const dfe_mesh* m, PP p, cudaStream_t st, int gbound, int* G_used) {
   constexpr int NR = LB + LC + 3, NRU = BWD ? 2 : 0;
   constexpr int CAP = R * 32 * W, THREADS = 32 * (W + 3);
-  auto kern = k1d_pipe<BWD, R, W, LB, LC>;
+  auto kern = k1d_pipe<BWD, R, W, LB, LC, SK>;
   const int nn = p.nn;
   static bool attr_done = false;
   if (!attr_done) {
@@ -926,7 +943,10 @@ int pipe1d_run(const dfe_mesh* m, long long B, bool bwd, const double* in0, long
       case 3: rc = run_cfg<false, 13, 8, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
       case 4: rc = run_cfg<false, 11, 8, 3, 2>(m, p, st, static_cast<int>(gmax), &G); break;
       case 5: rc = run_cfg<false, 11, 5, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      default: rc = run_cfg<false, 9, 12, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      default:
+        rc = p.per_sample ? run_cfg<false, 9, 12, 2, 2>(m, p, st, static_cast<int>(gmax), &G)
+                          : run_cfg<false, 9, 12, 2, 2, true>(m, p, st, static_cast<int>(gmax), &G);
+        break;
     }
   } else {
     switch (id) {
@@ -935,7 +955,10 @@ int pipe1d_run(const dfe_mesh* m, long long B, bool bwd, const double* in0, long
       case 3: rc = run_cfg<true, 9, 10, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
       case 4: rc = run_cfg<true, 9, 8, 3, 2>(m, p, st, static_cast<int>(gmax), &G); break;
       case 5: rc = run_cfg<true, 9, 5, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      default: rc = run_cfg<true, 11, 8, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      default:
+        rc = p.per_sample ? run_cfg<true, 11, 8, 2, 2>(m, p, st, static_cast<int>(gmax), &G)
+                          : run_cfg<true, 11, 8, 2, 2, true>(m, p, st, static_cast<int>(gmax), &G);
+        break;
     }
   }
   if (rc != DFE_OK) return rc;
