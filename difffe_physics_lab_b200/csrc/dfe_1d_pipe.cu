@@ -924,6 +924,8 @@ int pipe1d_run(const dfe_mesh* m, long long B, bool bwd, const double* in0, long
   const int id = cfg_id();
   static const int backoff = [] { const char* e = getenv("DFE_PIPE_BACKOFF"); return e ? atoi(e) : 0; }();
   p.backoff = backoff;
+  static const bool no_sk = getenv("DFE_PIPE_NOSK") != nullptr;   // tuning switch: generic kernel for a shared kappa too
+  const bool sk = !p.per_sample && !no_sk;
   static const bool want_trace = getenv("DFE_PIPE_TRACE") != nullptr;
   const size_t trace_n = 3 * 16 * 4 * 8;
   if (want_trace) {
@@ -944,8 +946,9 @@ int pipe1d_run(const dfe_mesh* m, long long B, bool bwd, const double* in0, long
       case 4: rc = run_cfg<false, 11, 8, 3, 2>(m, p, st, static_cast<int>(gmax), &G); break;
       case 5: rc = run_cfg<false, 11, 5, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
       default:
-        rc = p.per_sample ? run_cfg<false, 9, 12, 2, 2>(m, p, st, static_cast<int>(gmax), &G)
-                          : run_cfg<false, 9, 12, 2, 2, true>(m, p, st, static_cast<int>(gmax), &G);
+        // (the shared-kappa specialisation is used by the adjoint only: measured on config 5a it makes the forward
+        // kernel slower and erratic, 3.94 -> 4.4-5.1 ms — its shorter phase B moves the fold latency onto the critical path)
+        rc = run_cfg<false, 9, 12, 2, 2>(m, p, st, static_cast<int>(gmax), &G);
         break;
     }
   } else {
@@ -956,8 +959,8 @@ int pipe1d_run(const dfe_mesh* m, long long B, bool bwd, const double* in0, long
       case 4: rc = run_cfg<true, 9, 8, 3, 2>(m, p, st, static_cast<int>(gmax), &G); break;
       case 5: rc = run_cfg<true, 9, 5, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
       default:
-        rc = p.per_sample ? run_cfg<true, 11, 8, 2, 2>(m, p, st, static_cast<int>(gmax), &G)
-                          : run_cfg<true, 11, 8, 2, 2, true>(m, p, st, static_cast<int>(gmax), &G);
+        rc = !sk ? run_cfg<true, 11, 8, 2, 2>(m, p, st, static_cast<int>(gmax), &G)
+                 : run_cfg<true, 11, 8, 2, 2, true>(m, p, st, static_cast<int>(gmax), &G);
         break;
     }
   }
