@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(BT, (RPT <= 4 ? 2 : 1)) k_batch(const BArgs A)
 // load of the column shared by the BS samples, one fma per sample).  Replaces solver.py:174 (LU with partial
 // pivoting on the dense K_free) more literally than PCG does.
 constexpr int BW = 32;   // half bandwidth supported: one lane per sub-diagonal
-constexpr int BS = 4;    // samples per warp (the factor is loaded once per BS samples)
+constexpr int BS = 8;    // samples per warp (the factor is loaded once per BS samples: its L2 -> SM traffic is the bound)
 
 // Lower band of K_free, Ab[r * 33 + k] = K_free[r][r - k] (k = 0..32), scattered from the assembled matrix in parallel.
 // Rows n_free .. n_free + 34 are zero (the factor kernel prefetches past the end).
