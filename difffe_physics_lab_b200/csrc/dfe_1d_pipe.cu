@@ -941,7 +941,7 @@ int pipe1d_run(const dfe_mesh* m, long long B, bool bwd, const double* in0, long
   if (!bwd) {
     switch (id) {
       case 1: rc = run_cfg<false, 11, 10, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
-      case 2: rc = run_cfg<false, 7, 16, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
+      case 2: rc = run_cfg<false, 11, 8, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
       case 3: rc = run_cfg<false, 13, 8, 2, 2>(m, p, st, static_cast<int>(gmax), &G); break;
       case 4: rc = run_cfg<false, 9, 10, 3, 2>(m, p, st, static_cast<int>(gmax), &G); break;
       case 6: rc = run_cfg<false, 9, 10, 2, 3>(m, p, st, static_cast<int>(gmax), &G); break;

@@ -174,7 +174,7 @@ int dfe_batch_bwd(const dfe_mesh* m, int64_t B, const double* gbar, int64_t ldg,
 /* ---------------------------------------------------------------- the same batch, banded direct solver
  * When the half bandwidth of K_free is <= 32 (dfe_band_supported; e.g. FEMesh.rectangle(nx, ny) with nx <= 32 in the
  * reference's node numbering) the shared matrix is factored ONCE per call, K_free = L L^T, and every sample costs two
- * banded triangular solves (a warp owns 4 samples) — ~13x fewer flops than Jacobi-PCG at 961 unknowns and no
+ * banded triangular solves (a warp owns 8 samples) — ~13x fewer flops than Jacobi-PCG at 961 unknowns and no
  * reductions.  This is the closest replacement of solver.py:174 (dense LU) for config 5b.
  *   dfe_band_factor   vals_full from dfe_assemble; factor: dfe_band_factor_bytes(m) bytes of device memory;
  *                     status_dev (optional, device int32): 0 ok, 5 = pivot <= 0 (K_free not SPD)
