@@ -29,7 +29,8 @@ KAPPA_SCALAR, KAPPA_PER_SAMPLE, KAPPA_PER_ELEMENT, KAPPA_PER_SAMPLE_ELEMENT = ra
 SYMBOLS = [
     "dfe_last_error", "dfe_abi_version", "dfe_device_count",
     "dfe_mesh_create", "dfe_mesh_destroy", "dfe_mesh_get_info", "dfe_mesh_csr_host", "dfe_mesh_free_nodes_host",
-    "dfe_solve1d_workspace_bytes", "dfe_solve1d_fwd", "dfe_solve1d_bwd",
+    "dfe_solve1d_workspace_bytes", "dfe_solve1d_fwd", "dfe_solve1d_bwd", "dfe_solve1d_bwd_misfit",
+    "dfe_solve1d_supported", "dfe_mesh_fault",
     "dfe_assemble", "dfe_eliminate", "dfe_pcg_workspace_bytes", "dfe_pcg", "dfe_scatter", "dfe_gather_free",
     "dfe_grad_workspace_bytes", "dfe_grad",
     "dfe_batch_supported", "dfe_batch_fwd", "dfe_batch_bwd",
@@ -76,24 +77,42 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
-    """Compile csrc/*.cu into libdfe_b200.so for sm_100a (cross-compiles without a GPU)."""
+    """Compile csrc/*.cu into libdfe_b200.so for sm_100a (cross-compiles without a GPU).
+
+    One object file per translation unit (compiled in parallel, only when the source or a header changed), then one
+    link step; objects live in ``difffe_physics_lab_b200/build/`` (git-ignored)."""
     if not force and not needs_build():
         return LIB_PATH
-    cmd = [
-        nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-        "-Xcompiler", "-fPIC", "-shared", "-I", str(ROOT / "include"), "-I", str(PKG / "csrc"),
-        "-o", str(LIB_PATH),
-    ] + [str(PKG / "csrc" / s) for s in SOURCES]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    extra = os.environ.get("DFE_NVCC_FLAGS")      # e.g. -DDFE_PIPE_TRACE_BUILD=1 (debug timeline of the 1-D kernel)
-    if extra:
-        cmd[1:1] = extra.split()
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    from concurrent.futures import ThreadPoolExecutor
+
+    objdir = PKG / "build"
+    objdir.mkdir(exist_ok=True)
+    extra = (os.environ.get("DFE_NVCC_FLAGS") or "").split()      # e.g. -DDFE_SOME_DEBUG_SWITCH=1
+    flags = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
+             "-I", str(ROOT / "include"), "-I", str(PKG / "csrc")] + extra + (["-Xptxas=-v"] if verbose else [])
+    stamp = objdir / "flags.txt"
+    if not stamp.exists() or stamp.read_text() != " ".join(flags):
+        force = True
+    hdr_t = max(h.stat().st_mtime for h in HEADERS)
+
+    def compile_one(src: str):
+        cu, obj = PKG / "csrc" / src, objdir / (src + ".o")
+        if not force and obj.exists() and obj.stat().st_mtime > max(cu.stat().st_mtime, hdr_t):
+            return ""
+        res = subprocess.run([nvcc_path()] + flags + ["-c", str(cu), "-o", str(obj)], capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n" + res.stdout + res.stderr)
+        return res.stderr
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
+        logs = list(ex.map(compile_one, SOURCES))
+    stamp.write_text(" ".join(flags))
+    res = subprocess.run([nvcc_path(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB_PATH)]
+                         + [str(objdir / (s + ".o")) for s in SOURCES], capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     if verbose:
-        print(res.stderr)
+        print("\n".join(logs))
     return LIB_PATH
 
 
@@ -132,6 +151,12 @@ def lib() -> C.CDLL:
     L.dfe_solve1d_fwd.argtypes = [vp, i64, vp, i64, vp, ci, ci, vp, i64, vp, sz, vp]
     L.dfe_solve1d_bwd.restype = ci
     L.dfe_solve1d_bwd.argtypes = [vp, i64, vp, i64, vp, i64, vp, ci, ci, vp, i64, vp, vp, sz, vp]
+    L.dfe_solve1d_bwd_misfit.restype = ci
+    L.dfe_solve1d_bwd_misfit.argtypes = [vp, i64, vp, i64, vp, i64, vp, ci, ci, dbl, vp, i64, vp, vp, vp, sz, vp]
+    L.dfe_solve1d_supported.restype = ci
+    L.dfe_solve1d_supported.argtypes = [vp, ci, ci]
+    L.dfe_mesh_fault.restype = ci
+    L.dfe_mesh_fault.argtypes = [vp]
     L.dfe_assemble.restype = ci
     L.dfe_assemble.argtypes = [vp, vp, ci, vp, vp, vp, vp]
     L.dfe_eliminate.restype = ci

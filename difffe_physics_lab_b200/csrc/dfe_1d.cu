@@ -34,7 +34,7 @@ bool pipe1d_eligible(const dfe_mesh* m, long long B, int kappa_mode, int n_refin
                      const double* in1, const double* out, long long ldo);
 int pipe1d_run(const dfe_mesh* m, long long B, bool bwd, const double* in0, long long ld0, const double* in1,
                long long ld1, const double* kappa, int kappa_mode, double* out, long long ldo, double* gkappa,
-               void* ws, cudaStream_t st);
+               void* ws, cudaStream_t st, const Misfit1D* misfit);
 }  // namespace dfe
 
 namespace {
@@ -64,6 +64,7 @@ struct P1D {
   int* cnt;              // [B] arrival counters (zeroed per call)
   double* summ;          // [B][MAX_STAGES][G][4] chunk summaries
   double* gkpart;        // backward: [B][G] partial dL/dkappa
+  int* err;              // mesh handle's fault word (mapped host memory): set if a wait exceeded its bound
 };
 
 // Exclusive prefix (carry) of chunk c and the total over the G chunk summaries of one stage.
@@ -142,8 +143,17 @@ __device__ __forceinline__ void run_stage(const P1D& p, const Ctx& cx, int st, d
   if (cx.warp == 0) {
     if (cx.lane == 0) {
       const int target = (st + 1) * cx.G;
-      // plain spin: __nanosleep occasionally oversleeps by microseconds on B200 (measured, see dfe_1d_pipe.cu)
-      while (ld_relaxed(p.cnt + cx.s) < target) {}
+      // plain spin: __nanosleep occasionally oversleeps by microseconds on B200 (measured, see dfe_1d_pipe.cu).
+      // Bounded (~2 s): a protocol bug or a lost co-resident CTA raises the handle's fault word instead of hanging
+      // the GPU; the results of the call are then garbage and the next call on the handle reports it.
+      const long long t0 = clock64();
+      int spins = 0;
+      while (ld_relaxed(p.cnt + cx.s) < target) {
+        if ((++spins & 1023) == 0 && clock64() - t0 > 4000000000ll) {
+          *reinterpret_cast<volatile int*>(p.err) = 1;
+          break;
+        }
+      }
     }
     __syncwarp();
     Tri carry, total;
@@ -439,8 +449,19 @@ int launch(const dfe_mesh* m, long long B, P1D p, const Plan& pl, cudaStream_t s
   long long NG = resident / pl.G;
   if (NG > B) NG = B;
   p.NG = static_cast<int>(NG);
-  kern<<<static_cast<unsigned>(NG * pl.G), T, smem, st>>>(p);
-  DFE_CUDA_OK(cudaGetLastError());
+  // cooperative launch: the G chunks of a sample wait for each other, so the runtime must guarantee co-residency
+  // (it fails the launch instead of letting the kernel hang under MPS / SM partitioning)
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(NG * pl.G));
+  cfg.blockDim = dim3(T);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  DFE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
   return DFE_OK;
 }
 
@@ -514,6 +535,7 @@ P1D base_params(const dfe_mesh* m, long long B, const Plan& pl, const double* ka
   p.cnt = reinterpret_cast<int*>(w + pl.off_cnt);
   p.summ = reinterpret_cast<double*>(w + pl.off_summ);
   p.gkpart = reinterpret_cast<double*>(w + pl.off_gk);
+  p.err = m->d_fault;
   return p;
 }
 
@@ -553,7 +575,7 @@ extern "C" int dfe_solve1d_fwd(const dfe_mesh* m, int64_t B, const double* f, in
   p.out = u;
   p.ldo = ldu;
   if (mode == MODE_PIPE) {
-    rc = dfe::pipe1d_run(m, B, false, f, ldf, nullptr, 0, kappa, kappa_mode, u, ldu, nullptr, ws, st);
+    rc = dfe::pipe1d_run(m, B, false, f, ldf, nullptr, 0, kappa, kappa_mode, u, ldu, nullptr, ws, st, nullptr);
   } else if (mode == MODE_SPLIT) {
     rc = dfe::split1d_run(m, B, false, f, ldf, nullptr, 0, kappa, kappa_mode, u, ldu, nullptr, ws, st);
   } else {
@@ -564,24 +586,33 @@ extern "C" int dfe_solve1d_fwd(const dfe_mesh* m, int64_t B, const double* f, in
   return rc;
 }
 
-extern "C" int dfe_solve1d_bwd(const dfe_mesh* m, int64_t B, const double* gbar, int64_t ldg, const double* u,
-                               int64_t ldu, const double* kappa, int kappa_mode, int n_refine, double* gf,
-                               int64_t ldgf, double* gkappa, void* ws, size_t ws_bytes, void* stream) {
+namespace {
+
+// Shared by dfe_solve1d_bwd (misfit == nullptr: `gbar` is the upstream gradient) and dfe_solve1d_bwd_misfit (`gbar`
+// is u_data; the pipelined kernel forms the upstream gradient itself).
+int solve1d_bwd_impl(const dfe_mesh* m, int64_t B, const double* gbar, int64_t ldg, const double* u, int64_t ldu,
+                     const double* kappa, int kappa_mode, int n_refine, double* gf, int64_t ldgf, double* gkappa,
+                     void* ws, size_t ws_bytes, void* stream, const dfe::Misfit1D* misfit, const char* who) {
   Plan pl{};
   Mode1D mode = m ? mode_1d(auto_refine(n_refine, m->info.n_nodes)) : MODE_SEQ;
   if (m) make_plan(m, B, R_BWD, &pl);
-  int rc = common_checks(m, B, gbar, kappa, kappa_mode, ws, ws_bytes, pl, "dfe_solve1d_bwd");
+  int rc = common_checks(m, B, gbar, kappa, kappa_mode, ws, ws_bytes, pl, who);
   if (rc != DFE_OK) return rc;
   if (mode == MODE_PIPE &&
       !dfe::pipe1d_eligible(m, B, kappa_mode, auto_refine(n_refine, m->info.n_nodes), gbar, ldg, u, gf, ldgf))
     mode = MODE_SPLIT;
-  if (kappa_mode >= DFE_KAPPA_PER_ELEMENT && mode != MODE_SPLIT) {
-    dfe::set_error("dfe_solve1d_bwd: per-element kappa needs the split path (n_refine == 1, i.e. meshes up to 2e5 nodes)");
+  if (misfit && mode != MODE_PIPE) {
+    dfe::set_error("%s: the fused misfit adjoint runs on the pipelined kernel only (chain mesh up to 163840 nodes, scalar or "
+                   "per-sample kappa, 16-byte aligned rows); form gbar = scale * (u - u_data) and call dfe_solve1d_bwd", who);
     return DFE_ERR_UNSUPPORTED;
   }
-  DFE_REQUIRE(u && gkappa, "dfe_solve1d_bwd: null u / gkappa");
+  if (kappa_mode >= DFE_KAPPA_PER_ELEMENT && mode != MODE_SPLIT) {
+    dfe::set_error("%s: per-element kappa needs the split path (n_refine == 1, i.e. meshes up to 2e5 nodes)", who);
+    return DFE_ERR_UNSUPPORTED;
+  }
+  DFE_REQUIRE(u && gkappa, "%s: null u / gkappa", who);
   DFE_REQUIRE(ldg >= m->info.n_nodes && ldu >= m->info.n_nodes && (!gf || ldgf >= m->info.n_nodes),
-              "dfe_solve1d_bwd: leading dimension smaller than n_nodes");
+              "%s: leading dimension smaller than n_nodes", who);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int cur = -1;
   DFE_CUDA_OK(cudaGetDevice(&cur));
@@ -595,7 +626,7 @@ extern "C" int dfe_solve1d_bwd(const dfe_mesh* m, int64_t B, const double* gbar,
   p.ldo = ldgf;
   if (mode == MODE_PIPE || mode == MODE_SPLIT) {
     rc = mode == MODE_PIPE
-             ? dfe::pipe1d_run(m, B, true, gbar, ldg, u, ldu, kappa, kappa_mode, gf, ldgf, gkappa, ws, st)
+             ? dfe::pipe1d_run(m, B, true, gbar, ldg, u, ldu, kappa, kappa_mode, gf, ldgf, gkappa, ws, st, misfit)
              : dfe::split1d_run(m, B, true, gbar, ldg, u, ldu, kappa, kappa_mode, gf, ldgf, gkappa, ws, st);
     if (cur != m->info.device) cudaSetDevice(cur);
     return rc;
@@ -610,10 +641,51 @@ extern "C" int dfe_solve1d_bwd(const dfe_mesh* m, int64_t B, const double* gbar,
       k_reduce_gk<<<1, 1024, 0, st>>>(p.gkpart, B, G_used, 0, gkappa);
     }
     if (cudaGetLastError() != cudaSuccess) {
-      dfe::set_error("dfe_solve1d_bwd: reduce kernel launch failed");
+      dfe::set_error("%s: reduce kernel launch failed", who);
       rc = DFE_ERR_CUDA;
     }
   }
   if (cur != m->info.device) cudaSetDevice(cur);
   return rc;
+}
+
+}  // namespace
+
+extern "C" int dfe_solve1d_bwd(const dfe_mesh* m, int64_t B, const double* gbar, int64_t ldg, const double* u,
+                               int64_t ldu, const double* kappa, int kappa_mode, int n_refine, double* gf,
+                               int64_t ldgf, double* gkappa, void* ws, size_t ws_bytes, void* stream) {
+  return solve1d_bwd_impl(m, B, gbar, ldg, u, ldu, kappa, kappa_mode, n_refine, gf, ldgf, gkappa, ws, ws_bytes, stream,
+                          nullptr, "dfe_solve1d_bwd");
+}
+
+extern "C" int dfe_solve1d_bwd_misfit(const dfe_mesh* m, int64_t B, const double* u_data, int64_t ldd, const double* u,
+                                      int64_t ldu, const double* kappa, int kappa_mode, int n_refine, double scale,
+                                      double* gf, int64_t ldgf, double* gkappa, double* loss, void* ws, size_t ws_bytes,
+                                      void* stream) {
+  if (!loss) {
+    dfe::set_error("dfe_solve1d_bwd_misfit: null loss");
+    return DFE_ERR_INVALID;
+  }
+  const dfe::Misfit1D mf{scale, loss};
+  return solve1d_bwd_impl(m, B, u_data, ldd, u, ldu, kappa, kappa_mode, n_refine, gf, ldgf, gkappa, ws, ws_bytes, stream,
+                          &mf, "dfe_solve1d_bwd_misfit");
+}
+
+// 1: the fused 1-D path takes this mesh in BOTH directions with this kappa layout and refinement setting (decided once,
+// in the forward call, by the host layer); 0 otherwise (not a chain, or larger than the co-resident capacity of the
+// multi-sweep kernel).
+extern "C" int dfe_solve1d_supported(const dfe_mesh* m, int kappa_mode, int n_refine) {
+  if (!m || !m->chain || m->info.device < 0) return 0;
+  const long long nn = m->info.n_nodes;
+  const int nref = auto_refine(n_refine, nn);
+  if (nref == 1) return 1;                    // pipelined / split kernels: any size, any kappa layout
+  if (kappa_mode >= DFE_KAPPA_PER_ELEMENT) return 0;
+  // multi-sweep kernel: every chunk of a sample must be co-resident (2 CTAs per SM), backward is the tighter one
+  const long long cap = 2LL * m->sm_count * R_BWD * T;
+  return nn <= cap ? 1 : 0;
+}
+
+// Fault word of the fused 1-D kernels (0 = healthy).  Meaningful after the stream the calls ran on was synchronised.
+extern "C" int dfe_mesh_fault(const dfe_mesh* m) {
+  return (m && m->h_fault) ? *reinterpret_cast<volatile int*>(m->h_fault) : 0;
 }

@@ -60,6 +60,12 @@ struct MeshDev {
   const int* sell_src;       // (sell_nnz) index into vals_full, -1 for padding
 };
 
+// misfit adjoint of the fused 1-D path: gbar = scale * (u - u_data), loss = (scale / 2) * sum (u - u_data)^2
+struct Misfit1D {
+  double scale;
+  double* loss;   // device: [1] (shared kappa: summed over the batch) or [B] (per-sample kappa)
+};
+
 }  // namespace dfe
 
 struct dfe_mesh {

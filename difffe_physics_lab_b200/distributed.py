@@ -75,3 +75,57 @@ def sharded_loss_and_grad(solver_factory, kappa: torch.Tensor, f_local: torch.Te
     loss = loss_local.detach().clone()
     allreduce_sum_([loss, g_local])
     return loss, g_local
+
+
+class MisfitSweep:
+    """Data-parallel step of the kappa inverse-problem sweep (BASELINE config 5):
+
+        loss(kappa) = 1 / n_total * sum_b mean_i (u_b(f_b, kappa) - u_data_b)^2        over ALL ``n_total`` samples
+
+    with this rank holding the contiguous shard ``f_local`` / ``u_data_local``.  One ``step(kappa)`` is
+    forward solve -> fused misfit adjoint on the local shard (``DifferentiableFESolver.misfit``: gbar is formed inside the
+    adjoint kernel, its last reduction block writes ``[sum_b dL/dkappa, loss]`` — already scaled by 1 / n_total —
+    straight into the persistent buffer ``self.red``) -> ONE sum all-reduce of those two doubles, enqueued behind the
+    kernels with no host synchronisation and no copy kernel in between.  ``self.red`` is allocated once, from NCCL's
+    registered-memory pool when the backend offers one.  Returns views ``(loss, grad)`` of ``self.red``, identical on
+    every rank; they are overwritten by the next step.
+    """
+
+    def __init__(self, mesh, f_local: torch.Tensor, u_data_local: torch.Tensor, n_total: int, group=None, **solver_kw):
+        from .solver import DifferentiableFESolver            # local import: solver.py does not depend on this module
+
+        self._solver_cls = DifferentiableFESolver
+        self.mesh, self.f, self.u_data = mesh, f_local, u_data_local
+        self.n_total, self.group, self.solver_kw = int(n_total), group, solver_kw
+        self.registered = False
+        self.red = self._alloc_red(f_local.device)
+
+    def _alloc_red(self, dev: torch.device) -> torch.Tensor:
+        _, w = world()
+        if w > 1 and dev.type == "cuda":
+            try:                                               # NCCL user-buffer registration (ncclMemAlloc pool)
+                pg = self.group if self.group is not None else dist.group.WORLD
+                backend = pg._get_backend(dev)
+                pool = torch.cuda.MemPool(backend.mem_allocator)
+                with torch.cuda.use_mem_pool(pool):
+                    red = torch.zeros(2, dtype=torch.float64, device=dev)
+                backend.register_mem_pool(pool)
+                self._pool = pool
+                self.registered = True
+                return red
+            except Exception:                                  # older NCCL / no registration support: plain buffer
+                pass
+        return torch.zeros(2, dtype=torch.float64, device=dev)
+
+    def local_step(self, kappa: torch.Tensor) -> None:
+        """Forward + fused misfit adjoint of the local shard; fills ``self.red`` = [dL/dkappa, loss] (local part)."""
+        with torch.no_grad():                                  # the gradient is produced by the kernel itself
+            self._solver_cls(self.mesh, kappa=kappa.detach(), **self.solver_kw).misfit(
+                self.f, self.u_data, out2=self.red, weight=1.0 / self.n_total)
+
+    def step(self, kappa: torch.Tensor):
+        self.local_step(kappa)
+        _, w = world()
+        if w > 1:
+            dist.all_reduce(self.red, op=dist.ReduceOp.SUM, group=self.group)
+        return self.red[1], self.red[0]

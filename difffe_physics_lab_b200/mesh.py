@@ -174,8 +174,10 @@ class FEMesh:
 
     def _fingerprint(self):
         n, e = self.nodes, self.elements
+        # the Dirichlet items themselves, not their hash: hash(-1.0) == hash(-2.0) in CPython.  In-place edits of
+        # nodes / elements through .data or a numpy view are not tracked (torch does not bump _version for them).
         return (n.data_ptr(), n._version, tuple(n.shape), e.data_ptr(), e._version, tuple(e.shape),
-                hash(tuple(self.dirichlet_nodes.items())))
+                tuple(self.dirichlet_nodes.items()))
 
     def _native(self, device: int) -> NativeMesh:
         """Native handle for CUDA device ``device`` (-1: host-only symbolic handle)."""

@@ -14,7 +14,10 @@ reference accepts), ``(n_el,)`` (shared per-element field), ``(B, 1)`` (per-samp
 ``(B, n_el)``.  Un-batched calls keep returning ``(n_nodes,)``.
 
 Device policy: a CPU ``f`` is copied to the current CUDA device, solved there, and ``u`` is returned
-on ``f``'s device (``PhysicsLoss`` feeds CPU tensors, reference loss.py:78-83).
+on ``f``'s device (``PhysicsLoss`` feeds CPU tensors, reference loss.py:78-83) unless ``out_device`` says
+otherwise.  Large host batches on the fused 1-D path are streamed: row chunks go host -> device on a copy
+stream (through pinned staging when ``f`` is pageable) while earlier chunks are being solved, and ``u`` /
+``dL/df`` chunks return on a second copy stream — the host <-> device traffic overlaps the kernels.
 """
 from __future__ import annotations
 
@@ -37,8 +40,9 @@ class KernelTimer:
     ``launches`` counts the kernels of libdfe_b200 launched while active."""
 
     _active: Optional["KernelTimer"] = None
-    # kernels of libdfe_b200 launched per ABI call (default pipelined 1-D path: k1d_pipe_ck + k1d_pipe [+ k1d_pipe_gk])
-    KERNELS_PER_CALL = {"solve1d_fwd": 2, "solve1d_bwd": 3, "batch_fwd": 1, "batch_bwd": 1, "band_factor": 1,
+    # kernels of libdfe_b200 launched per ABI call (default pipelined 1-D path: k1d_pipe_ck + k1d_pipe [+ k1d_pipe_gk]
+    # + k1d_pipe_poison)
+    KERNELS_PER_CALL = {"solve1d_fwd": 3, "solve1d_bwd": 4, "solve1d_bwd_misfit": 4, "batch_fwd": 1, "batch_bwd": 1, "band_factor": 1,
                         "band_fwd": 3, "band_bwd": 3, "assemble": 1, "eliminate": 2, "pcg": 1, "scatter": 1,
                         "gather": 1, "grad": 3}
 
@@ -111,71 +115,328 @@ def _kappa_mode(kappa: torch.Tensor, B: int, n_el: int, batched: bool) -> int:
         "[per-sample forms need a batched f of shape (B, n_nodes)]")
 
 
+_PER_SAMPLE_MODES = (_native.KAPPA_PER_SAMPLE, _native.KAPPA_PER_SAMPLE_ELEMENT)
+
+
+def _check_fault(nm, what: str) -> None:
+    """Raise if a bounded wait inside a fused 1-D kernel expired (call after a synchronisation point)."""
+    if _native.lib().dfe_mesh_fault(nm.handle):
+        raise _native.DfeError(_native.ERR_CUDA, f"{what}: a fused 1-D kernel on this mesh exceeded its wait bound; the "
+                               "results of that call are NaN — rebuild the mesh handle")
+
+
+# --------------------------------------------------------------------------- host <-> device row streaming
+_PIPE_MIN_BYTES = 32 << 20       # below this a plain copy is as fast
+_PIPE_CHUNK_BYTES = 16 << 20     # smallest chunk worth a separate copy + launch
+_side = {}
+
+
+def _side_streams(dev: torch.device):
+    st = _side.get(dev.index)
+    if st is None:
+        st = _side[dev.index] = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+    return st
+
+
+def _row_chunks(B: int, n: int, host_io: bool):
+    """Row ranges of a (B, n) float64 batch: one range unless rows cross the host boundary and the batch is large."""
+    total = 8 * B * n
+    if not host_io or B < 2 or total < _PIPE_MIN_BYTES:
+        return [(0, B)]
+    k = int(min(8, B, max(1, total // _PIPE_CHUNK_BYTES)))
+    bs = -(-B // k)
+    return [(lo, min(B, lo + bs)) for lo in range(0, B, bs)]
+
+
+class _RowPipe:
+    """Streams the rows of a batch through the device while kernels run (one instance per forward / backward call).
+
+    ``in_host``  (B, n) CPU tensor or None: chunk j is copied into a rotating device buffer on the H2D stream (directly
+                 when pinned, else through two pinned staging buffers) and handed to the kernel as ``src``.
+    ``out_host`` (B, n) pinned CPU tensor or None: after the kernel of chunk j the rows of ``out_dev`` (a full device
+                 tensor) — or, when ``out_dev`` is None, of a rotating device buffer handed to the kernel as ``dst`` — are
+                 copied back on the D2H stream.
+    The compute stream is the caller's current stream; ``finish()`` makes the host wait for the D2H copies only.
+    """
+
+    NBUF = 3
+
+    def __init__(self, dev, n, chunks, in_host=None, out_host=None, out_dev=None):
+        self.dev, self.n, self.chunks = dev, n, chunks
+        self.in_host, self.out_host, self.out_dev = in_host, out_host, out_dev
+        self.main = torch.cuda.current_stream(dev)
+        self.h2d, self.d2h = _side_streams(dev)
+        bs = max(hi - lo for lo, hi in chunks)
+        nb = min(self.NBUF, len(chunks))
+        self.ibuf = [torch.empty((bs, n), dtype=torch.float64, device=dev) for _ in range(nb)] if in_host is not None else None
+        self.obuf = ([torch.empty((bs, n), dtype=torch.float64, device=dev) for _ in range(nb)]
+                     if (out_host is not None and out_dev is None) else None)
+        self.stage = None
+        if in_host is not None and not in_host.is_pinned():
+            self.stage = [torch.empty((bs, n), dtype=torch.float64, pin_memory=True) for _ in range(min(2, len(chunks)))]
+        ev = torch.cuda.Event
+        self.copied = [ev() for _ in chunks]
+        self.done = [ev() for _ in chunks]
+        self.back = [ev() for _ in chunks]
+        # buffers were allocated on the compute stream: order the side streams after everything enqueued so far
+        e0 = ev()
+        e0.record(self.main)
+        self.h2d.wait_event(e0)
+        self.d2h.wait_event(e0)
+        self._issued = 0
+        if in_host is not None:                 # copies run up to NBUF - 1 chunks ahead of the kernels
+            for j in range(min(nb - 1, len(chunks))):
+                self._issue_h2d(j)
+
+    def _issue_h2d(self, j):
+        lo, hi = self.chunks[j]
+        nb = len(self.ibuf)
+        with torch.cuda.stream(self.h2d):
+            if j >= nb:
+                self.h2d.wait_event(self.done[j - nb])          # the kernel that read this buffer has finished
+            src = self.in_host[lo:hi]
+            if self.stage is not None:
+                k = j % len(self.stage)
+                if j >= len(self.stage):
+                    self.copied[j - len(self.stage)].synchronize()   # staging buffer drained (host wait)
+                self.stage[k][:hi - lo].copy_(src)
+                src = self.stage[k][:hi - lo]
+            self.ibuf[j % nb][:hi - lo].copy_(src, non_blocking=True)
+            self.copied[j].record(self.h2d)
+        self._issued = j + 1
+
+    def run(self, kernel):
+        """kernel(j, lo, hi, src, dst): enqueue the work of rows [lo, hi) on the current stream."""
+        for j, (lo, hi) in enumerate(self.chunks):
+            src = dst = None
+            if self.in_host is not None:
+                while self._issued <= min(j + len(self.ibuf) - 1, len(self.chunks) - 1):
+                    self._issue_h2d(self._issued)
+                self.main.wait_event(self.copied[j])
+                src = self.ibuf[j % len(self.ibuf)][:hi - lo]
+            if self.obuf is not None:
+                nb = len(self.obuf)
+                if j >= nb:
+                    self.main.wait_event(self.back[j - nb])       # the D2H copy out of this buffer has finished
+                dst = self.obuf[j % nb][:hi - lo]
+            kernel(j, lo, hi, src, dst)
+            self.done[j].record(self.main)
+            if self.out_host is not None:
+                with torch.cuda.stream(self.d2h):
+                    self.d2h.wait_event(self.done[j])
+                    self.out_host[lo:hi].copy_(dst if dst is not None else self.out_dev[lo:hi], non_blocking=True)
+                    self.back[j].record(self.d2h)
+
+    def finish(self):
+        if self.out_host is not None:
+            self.back[-1].synchronize()
+
+
+def _pinned_like(B: int, n: int) -> torch.Tensor:
+    return torch.empty((B, n), dtype=torch.float64, pin_memory=True)
+
+
 class _FESolve(torch.autograd.Function):
-    """u = K(kappa)^{-1}-solve of the assembled P1 system; backward = adjoint solve + dL/dkappa, dL/df."""
+    """u = K(kappa)^{-1}-solve of the assembled P1 system; backward = adjoint solve + dL/dkappa, dL/df.
+
+    ``f`` is (B, n) float64 contiguous, on the CPU or on ``dev``; ``kappa`` float64 contiguous on ``dev``.  ``u`` is returned
+    on ``out_dev``; a device copy is kept for the adjoint either way."""
 
     @staticmethod
-    def forward(ctx, f: torch.Tensor, kappa: torch.Tensor, mesh: FEMesh, mode: int, opts: dict):
-        # f: (B, n) float64 contiguous CUDA; kappa: float64 contiguous CUDA, layout `mode`
-        dev = f.device
+    def forward(ctx, f: torch.Tensor, kappa: torch.Tensor, mesh: FEMesh, mode: int, opts: dict, dev: torch.device,
+                out_dev: torch.device):
         nm = mesh._native(dev.index)
         B, n = f.shape
         L = _native.lib()
-        u = torch.empty_like(f)
-        # fused 1-D path: chain meshes; per-element kappa only where one Neumann sweep suffices (<= 2e5 nodes)
-        per_elem = mode in (_native.KAPPA_PER_ELEMENT, _native.KAPPA_PER_SAMPLE_ELEMENT)
-        one_sweep = int(opts["n_refine"]) == 1 or (int(opts["n_refine"]) < 0 and n <= 200000)
-        fused = bool(nm.info.chain1d) and (not per_elem or one_sweep)
+        f_host = not f.is_cuda
+        ctx.f_host = f_host
+        out_host = out_dev.type != "cuda"
+        # fused 1-D path: decided once, here, for both directions (dfe_solve1d_supported)
+        fused = bool(nm.info.chain1d) and bool(L.dfe_solve1d_supported(nm.handle, mode, int(opts["n_refine"])))
+        if bool(nm.info.chain1d) and not fused and n > 200000:
+            # the only other route is Jacobi-PCG, which needs O(n) iterations on a 1-D chain: refuse instead
+            raise NotImplementedError(
+                f"1-D chain mesh with {n} nodes: above 2e5 nodes the fused path needs the multi-sweep kernel, which holds "
+                "every chunk of a sample co-resident (about 2 * #SMs * 3328 nodes, scalar / per-sample kappa only)")
         saved_mats = None
+        ctx.batch = None
         with torch.cuda.device(dev):
+            u = torch.empty((B, n), dtype=torch.float64, device=dev)
+            u_out = u
             if fused:
-                ws = _ws(L.dfe_solve1d_workspace_bytes(nm.handle, B), dev)
-                with _timed("solve1d_fwd", dev):
-                    _native.check(L.dfe_solve1d_fwd(nm.handle, B, f.data_ptr(), f.stride(0), kappa.data_ptr(), mode,
-                                                    int(opts["n_refine"]), u.data_ptr(), u.stride(0), ws.data_ptr(),
-                                                    ws.numel(), _stream(dev)))
+                chunks = _row_chunks(B, n, f_host or out_host)
+                ws = _ws(L.dfe_solve1d_workspace_bytes(nm.handle, max(hi - lo for lo, hi in chunks)), dev)
+                st = _stream(dev)
+                krow = kappa.numel() // B if mode in _PER_SAMPLE_MODES else 0
+                kflat = kappa.reshape(-1)
+                if len(chunks) == 1 and f_host:
+                    f = f.to(dev, non_blocking=f.is_pinned())
+                    f_host = False
+                stream_out = out_host and len(chunks) > 1
+                if stream_out:
+                    u_out = _pinned_like(B, n)
+
+                def kern(j, lo, hi, src, dst):
+                    fin = src if src is not None else f[lo:hi]
+                    with _timed("solve1d_fwd", dev):
+                        _native.check(L.dfe_solve1d_fwd(nm.handle, hi - lo, fin.data_ptr(), fin.stride(0),
+                                                        kflat[lo * krow:].data_ptr(), mode, int(opts["n_refine"]),
+                                                        u[lo:hi].data_ptr(), u.stride(0), ws.data_ptr(), ws.numel(), st))
+
+                if f_host or stream_out:
+                    pipe = _RowPipe(dev, n, chunks, f if f_host else None, u_out if stream_out else None, u)
+                    pipe.run(kern)
+                    pipe.finish()
+                else:                                       # everything on the device: one launch, no events
+                    kern(0, 0, B, None, None)
+                if out_host:
+                    if not stream_out:
+                        u_out = u.to(out_dev)
+                    _check_fault(nm, "dfe_solve1d_fwd")      # the host waited for u: the fault word is final
             else:
-                # many samples, one matrix, small mesh: one CTA per sample (config 5b)
+                if f_host:
+                    f = f.to(dev, non_blocking=f.is_pinned())
                 # many samples, one matrix: banded direct solver or one-CTA-per-sample PCG (config 5b)
-                ctx.batch = None
                 if B >= int(opts.get("batch_min", 2)) and mode in (_native.KAPPA_SCALAR, _native.KAPPA_PER_ELEMENT):
                     ctx.batch = _batch_solver(L, nm, opts)
                 fwd = {"band": _band_forward, "pcg": _batch_forward, None: _general_forward}[ctx.batch]
                 saved_mats = fwd(L, nm, f, kappa, mode, u, opts)
-        ctx.mesh, ctx.mode, ctx.opts, ctx.fused = mesh, mode, opts, fused
+                if out_host:
+                    u_out = u.to(out_dev)
+        ctx.mesh, ctx.mode, ctx.opts, ctx.fused, ctx.dev = mesh, mode, opts, fused, dev
         ctx.mats = saved_mats
-        if fused:
-            ctx.batch = None
         ctx.save_for_backward(u, kappa)
-        return u
+        return u_out
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, gbar: torch.Tensor):
         u, kappa = ctx.saved_tensors
         need_f, need_k = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        dev = u.device
+        dev = ctx.dev
         nm = ctx.mesh._native(dev.index)
         L = _native.lib()
         B, n = u.shape
+        mode = ctx.mode
         gbar = gbar.contiguous()
-        gf = torch.empty_like(u) if need_f else None
+        g_host = not gbar.is_cuda
+        gf_host = need_f and ctx.f_host
         gk = torch.empty_like(kappa)
         with torch.cuda.device(dev):
             if ctx.fused:
-                ws = _ws(L.dfe_solve1d_workspace_bytes(nm.handle, B), dev)
-                with _timed("solve1d_bwd", dev):
-                    _native.check(L.dfe_solve1d_bwd(nm.handle, B, gbar.data_ptr(), gbar.stride(0), u.data_ptr(),
-                                                    u.stride(0), kappa.data_ptr(), ctx.mode, int(ctx.opts["n_refine"]),
-                                                    _ptr(gf), gf.stride(0) if gf is not None else n, gk.data_ptr(),
-                                                    ws.data_ptr(), ws.numel(), _stream(dev)))
-            elif ctx.batch == "band":
-                _band_backward(L, nm, gbar, u, kappa, ctx.mode, ctx.mats, gf, gk, ctx.opts)
-            elif ctx.batch == "pcg":
-                _batch_backward(L, nm, gbar, u, kappa, ctx.mode, ctx.mats, gf, gk, ctx.opts)
+                chunks = _row_chunks(B, n, g_host or gf_host)
+                ws = _ws(L.dfe_solve1d_workspace_bytes(nm.handle, max(hi - lo for lo, hi in chunks)), dev)
+                st = _stream(dev)
+                per_sample = mode in _PER_SAMPLE_MODES
+                krow = kappa.numel() // B if per_sample else 0
+                kflat, gkflat = kappa.reshape(-1), gk.reshape(-1)
+                if len(chunks) == 1 and g_host:
+                    gbar = gbar.to(dev, non_blocking=gbar.is_pinned())
+                    g_host = False
+                gf = None
+                if need_f:
+                    gf = _pinned_like(B, n) if (gf_host and len(chunks) > 1) else torch.empty((B, n), dtype=torch.float64, device=dev)
+                stream_gf = need_f and not gf.is_cuda
+                # shared kappa: one partial per chunk, added in chunk order below (deterministic)
+                gk_parts = None if per_sample or len(chunks) == 1 else torch.empty((len(chunks), kappa.numel()), dtype=torch.float64, device=dev)
+
+                def kern(j, lo, hi, src, dst):
+                    gin = src if src is not None else gbar[lo:hi]
+                    gout = dst if dst is not None else (gf[lo:hi] if need_f else None)
+                    gko = gkflat[lo * krow:] if per_sample else (gkflat if gk_parts is None else gk_parts[j])
+                    with _timed("solve1d_bwd", dev):
+                        _native.check(L.dfe_solve1d_bwd(nm.handle, hi - lo, gin.data_ptr(), gin.stride(0), u[lo:hi].data_ptr(),
+                                                        u.stride(0), kflat[lo * krow:].data_ptr(), mode, int(ctx.opts["n_refine"]),
+                                                        _ptr(gout), gout.stride(0) if gout is not None else n, gko.data_ptr(),
+                                                        ws.data_ptr(), ws.numel(), st))
+
+                pipe = _RowPipe(dev, n, chunks, gbar if g_host else None, gf if stream_gf else None, None) if (g_host or stream_gf) else None
+                if pipe is not None:
+                    pipe.run(kern)
+                else:
+                    for j, (lo, hi) in enumerate(chunks):
+                        kern(j, lo, hi, None, None)
+                if gk_parts is not None:
+                    gk.copy_(gk_parts.sum(dim=0).reshape(gk.shape))   # torch.sum on CUDA is deterministic (no atomics)
+                if pipe is not None:
+                    pipe.finish()
+                if need_f and gf_host and gf.is_cuda:
+                    gf = gf.cpu()
             else:
-                _general_backward(L, nm, gbar, u, kappa, ctx.mode, ctx.mats, gf, gk, ctx.opts)
-        return gf, (gk if need_k else None), None, None, None
+                if g_host:
+                    gbar = gbar.to(dev, non_blocking=gbar.is_pinned())
+                gf = torch.empty_like(u) if need_f else None
+                if ctx.batch == "band":
+                    _band_backward(L, nm, gbar, u, kappa, mode, ctx.mats, gf, gk, ctx.opts)
+                elif ctx.batch == "pcg":
+                    _batch_backward(L, nm, gbar, u, kappa, mode, ctx.mats, gf, gk, ctx.opts)
+                else:
+                    _general_backward(L, nm, gbar, u, kappa, mode, ctx.mats, gf, gk, ctx.opts)
+                if gf_host:
+                    gf = gf.cpu()
+        return gf, (gk if need_k else None), None, None, None, None, None
+
+
+class _FEMisfit(torch.autograd.Function):
+    """loss = (1 / n_nodes) * sum_b sum_i (u_bi - u_data_bi)^2 and its gradients in two kernels (fused 1-D path):
+    the forward solve, then the misfit adjoint (``dfe_solve1d_bwd_misfit``) that forms gbar = 2 (u - u_data) / n_nodes on
+    the fly and accumulates the loss next to dL/dkappa.  The gradients are computed in ``forward`` (the loss is a
+    scalar, so ``backward`` only scales them) — this is the step of the reference's kappa-recovery loop
+    (examples/poisson_1d_demo.py:104-110) without ever materialising gbar.
+
+    ``out2`` (optional, shared kappa only): a persistent 2-double device buffer that receives
+    [sum_b dL/dkappa, loss] — the words a data-parallel step all-reduces."""
+
+    @staticmethod
+    def forward(ctx, f, kappa, u_data, mesh, mode, opts, out2, weight):
+        dev = f.device
+        nm = mesh._native(dev.index)
+        B, n = f.shape
+        L = _native.lib()
+        need_f = ctx.needs_input_grad[0]
+        per_sample = mode == _native.KAPPA_PER_SAMPLE
+        with torch.cuda.device(dev):
+            st = _stream(dev)
+            u = torch.empty((B, n), dtype=torch.float64, device=dev)
+            ws = _ws(L.dfe_solve1d_workspace_bytes(nm.handle, B), dev)
+            with _timed("solve1d_fwd", dev):
+                _native.check(L.dfe_solve1d_fwd(nm.handle, B, f.data_ptr(), f.stride(0), kappa.data_ptr(), mode,
+                                                int(opts["n_refine"]), u.data_ptr(), u.stride(0), ws.data_ptr(), ws.numel(), st))
+            gf = torch.empty((B, n), dtype=torch.float64, device=dev) if need_f else None
+            if per_sample:
+                gk = torch.empty(B, dtype=torch.float64, device=dev)
+                lossv = torch.empty(B, dtype=torch.float64, device=dev)
+                gk_ptr, loss_ptr = gk.data_ptr(), lossv.data_ptr()
+            else:
+                if out2 is None:
+                    out2 = torch.empty(2, dtype=torch.float64, device=dev)
+                gk_ptr, loss_ptr = out2.data_ptr(), out2.data_ptr() + 8
+            with _timed("solve1d_bwd_misfit", dev):
+                _native.check(L.dfe_solve1d_bwd_misfit(nm.handle, B, u_data.data_ptr(), u_data.stride(0), u.data_ptr(),
+                                                       u.stride(0), kappa.data_ptr(), mode, int(opts["n_refine"]),
+                                                       2.0 * weight / n,
+                                                       _ptr(gf), gf.stride(0) if gf is not None else n, gk_ptr, loss_ptr,
+                                                       ws.data_ptr(), ws.numel(), st))
+            if per_sample:
+                loss = lossv.sum()
+                gk = gk.reshape(kappa.shape)
+            elif any(ctx.needs_input_grad[:2]):
+                loss = out2[1].clone()
+                gk = out2[0].clone().reshape(kappa.shape)
+            else:                       # no graph (the sharded sweep reads out2 itself): no copy kernels
+                loss = out2[1]
+                gk = out2[0].reshape(kappa.shape)
+        opts["last_u"] = u
+        ctx.save_for_backward(gk, gf if gf is not None else torch.empty(0, device=dev))
+        ctx.has_gf = gf is not None
+        return loss
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout):
+        gk, gf = ctx.saved_tensors
+        return (gout * gf if ctx.has_gf and ctx.needs_input_grad[0] else None,
+                gout * gk if ctx.needs_input_grad[1] else None, None, None, None, None, None, None)
 
 
 def _raise_batch_status(status, iters, relres, tol, what):
@@ -403,7 +664,7 @@ class DifferentiableFESolver(nn.Module):
     """
 
     def __init__(self, mesh: FEMesh, kappa: float = 1.0, *, pcg_tol: float = 1e-13,
-                 pcg_maxit: Optional[int] = None, n_refine: int = -1):
+                 pcg_maxit: Optional[int] = None, n_refine: int = -1, out_device=None):
         super().__init__()
         self.mesh = mesh
         # Same rule as the reference (solver.py:35-39): numbers become 0-dim float64 tensors, tensors are
@@ -414,6 +675,7 @@ class DifferentiableFESolver(nn.Module):
         else:
             self._kappa = kappa.to(dtype=torch.float64)
         self._opts = {"pcg_tol": pcg_tol, "pcg_maxit": pcg_maxit, "n_refine": n_refine}
+        self._out_device = None if out_device is None else torch.device(out_device)
 
     @property
     def kappa(self) -> torch.Tensor:
@@ -424,8 +686,7 @@ class DifferentiableFESolver(nn.Module):
         """[(iterations, relative residual)] of the most recent general-path forward (diagnostics)."""
         return self._opts.get("last_pcg")
 
-    def forward(self, f: torch.Tensor) -> torch.Tensor:
-        """Solve ``-div(kappa grad u) = f``; ``f`` is ``(n_nodes,)`` or ``(B, n_nodes)``, any float dtype."""
+    def _resolve(self, f: torch.Tensor):
         mesh = self.mesh
         if mesh.dim not in (1, 2):
             raise NotImplementedError("Only 1D and 2D supported")
@@ -436,16 +697,60 @@ class DifferentiableFESolver(nn.Module):
         batched = f.dim() == 2
         if f.dim() not in (1, 2) or f.shape[-1] != mesh.n_nodes:
             raise ValueError(f"f must have shape (n_nodes,) or (B, n_nodes) with n_nodes={mesh.n_nodes}, got {tuple(f.shape)}")
-        dev = f.device if f.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        dev = f.device if f.is_cuda else (self._out_device if self._out_device is not None and self._out_device.type == "cuda"
+                                          else torch.device("cuda", torch.cuda.current_device()))
         if dev.index is None:
             dev = torch.device("cuda", torch.cuda.current_device())
-        kappa = self.kappa
         B = f.shape[0] if batched else 1
-        mode = _kappa_mode(kappa, B, mesh.n_elements, batched)
-        # dtype/device moves are ordinary differentiable torch ops; the Function sees f64 CUDA tensors
-        f_dev = f.to(device=dev, dtype=torch.float64).reshape(B, mesh.n_nodes).contiguous()
-        k_dev = kappa.to(device=dev).contiguous()
-        u = _FESolve.apply(f_dev, k_dev, mesh, mode, self._opts)
+        mode = _kappa_mode(self.kappa, B, mesh.n_elements, batched)
+        return dev, batched, B, mode
+
+    def forward(self, f: torch.Tensor) -> torch.Tensor:
+        """Solve ``-div(kappa grad u) = f``; ``f`` is ``(n_nodes,)`` or ``(B, n_nodes)``, any float dtype.
+
+        ``u`` comes back on ``f``'s device (CPU in -> CPU out, as the reference's callers expect) unless the module was
+        built with ``out_device="cuda"``, which keeps the solution of a host-resident ``f`` on the GPU."""
+        mesh = self.mesh
+        dev, batched, B, mode = self._resolve(f)
+        out_dev = self._out_device if self._out_device is not None else f.device
+        if out_dev.type == "cuda" and out_dev.index is None:
+            out_dev = dev
+        # dtype moves and reshapes are ordinary differentiable torch ops; the Function sees (B, n) float64 rows and
+        # does the host <-> device transfers itself (streamed for large batches)
+        f2 = f.to(dtype=torch.float64).reshape(B, mesh.n_nodes).contiguous()
+        k_dev = self.kappa.to(device=dev).contiguous()
+        u = _FESolve.apply(f2, k_dev, mesh, mode, self._opts, dev, out_dev)
         if not batched:
             u = u.reshape(mesh.n_nodes)
-        return u if f.is_cuda else u.to(f.device)
+        return u
+
+    def misfit(self, f: torch.Tensor, u_data: torch.Tensor, out2: Optional[torch.Tensor] = None,
+               weight: float = 1.0) -> torch.Tensor:
+        """Data-misfit loss ``weight * sum_b mean_i (u_b(f_b, kappa) - u_data_b)^2`` of the solution against ``u_data``
+        (for one sample: the reference demo's ``((solver(f) - u_data) ** 2).mean()``,
+        examples/poisson_1d_demo.py:104-110), differentiable w.r.t. ``kappa`` and ``f``.
+
+        On the fused 1-D path (chain mesh, scalar or per-sample kappa, CUDA inputs) this is two kernels: the forward
+        solve and a misfit adjoint that forms the upstream gradient on the fly — gbar and the squared differences never
+        touch HBM.  Elsewhere it is evaluated as ``((self(f) - u_data) ** 2).sum() / n_nodes``."""
+        mesh = self.mesh
+        dev, batched, B, mode = self._resolve(f)
+        n = mesh.n_nodes
+        fast = (f.is_cuda and u_data.is_cuda and mode in (_native.KAPPA_SCALAR, _native.KAPPA_PER_SAMPLE)
+                and bool(mesh._native(dev.index).info.chain1d) and n <= 163840
+                and self._opts["n_refine"] in (-1, 1) and f.dtype == torch.float64 and u_data.dtype == torch.float64)
+        if fast:
+            f2 = f.reshape(B, n).contiguous()
+            d2 = u_data.detach().reshape(B, n).contiguous()
+            fast = f2.data_ptr() % 16 == 0 and d2.data_ptr() % 16 == 0
+        if fast:
+            k_dev = self.kappa.to(device=dev).contiguous()
+            try:
+                return _FEMisfit.apply(f2, k_dev, d2, mesh, mode, self._opts, out2, float(weight))
+            except NotImplementedError:      # the pipelined kernel does not take this call (DFE_ERR_UNSUPPORTED)
+                pass
+        u = self(f)
+        loss = ((u - u_data.to(u.device)) ** 2).sum() * (float(weight) / n)
+        if out2 is not None:
+            raise NotImplementedError("misfit(out2=...) needs the fused misfit adjoint (chain mesh, shared scalar kappa)")
+        return loss

@@ -99,12 +99,27 @@ int dfe_mesh_free_nodes_host(const dfe_mesh* m, const int64_t** free_nodes, int6
  * One persistent kernel per call: per-sample HBM traffic is read f + write u (forward),
  * read gbar + read u (+ write gf) (backward).  K is never materialised.
  *   f, u, gbar, gf : (B, n_nodes) f64 with row strides ld* (elements)
- *   kappa          : SCALAR -> [1], PER_SAMPLE -> [B]   (other modes: DFE_ERR_UNSUPPORTED for now)
+ *   kappa          : SCALAR -> [1], PER_SAMPLE -> [B], PER_ELEMENT -> [n_el], PER_SAMPLE_ELEMENT -> (B, n_el)
+ *                    (the per-element layouts run with one Neumann sweep only, i.e. up to 2e5 nodes)
  *   n_refine       : Neumann/refinement sweeps after the structured solve (1 meets 1e-12 up to
  *                    ~2e5 nodes; pass 2 beyond; <0 selects automatically)
- *   gkappa         : PER_SAMPLE -> [B];  SCALAR -> [1] (sum over the batch, fixed order)
+ *   gkappa         : PER_SAMPLE -> [B];  SCALAR -> [1] (sum over the batch, fixed order);
+ *                    PER_ELEMENT -> [n_el] (sum over the batch);  PER_SAMPLE_ELEMENT -> (B, n_el)
  *   gf may be NULL (f does not require grad).
  * Workspace: dfe_solve1d_workspace_bytes(m, B) bytes of device memory, contents undefined.
+ *
+ * dfe_solve1d_supported   1 if the fused path takes this mesh in BOTH directions for (kappa_mode, n_refine); the
+ *                         host layer asks once, in forward, and routes the call to the general path otherwise.
+ * dfe_solve1d_bwd_misfit  the adjoint of a data-misfit loss in ONE pass (BASELINE config 5, reference
+ *                         examples/poisson_1d_demo.py:104-110: loss = mean((u - u_data)^2); loss.backward()):
+ *                         reads u_data and u, forms gbar = scale * (u - u_data) on the fly (Dirichlet entries dropped),
+ *                         and returns  loss = (scale / 2) * sum_i (u_i - u_data_i)^2  next to dL/dkappa —
+ *                         SCALAR: gkappa[1], loss[1] summed over the batch (pass adjacent words of one buffer and
+ *                         all-reduce it); PER_SAMPLE: gkappa[B], loss[B].  Pipelined kernel only (chain mesh up to
+ *                         163840 nodes, 16-byte aligned rows), else DFE_ERR_UNSUPPORTED.
+ * dfe_mesh_fault          sticky fault word of the handle (0 = healthy): set when a wait inside a fused 1-D kernel
+ *                         exceeded its bound; the outputs of that call are overwritten with NaN and every later
+ *                         dfe_solve1d_* call on the handle fails.  Read it after synchronising the stream.
  */
 size_t dfe_solve1d_workspace_bytes(const dfe_mesh* m, int64_t B);
 int dfe_solve1d_fwd(const dfe_mesh* m, int64_t B, const double* f, int64_t ldf, const double* kappa,
@@ -113,6 +128,11 @@ int dfe_solve1d_fwd(const dfe_mesh* m, int64_t B, const double* f, int64_t ldf, 
 int dfe_solve1d_bwd(const dfe_mesh* m, int64_t B, const double* gbar, int64_t ldg, const double* u,
                     int64_t ldu, const double* kappa, int kappa_mode, int n_refine, double* gf,
                     int64_t ldgf, double* gkappa, void* ws, size_t ws_bytes, void* stream);
+int dfe_solve1d_bwd_misfit(const dfe_mesh* m, int64_t B, const double* u_data, int64_t ldd, const double* u,
+                           int64_t ldu, const double* kappa, int kappa_mode, int n_refine, double scale, double* gf,
+                           int64_t ldgf, double* gkappa, double* loss, void* ws, size_t ws_bytes, void* stream);
+int dfe_solve1d_supported(const dfe_mesh* m, int kappa_mode, int n_refine);
+int dfe_mesh_fault(const dfe_mesh* m);
 
 /* ---------------------------------------------------------------- general path (2-D triangles, and 1-D meshes that are not chains)
  * dfe_assemble   replaces solver.py:82-96 / :112-145: K on the structural CSR of all nodes and F,

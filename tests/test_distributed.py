@@ -74,7 +74,23 @@ def _worker(rank, world_size, port, out):
         # packed all-reduce of several tensors in one collective
         a, b = torch.full((3,), float(rank + 1), dtype=torch.float64), torch.tensor(10.0 * (rank + 1), dtype=torch.float64)
         D.allreduce_sum_([a, b])
-        out[rank] = (float(loss), float(grad), a.tolist(), float(b), D.shard_bounds(n_total))
+        # MisfitSweep: the persistent [dL/dkappa, loss] buffer and its single all-reduce (the local kernels are CUDA-only,
+        # so the local step is the oracle here; the product's local_step writes the same two words)
+        class OracleSweep(D.MisfitSweep):
+            def local_step(self, kap):
+                k = kap.detach().clone().requires_grad_(True)
+                u = _OracleSolve.apply(k, self.f, self.mesh)
+                l = ((u - self.u_data) ** 2).sum() / (u.shape[-1] * self.n_total)
+                (g,) = torch.autograd.grad(l, k)
+                self.red[0], self.red[1] = g, l.detach()
+
+        sw = OracleSweep(mesh, D.shard(f), D.shard(u_data), n_total)
+        buf = sw.red.data_ptr()
+        l2, g2 = sw.step(kappa)
+        l2, g2 = float(l2), float(g2)
+        sw.step(kappa * 1.5)
+        assert sw.red.data_ptr() == buf and not sw.registered          # persistent buffer; no NCCL pool on gloo
+        out[rank] = (float(loss), float(grad), a.tolist(), float(b), D.shard_bounds(n_total), l2, g2)
     finally:
         dist.destroy_process_group()
 
@@ -91,9 +107,11 @@ def test_sharded_step_matches_single_process():
     loss = ((_OracleSolve.apply(k, f, mesh) - u_data) ** 2).mean()
     loss.backward()
     for r in (0, 1):
-        l, g, a, b, bounds = out[r]
+        l, g, a, b, bounds, l2, g2 = out[r]
         assert abs(l - float(loss)) <= 1e-15 + 1e-13 * abs(float(loss))
         assert abs(g - float(k.grad)) <= 1e-13 * abs(float(k.grad))
+        assert abs(l2 - float(loss)) <= 1e-15 + 1e-13 * abs(float(loss))
+        assert abs(g2 - float(k.grad)) <= 1e-13 * abs(float(k.grad))
         assert a == [3.0, 3.0, 3.0] and b == 30.0
     assert out[0][4] == (0, 5) and out[1][4] == (5, 10)
     assert out[0][0] == out[1][0] and out[0][1] == out[1][1]        # identical on every rank
