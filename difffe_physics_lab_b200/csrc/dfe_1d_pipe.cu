@@ -860,7 +860,11 @@ int run_cfg(const dfe_mesh* m, PP p, cudaStream_t st, int gbound, int* G_used, u
   }
   // cooperative launch: the CTAs of a group wait for each other's chunk totals, so all NG*G CTAs must be co-resident —
   // the runtime checks exactly that and fails the launch (instead of hanging) under MPS / SM partitioning
-  {
+  static const bool plain_launch = getenv("DFE_PIPE_PLAIN_LAUNCH") != nullptr;   // A/B switch for measurements
+  if (plain_launch) {
+    kern<<<static_cast<unsigned>(g.NG * g.G), THREADS, g.smem, st>>>(p);
+    DFE_CUDA_OK(cudaGetLastError());
+  } else {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(static_cast<unsigned>(g.NG * g.G));
     cfg.blockDim = dim3(THREADS);
@@ -979,8 +983,11 @@ int pipe1d_run(const dfe_mesh* m, long long B, bool bwd, const double* in0, long
         break;
     }
   } else if (misfit) {
-    rc = !sk ? run_cfg<true, 11, 8, 2, 2, false, true>(m, p, st, gb, &G, ticket)
-             : run_cfg<true, 11, 8, 2, 2, true, true>(m, p, st, gb, &G, ticket);
+    // 9 nodes per thread: the misfit adjoint holds LB + 2 u-row slots next to the 7 ring slots, and with 11 nodes per
+    // thread the chunk that still fits the shared memory fills only 6 of the 8 compute warps (measured on config 5a:
+    // 6.0 ms per launch; the groups-per-iteration-time figure NG / (R + overhead) decides, not the bytes per CTA)
+    rc = !sk ? run_cfg<true, 9, 8, 2, 2, false, true>(m, p, st, gb, &G, ticket)
+             : run_cfg<true, 9, 8, 2, 2, true, true>(m, p, st, gb, &G, ticket);
   } else {
     switch (id) {
       case 1: rc = run_cfg<true, 9, 11, 2, 2>(m, p, st, gb, &G, ticket); break;
@@ -998,7 +1005,9 @@ int pipe1d_run(const dfe_mesh* m, long long B, bool bwd, const double* in0, long
     DFE_CUDA_OK(cudaGetLastError());
   }
   const long long nk = p.per_sample ? B : 1;
-  k1d_pipe_poison<<<m->sm_count, 256, 0, st>>>(p.err, out, ldo, B, p.nn, bwd ? gkappa : nullptr, nk,
+  static const bool no_poison = getenv("DFE_PIPE_NO_POISON") != nullptr;   // A/B switch for measurements
+  if (!no_poison)
+    k1d_pipe_poison<<<m->sm_count, 256, 0, st>>>(p.err, out, ldo, B, p.nn, bwd ? gkappa : nullptr, nk,
                                                misfit ? misfit->loss : nullptr, nk);
   DFE_CUDA_OK(cudaGetLastError());
   return DFE_OK;
