@@ -64,7 +64,7 @@ struct P1D {
   int* cnt;              // [B] arrival counters (zeroed per call)
   double* summ;          // [B][MAX_STAGES][G][4] chunk summaries
   double* gkpart;        // backward: [B][G] partial dL/dkappa
-  int* err;              // mesh handle's fault word (mapped host memory): set if a wait exceeded its bound
+  int* err;              // mesh handle's device fault word: set if a wait exceeded its bound
 };
 
 // Exclusive prefix (carry) of chunk c and the total over the G chunk summaries of one stage.
@@ -535,7 +535,7 @@ P1D base_params(const dfe_mesh* m, long long B, const Plan& pl, const double* ka
   p.cnt = reinterpret_cast<int*>(w + pl.off_cnt);
   p.summ = reinterpret_cast<double*>(w + pl.off_summ);
   p.gkpart = reinterpret_cast<double*>(w + pl.off_gk);
-  p.err = m->d_fault;
+  p.err = m->d_fault_dev;
   return p;
 }
 
@@ -581,6 +581,7 @@ extern "C" int dfe_solve1d_fwd(const dfe_mesh* m, int64_t B, const double* f, in
   } else {
     DFE_CUDA_OK(cudaMemsetAsync(p.cnt, 0, static_cast<size_t>(B) * sizeof(int), st));
     rc = launch<false, R_FWD>(m, B, p, pl, st);
+    if (rc == DFE_OK) rc = dfe::poison1d_launch(m, u, ldu, B, p.nn, nullptr, 0, nullptr, 0, st);
   }
   if (cur != m->info.device) cudaSetDevice(cur);
   return rc;
@@ -644,6 +645,7 @@ int solve1d_bwd_impl(const dfe_mesh* m, int64_t B, const double* gbar, int64_t l
       dfe::set_error("%s: reduce kernel launch failed", who);
       rc = DFE_ERR_CUDA;
     }
+    if (rc == DFE_OK) rc = dfe::poison1d_launch(m, gf, ldgf, B, p.nn, gkappa, p.per_sample ? B : 1, nullptr, 0, st);
   }
   if (cur != m->info.device) cudaSetDevice(cur);
   return rc;

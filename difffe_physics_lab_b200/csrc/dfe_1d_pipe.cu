@@ -62,7 +62,7 @@ struct PP {
   double* gkpart;             // backward: [B][G+2] partial dL/dkappa (chunks, boundary terms of sweep 0 and 1)
   double* losspart;           // misfit adjoint: [B][G] partial sum_i (u_i - u_data_i)^2
   double mf_scale;            // misfit adjoint: gbar = mf_scale * (u - u_data), formed on the fly (in0 = u_data)
-  int* err;                   // mesh handle's fault word (mapped host memory): set to 1 if a wait exceeded its bound
+  int* err;                   // mesh handle's device fault word: set to 1 if a wait exceeded its bound
   int backoff;                // cycles a fold-warp lane waits between two polls of a chunk total (DFE_PIPE_BACKOFF)
 };
 
@@ -778,14 +778,16 @@ __global__ void __launch_bounds__(256) k1d_pipe_gk(const double* part, const dou
   }
 }
 
-// A wait that exceeded its bound leaves garbage behind: make it loud.  Runs after every pipelined launch; reads the
-// handle's fault word (one load per CTA) and, only if it is set, overwrites every output of the call with NaN.
-__global__ void k1d_pipe_poison(const int* err, double* out, long long ldo, long long B, int nn, double* gk,
-                                long long ngk, double* loss, long long nloss) {
+// A wait that exceeded its bound leaves garbage behind: make it loud.  Runs after every fused 1-D launch as ONE CTA;
+// reads the handle's device fault word and, only if it is set, raises the host-visible word and overwrites every
+// output of the call with NaN (slow, but this is the fault path).
+__global__ void k1d_pipe_poison(const int* err, int* err_host, double* out, long long ldo, long long B, int nn,
+                                double* gk, long long ngk, double* loss, long long nloss) {
   __shared__ int bad;
   if (threadIdx.x == 0) bad = *reinterpret_cast<const volatile int*>(err);
   __syncthreads();
   if (!bad) return;
+  if (threadIdx.x == 0) *reinterpret_cast<volatile int*>(err_host) = 1;
   const double nan = __longlong_as_double(0x7FF8000000000000ll);
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   const long long t0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -962,7 +964,7 @@ int pipe1d_run(const dfe_mesh* m, long long B, bool bwd, const double* in0, long
   p.mf_scale = misfit ? misfit->scale : 0.0;
   double* blk = reinterpret_cast<double*>(w + L.blk);
   unsigned* ticket = reinterpret_cast<unsigned*>(w + L.ticket);
-  p.err = m->d_fault;   // sticky, host-visible; k1d_pipe_poison turns a fault into NaN outputs
+  p.err = m->d_fault_dev;   // sticky; k1d_pipe_poison turns a fault into NaN outputs and raises the host-visible word
   int rc, G = 0;
   const int id = cfg_id();
   static const int backoff = [] { const char* e = getenv("DFE_PIPE_BACKOFF"); return e ? atoi(e) : 0; }();
@@ -1005,10 +1007,12 @@ int pipe1d_run(const dfe_mesh* m, long long B, bool bwd, const double* in0, long
     DFE_CUDA_OK(cudaGetLastError());
   }
   const long long nk = p.per_sample ? B : 1;
-  static const bool no_poison = getenv("DFE_PIPE_NO_POISON") != nullptr;   // A/B switch for measurements
-  if (!no_poison)
-    k1d_pipe_poison<<<m->sm_count, 256, 0, st>>>(p.err, out, ldo, B, p.nn, bwd ? gkappa : nullptr, nk,
-                                               misfit ? misfit->loss : nullptr, nk);
+  return poison1d_launch(m, out, ldo, B, p.nn, bwd ? gkappa : nullptr, nk, misfit ? misfit->loss : nullptr, nk, st);
+}
+
+int poison1d_launch(const dfe_mesh* m, double* out, long long ldo, long long B, int nn, double* gk, long long ngk,
+                    double* loss, long long nloss, cudaStream_t st) {
+  k1d_pipe_poison<<<1, 1024, 0, st>>>(m->d_fault_dev, m->d_fault, out, ldo, B, nn, gk, ngk, loss, nloss);
   DFE_CUDA_OK(cudaGetLastError());
   return DFE_OK;
 }

@@ -66,6 +66,11 @@ struct Misfit1D {
   double* loss;   // device: [1] (shared kappa: summed over the batch) or [B] (per-sample kappa)
 };
 
+// after a fused 1-D launch: if the handle's device fault word is set, overwrite the outputs with NaN and raise the
+// host-visible word (one tiny CTA when healthy)
+int poison1d_launch(const dfe_mesh* m, double* out, long long ldo, long long B, int nn, double* gk, long long ngk,
+                    double* loss, long long nloss, cudaStream_t st);
+
 }  // namespace dfe
 
 struct dfe_mesh {
@@ -84,6 +89,9 @@ struct dfe_mesh {
   // every later dfe_solve1d_* call on this handle fails with DFE_ERR_CUDA
   int* h_fault = nullptr;
   int* d_fault = nullptr;
+  // device-resident copy of the fault word: the kernels raise THIS one (a read of mapped host memory from a kernel
+  // costs ~150 us on B200); the poison kernel that follows every fused launch copies it into the host-visible word
+  int* d_fault_dev = nullptr;
   // ---- device
   dfe::MeshDev dev{};
   std::vector<void*> allocs;  // every cudaMalloc owned by the handle

@@ -325,6 +325,15 @@ extern "C" int dfe_mesh_create(int dim, int64_t n_nodes, int64_t n_el, const dou
           m->h_fault = static_cast<int*>(hf);
           m->d_fault = static_cast<int*>(df);
           *m->h_fault = 0;
+          void* dd = nullptr;
+          if (cudaMalloc(&dd, 64) == cudaSuccess && cudaMemset(dd, 0, 64) == cudaSuccess) {
+            m->allocs.push_back(dd);
+            m->d_fault_dev = static_cast<int*>(dd);
+          } else {
+            cudaGetLastError();
+            set_error("dfe_mesh_create: cannot allocate the device fault word");
+            rc = DFE_ERR_CUDA;
+          }
         } else {
           cudaGetLastError();
           if (hf) cudaFreeHost(hf);

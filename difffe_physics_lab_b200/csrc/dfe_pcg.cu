@@ -19,18 +19,7 @@
 
 namespace {
 
-// Grid-wide fixed-order sum of two values for a cooperative (co-resident) launch, fused with the grid barrier the
-// CG phases need anyway: *data-as-flag* — every CTA release-stores its two partial sums into its slot of the epoch's
-// buffer (pre-set to an all-ones sentinel), warp 0 of every CTA polls all G slots with relaxed loads and adds them in
-// a fixed order (lane-strided, then a butterfly), one acquire fence, one CTA barrier.  No atomic, no separate counter,
-// no second read of a partials array: one L2 round trip after the last CTA arrives.  Three buffers rotate; a CTA
-// resets its own slot of epoch E-2 just before it publishes epoch E (everybody finished reading E-2 before
-// publishing E-1, which this CTA has seen complete), and the release orders the reset before the publication.
-constexpr unsigned long long SENTQ = 0xFFFFFFFFFFFFFFFFull;
-__device__ __forceinline__ unsigned long long as_bits(double v) {
-  const unsigned long long u = static_cast<unsigned long long>(__double_as_longlong(v));
-  return u == SENTQ ? 0x7FF8000000000000ull : u;   // a NaN that happens to carry the sentinel payload
-}
+#include "dfe_gridsync.cuh"   // grid_sum2: fixed-order grid reduction fused with the phase barrier, bounded polls
 
 constexpr int PT = 768;  // threads per CTA: one CTA per SM (148 arrivals per grid barrier instead of 444)
 constexpr int PW = PT / 32;
@@ -49,75 +38,17 @@ struct PcgArgs {
   double* p1;
   double* q;
   double* part;   // [3 epochs][gridDim.x][2] exchange slots, pre-set to the sentinel
-  double* out;    // [0]=iterations, [1]=relres, [2]=status (0 ok, 4 not converged, 5 breakdown)
+  double* out;    // [0]=iterations, [1]=relres, [2]=status (0 ok, 4 not converged, 5 breakdown, 7 barrier timeout)
+  int* abort_flag; // zeroed before the launch; raised by a grid barrier that waited longer than its bound
   double tol;
   long long maxit;
   int backoff;    // cycles an early arriver waits between two polls of a slot
 };
 
-// Sums of `v0` and `v1` over the whole grid; every thread of every CTA returns the same bits.  Doubles as the grid
-// barrier between the CG phases (all global writes of every CTA before the call are visible after it).
-__device__ __forceinline__ void grid_sum2(double* slots, unsigned int& epoch, double& v0, double& v1, double* sh,
-                                          const int backoff) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int G = gridDim.x;
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    v0 += __shfl_xor_sync(0xffffffffu, v0, d);
-    v1 += __shfl_xor_sync(0xffffffffu, v1, d);
-  }
-  if (lane == 0) { sh[2 * warp] = v0; sh[2 * warp + 1] = v1; }
-  __syncthreads();
-  ++epoch;
-  if (warp == 0) {
-    double a = 0.0, b = 0.0;
-    for (int w = lane; w < PW; w += 32) { a += sh[2 * w]; b += sh[2 * w + 1]; }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      a += __shfl_xor_sync(0xffffffffu, a, d);
-      b += __shfl_xor_sync(0xffffffffu, b, d);
-    }
-    double* cur = slots + static_cast<size_t>(epoch % 3) * 2 * G;
-    if (lane == 0) {
-      unsigned long long* old = reinterpret_cast<unsigned long long*>(slots + static_cast<size_t>((epoch + 1) % 3) * 2 * G) + 2 * blockIdx.x;
-      asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(old), "l"(SENTQ), "l"(SENTQ) : "memory");
-      asm volatile("st.release.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(cur + 2 * blockIdx.x), "l"(as_bits(a)), "l"(as_bits(b)) : "memory");
-    }
-    double sa = 0.0, sb = 0.0;
-    for (int i = lane; i < G; i += 32) {
-      unsigned long long ua, ub;
-      while (true) {
-        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(ua), "=l"(ub) : "l"(cur + 2 * i) : "memory");
-        if (ua != SENTQ && ub != SENTQ) break;
-        // early arrivers back off for ~250 cycles (a busy wait on the clock, not __nanosleep, which oversleeps by
-        // microseconds on B200): hundreds of spinning lanes on a handful of L2 lines delay the stores they wait for
-        const long long t0 = clock64();
-        while (clock64() - t0 < backoff) {}
-      }
-      sa += __longlong_as_double(static_cast<long long>(ua));
-      sb += __longlong_as_double(static_cast<long long>(ub));
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      sa += __shfl_xor_sync(0xffffffffu, sa, d);
-      sb += __shfl_xor_sync(0xffffffffu, sb, d);
-    }
-    // (the butterfly above made every lane's polls complete; one fence, then the CTA barrier, as a grid barrier does)
-    __syncwarp();
-    if (lane == 0) {
-      asm volatile("fence.acq_rel.gpu;" ::: "memory");
-      sh[2 * PW] = sa;
-      sh[2 * PW + 1] = sb;
-    }
-  }
-  __syncthreads();
-  v0 = sh[2 * PW];
-  v1 = sh[2 * PW + 1];
-}
-
 __global__ void __launch_bounds__(PT, 1) k_pcg(const PcgArgs A) {
   unsigned int epoch = 0;
   __shared__ double sh[2 * PW + 2];
+  const GridSync gs{A.part, A.abort_flag, A.backoff};
   const int lane = threadIdx.x & 31;
   // A CTA owns a CONTIGUOUS block of SELL slices and walks it front to back, PW slices at a time: the neighbours a
   // row gathers (rows +-1 and, on a structured mesh, +- one mesh line) were touched by this SM a trip or two ago and
@@ -144,7 +75,7 @@ __global__ void __launch_bounds__(PT, 1) k_pcg(const PcgArgs A) {
       rz = fma(bi, zi, rz);
     }
   }
-  grid_sum2(A.part, epoch, bb, rz, sh, A.backoff);
+  grid_sum2<PW>(gs, epoch, bb, rz, sh);
   const double bnorm = sqrt(bb);
   double status = 0.0, relres = 0.0;
   long long it = 0;
@@ -210,7 +141,11 @@ __global__ void __launch_bounds__(PT, 1) k_pcg(const PcgArgs A) {
         }
       }
       double unused = 0.0;
-      grid_sum2(A.part, epoch, pq, unused, sh, A.backoff);
+      grid_sum2<PW>(gs, epoch, pq, unused, sh);
+      if (grid_aborted(gs)) {
+        status = 7.0;
+        break;
+      }
       if (!(pq > 0.0) || !isfinite(pq)) {
         status = 5.0;
         break;
@@ -244,7 +179,11 @@ __global__ void __launch_bounds__(PT, 1) k_pcg(const PcgArgs A) {
           rr = fma(ri2, ri2, rr);
         }
       }
-      grid_sum2(A.part, epoch, rz_new, rr, sh, A.backoff);   // two independent reductions share one exchange
+      grid_sum2<PW>(gs, epoch, rz_new, rr, sh);   // two independent reductions share one exchange
+      if (grid_aborted(gs)) {
+        status = 7.0;
+        break;
+      }
       ++it;
       relres = sqrt(rr) / bnorm;
       if (!isfinite(rr)) {
@@ -297,7 +236,7 @@ int plan_pcg(const dfe_mesh* m, PcgPlan* pl, bool query_device) {
   pl->off_q = off; off += vec;
   pl->off_part = off; off += 6 * static_cast<size_t>(max_grid) * sizeof(double);
   pl->off_out = off; off += 256;
-  pl->off_bar = off; off += 256;
+  pl->off_bar = off; off += 256;   // abort word of the bounded grid barriers
   pl->total = off;
   return DFE_OK;
 }
@@ -351,6 +290,7 @@ extern "C" int dfe_pcg(const dfe_mesh* m, const double* sell_vals, const double*
     A.q = reinterpret_cast<double*>(w + pl.off_q);
     A.part = reinterpret_cast<double*>(w + pl.off_part);
     A.out = reinterpret_cast<double*>(w + pl.off_out);
+    A.abort_flag = reinterpret_cast<int*>(w + pl.off_bar);
     A.tol = tol;
     A.maxit = maxit;
     static const int backoff = [] { const char* e = getenv("DFE_PCG_BACKOFF"); return e ? atoi(e) : 250; }();
@@ -358,6 +298,7 @@ extern "C" int dfe_pcg(const dfe_mesh* m, const double* sell_vals, const double*
     void* args[] = {&A};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e = cudaMemsetAsync(A.part, 0xFF, 6 * static_cast<size_t>(pl.grid) * sizeof(double), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(A.abort_flag, 0, sizeof(int), st);
     if (e == cudaSuccess) e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_pcg), dim3(pl.grid), dim3(PT), args, 0, st);
     if (e != cudaSuccess) {
       dfe::set_error("dfe_pcg: cooperative launch failed: %s", cudaGetErrorString(e));
@@ -376,6 +317,10 @@ extern "C" int dfe_pcg(const dfe_mesh* m, const double* sell_vals, const double*
           dfe::set_error("dfe_pcg: not converged after %lld iterations (relative residual %.3e, tol %.3e)",
                          static_cast<long long>(out[0]), out[1], tol);
           rc = DFE_ERR_NOT_CONVERGED;
+        } else if (out[2] == 7.0) {
+          dfe::set_error("dfe_pcg: a grid barrier waited longer than its bound (lost co-resident CTA?) at iteration %lld",
+                         static_cast<long long>(out[0]));
+          rc = DFE_ERR_CUDA;
         } else if (out[2] == 5.0) {
           dfe::set_error("dfe_pcg: breakdown at iteration %lld (p^T K p <= 0 or non-finite): K_free is not SPD — "
                          "does the mesh have a Dirichlet node?",
