@@ -643,13 +643,14 @@ def run_b200_2d(args, w, rank, local_rank, world, dev):
     peak, peak_src = measured_peak()
     N, nnz = I.n_free, I.nnz_free
     bytes_iter = 12 * nnz + 104 * N + 4 * (N + 1)              # SURVEY §8d accounting convention
-    calls, ms_pcg = ksum.get("pcg", (0, 0.0))
+    solver2d = "mg" if "mg_pcg" in ksum else "jacobi"
+    calls, ms_pcg = ksum.get("mg_pcg") or ksum.get("pcg", (0, 0.0))
     iters_step = its.get("fwd", 0) + its.get("adj", 0)
     roofline = None
     if calls:
         ms_launch = ms_pcg / calls
         alg = bytes_iter * iters_step / 2.0                     # per PCG launch (forward and adjoint solves average)
-        roofline = {"bound": "hbm", "kernel": "k_pcg (cooperative Jacobi-PCG)", "achieved": alg / (ms_launch * 1e-3) / 1e9,
+        roofline = {"bound": "hbm", "kernel": "k_mgpcg (cooperative multigrid-preconditioned CG)" if solver2d == "mg" else "k_pcg (cooperative Jacobi-PCG)", "achieved": alg / (ms_launch * 1e-3) / 1e9,
                     "peak": peak, "unit": "GB/s", "frac": alg / (ms_launch * 1e-3) / 1e9 / peak,
                     "traffic": measured_traffic("k_pcg") if args.workload == "c4" and not args.n_elements else None,
                     "note": "achieved = SURVEY 8(d) accounting bytes / time; the gathered vectors stay in the 126 MB L2 "

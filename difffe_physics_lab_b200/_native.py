@@ -19,8 +19,10 @@ import subprocess
 PKG = pathlib.Path(__file__).resolve().parent
 ROOT = PKG.parent
 LIB_PATH = PKG / "libdfe_b200.so"
-SOURCES = ["dfe_mesh.cu", "dfe_1d.cu", "dfe_1d_split.cu", "dfe_1d_pipe.cu", "dfe_general.cu", "dfe_pcg.cu", "dfe_batch.cu"]
-HEADERS = [PKG / "csrc" / "dfe_internal.h", PKG / "csrc" / "dfe_1d_common.cuh", ROOT / "include" / "dfe.h"]
+SOURCES = ["dfe_mesh.cu", "dfe_1d.cu", "dfe_1d_split.cu", "dfe_1d_pipe.cu", "dfe_general.cu", "dfe_pcg.cu", "dfe_mg.cu",
+           "dfe_batch.cu"]
+HEADERS = [PKG / "csrc" / "dfe_internal.h", PKG / "csrc" / "dfe_1d_common.cuh", PKG / "csrc" / "dfe_gridsync.cuh",
+           ROOT / "include" / "dfe.h"]
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOT_CONVERGED, ERR_BREAKDOWN, ERR_WORKSPACE = range(7)
 KAPPA_SCALAR, KAPPA_PER_SAMPLE, KAPPA_PER_ELEMENT, KAPPA_PER_SAMPLE_ELEMENT = range(4)
@@ -33,6 +35,7 @@ SYMBOLS = [
     "dfe_solve1d_supported", "dfe_mesh_fault",
     "dfe_assemble", "dfe_eliminate", "dfe_pcg_workspace_bytes", "dfe_pcg", "dfe_scatter", "dfe_gather_free",
     "dfe_grad_workspace_bytes", "dfe_grad",
+    "dfe_mg_supported", "dfe_mg_hierarchy_bytes", "dfe_mg_workspace_bytes", "dfe_mg_setup", "dfe_mg_pcg",
     "dfe_batch_supported", "dfe_batch_fwd", "dfe_batch_bwd",
     "dfe_band_supported", "dfe_band_factor_bytes", "dfe_band_workspace_bytes", "dfe_band_factor", "dfe_band_fwd", "dfe_band_bwd",
 ]
@@ -173,6 +176,16 @@ def lib() -> C.CDLL:
     L.dfe_grad_workspace_bytes.argtypes = [vp]
     L.dfe_grad.restype = ci
     L.dfe_grad.argtypes = [vp, vp, vp, vp, ci, vp, vp, vp, sz, vp]
+    L.dfe_mg_supported.restype = ci
+    L.dfe_mg_supported.argtypes = [vp]
+    L.dfe_mg_hierarchy_bytes.restype = sz
+    L.dfe_mg_hierarchy_bytes.argtypes = [vp]
+    L.dfe_mg_workspace_bytes.restype = sz
+    L.dfe_mg_workspace_bytes.argtypes = [vp]
+    L.dfe_mg_setup.restype = ci
+    L.dfe_mg_setup.argtypes = [vp, vp, vp, sz, vp]
+    L.dfe_mg_pcg.restype = ci
+    L.dfe_mg_pcg.argtypes = [vp, vp, vp, vp, dbl, i64, ci, C.POINTER(i64), C.POINTER(dbl), vp, sz, vp]
     L.dfe_batch_supported.restype = ci
     L.dfe_batch_supported.argtypes = [vp]
     L.dfe_batch_fwd.restype = ci

@@ -235,14 +235,15 @@ extern "C" int dfe_eliminate(const dfe_mesh* m, const double* vals_full, const d
   int prev;
   int rc = enter(m, "dfe_eliminate", &prev);
   if (rc) return rc;
-  if (!vals_full || !F || !sell_vals || !F_free || !dinv) {
+  if (!vals_full || !F || !F_free || !dinv) {
     dfe::set_error("dfe_eliminate: null argument");
     rc = DFE_ERR_INVALID;
   } else if (m->dev.n_free > 0) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     k_eliminate<<<blocks(m->dev.n_free, 128), 128, 0, st>>>(m->dev, vals_full, F, vals_free, F_free, dinv);
-    k_fill_sell<<<blocks(m->dev.sell_nnz, 256) < 4096u ? blocks(m->dev.sell_nnz, 256) : 4096u, 256, 0, st>>>(
-        m->dev, vals_full, sell_vals);
+    if (sell_vals)
+      k_fill_sell<<<blocks(m->dev.sell_nnz, 256) < 4096u ? blocks(m->dev.sell_nnz, 256) : 4096u, 256, 0, st>>>(
+          m->dev, vals_full, sell_vals);
     rc = check_launch("dfe_eliminate");
   }
   leave(m, prev);

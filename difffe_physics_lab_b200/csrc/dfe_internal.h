@@ -77,6 +77,9 @@ struct dfe_mesh {
   dfe_mesh_info info{};
   // ---- host-side symbolic data (int64 copies exposed through the ABI)
   std::vector<int64_t> h_rowptr, h_col, h_rowptr_f, h_col_f, h_free;
+  // ---- structured 2-D mesh (topology of FEMesh.rectangle(gx, gy) with every boundary node Dirichlet): quads per side,
+  // 0 when the mesh is anything else.  Enables the multigrid-preconditioned solver (dfe_mg_*).
+  int grid_nx = 0, grid_ny = 0;
   // ---- 1-D chain description
   bool chain = false;
   bool bc_left = false, bc_right = false, lift_left_first = true;

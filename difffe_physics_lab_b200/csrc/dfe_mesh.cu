@@ -252,6 +252,28 @@ extern "C" int dfe_mesh_create(int dim, int64_t n_nodes, int64_t n_el, const dou
     m->lift_left_first = !(m->bc_left && m->bc_right) || dir_order[0] < dir_order[n - 1];
   }
 
+  // ---- rectangle() topology (mesh.py:79-121): node id = row*(gx+1)+col, quad (r,c) -> [a,b,d], [b,c,d] with
+  // a = r(gx+1)+c, b = a+1, c = a+gx+2, d = a+gx+1, and exactly the boundary nodes Dirichlet
+  if (dim == 2 && ne >= 2 && h_elems[0] == 0 && h_elems[1] == 1 && h_elems[2] >= 2) {
+    const long long gx = h_elems[2] - 1;
+    const long long gy = (n % (gx + 1) == 0) ? n / (gx + 1) - 1 : 0;
+    bool ok = gx >= 2 && gy >= 2 && static_cast<long long>(ne) == 2 * gx * gy && nd == 2 * (gx + gy);
+    for (long long q = 0; ok && q < gx * gy; ++q) {
+      const int a = static_cast<int>((q / gx) * (gx + 1) + q % gx), b = a + 1, c = a + static_cast<int>(gx) + 2, d = c - 1;
+      const int* t = h_elems.data() + 6 * q;
+      ok = t[0] == a && t[1] == b && t[2] == d && t[3] == b && t[4] == c && t[5] == d;
+    }
+    for (long long p = 0; ok && p < n; ++p) {
+      const long long r = p / (gx + 1), cc = p % (gx + 1);
+      const bool boundary = r == 0 || r == gy || cc == 0 || cc == gx;
+      ok = boundary == (dir_order[p] >= 0);
+    }
+    if (ok) {
+      m->grid_nx = static_cast<int>(gx);
+      m->grid_ny = static_cast<int>(gy);
+    }
+  }
+
   // ---- host copies exposed through the ABI
   m->h_rowptr.assign(rowptr.begin(), rowptr.end());
   m->h_col.assign(col.begin(), col.end());

@@ -44,7 +44,7 @@ class KernelTimer:
     # + k1d_pipe_poison)
     KERNELS_PER_CALL = {"solve1d_fwd": 3, "solve1d_bwd": 4, "solve1d_bwd_misfit": 4, "batch_fwd": 1, "batch_bwd": 1, "band_factor": 1,
                         "band_fwd": 3, "band_bwd": 3, "assemble": 1, "eliminate": 2, "pcg": 1, "scatter": 1,
-                        "gather": 1, "grad": 3}
+                        "gather": 1, "grad": 3, "mg_setup": 20, "mg_pcg": 1}
 
     def __init__(self):
         self.events = []
@@ -567,8 +567,35 @@ def _batch_backward(L, nm, gbar, u, kappa, mode, mats, gf, gk, opts):
     gk.copy_(gk_b.sum(dim=0).reshape(gk.shape))   # torch.sum on CUDA is deterministic (no atomics)
 
 
+def _use_mg(L, nm, opts) -> bool:
+    """Structured 2-D mesh (FEMesh.rectangle() topology): CG preconditioned by a multigrid V-cycle instead of Jacobi."""
+    want = opts.get("solver2d", "auto")
+    if want not in ("auto", "mg", "jacobi"):
+        raise ValueError(f"solver2d must be 'auto', 'mg' or 'jacobi', got {want!r}")
+    return want != "jacobi" and bool(L.dfe_mg_supported(nm.handle))
+
+
+def _solve_general(L, nm, mat, rhs, x, opts, ws_j, ws_m, st, key):
+    """One linear solve with the operator `mat` = ('mg', hierarchy) or ('jacobi', sell, dinv); returns (iters, relres)."""
+    it, rel = C.c_int64(0), C.c_double(0.0)
+    tol = float(opts["pcg_tol"])
+    dev = rhs.device
+    if mat[0] == "mg":
+        with _timed("mg_pcg", dev):
+            _native.check(L.dfe_mg_pcg(nm.handle, mat[1].data_ptr(), rhs.data_ptr(), x.data_ptr(), tol,
+                                       int(opts["pcg_maxit"] or 1000), int(opts.get("mg_nu", 2)), C.byref(it), C.byref(rel),
+                                       ws_m.data_ptr(), ws_m.numel(), st))
+    else:
+        with _timed("pcg", dev):
+            _native.check(L.dfe_pcg(nm.handle, mat[1].data_ptr(), mat[2].data_ptr(), rhs.data_ptr(), x.data_ptr(), tol,
+                                    int(opts["pcg_maxit"] or max(10 * nm.info.n_free, 1000)), C.byref(it), C.byref(rel),
+                                    ws_j.data_ptr(), ws_j.numel(), st))
+    return it.value, rel.value
+
+
 def _general_forward(L, nm, f, kappa, mode, u, opts):
-    """assemble -> eliminate -> PCG -> scatter, per sample; the matrix is reused when kappa is shared."""
+    """assemble -> eliminate -> PCG -> scatter, per sample; the matrix (and its multigrid hierarchy) is built once when
+    kappa is shared by the batch."""
     dev = f.device
     I = nm.info
     B = f.shape[0]
@@ -577,38 +604,56 @@ def _general_forward(L, nm, f, kappa, mode, u, opts):
     shared = mode in (_native.KAPPA_SCALAR, _native.KAPPA_PER_ELEMENT)
     amode = _native.KAPPA_SCALAR if mode in (_native.KAPPA_SCALAR, _native.KAPPA_PER_SAMPLE) else _native.KAPPA_PER_ELEMENT
     kflat = kappa.reshape(-1)
-    ws = _ws(L.dfe_pcg_workspace_bytes(nm.handle), dev)
+    mg = _use_mg(L, nm, opts)
+    ws_j = _ws(L.dfe_pcg_workspace_bytes(nm.handle), dev)
+    ws_m = _ws(L.dfe_mg_workspace_bytes(nm.handle), dev) if mg else None
     vals = torch.empty(max(I.nnz_full, 1), dtype=torch.float64, device=dev)
     F = torch.empty(I.n_nodes, dtype=torch.float64, device=dev)
     x = torch.empty(max(I.n_free, 1), dtype=torch.float64, device=dev)
+    Ff = torch.empty(max(I.n_free, 1), dtype=torch.float64, device=dev)
     mats = []
     iters = []
     for b in range(B):
-        sell = torch.empty(max(I.sell_nnz, 1), dtype=torch.float64, device=dev)
-        dinv = torch.empty(max(I.n_free, 1), dtype=torch.float64, device=dev)
-        Ff = torch.empty(max(I.n_free, 1), dtype=torch.float64, device=dev)
         if mode == _native.KAPPA_PER_SAMPLE:
             kb = kflat[b:b + 1]
         elif mode == _native.KAPPA_PER_SAMPLE_ELEMENT:
             kb = kflat[b * n_el:(b + 1) * n_el]
         else:
             kb = kflat
-        # assembly is repeated per sample even for shared kappa: F depends on f[b]; cheap next to PCG
+        # assembly is repeated per sample even for shared kappa: F depends on f[b]; cheap next to the solve
         with _timed("assemble", dev):
             _native.check(L.dfe_assemble(nm.handle, kb.data_ptr(), amode, f[b].data_ptr(), vals.data_ptr(), F.data_ptr(), st))
+        new_matrix = not shared or b == 0
+        mat = mats[0] if not new_matrix else None
+        if new_matrix and mg:
+            hier = _ws(L.dfe_mg_hierarchy_bytes(nm.handle), dev)
+            try:
+                with _timed("mg_setup", dev):
+                    _native.check(L.dfe_mg_setup(nm.handle, vals.data_ptr(), hier.data_ptr(), hier.numel(), st))
+                mat = ("mg", hier)
+            except NotImplementedError:          # not numerically a 5-point operator (distorted grid): Jacobi-PCG
+                if opts.get("solver2d", "auto") == "mg":
+                    raise
+                mg = False
+        if mat is None:
+            sell = torch.empty(max(I.sell_nnz, 1), dtype=torch.float64, device=dev)
+            dinv = torch.empty(max(I.n_free, 1), dtype=torch.float64, device=dev)
+            mat = ("jacobi", sell, dinv)
         with _timed("eliminate", dev):
-            _native.check(L.dfe_eliminate(nm.handle, vals.data_ptr(), F.data_ptr(), None, sell.data_ptr(), Ff.data_ptr(),
-                                          dinv.data_ptr(), st))
-        it, rel = C.c_int64(0), C.c_double(0.0)
-        with _timed("pcg", dev):
-            _native.check(L.dfe_pcg(nm.handle, sell.data_ptr(), dinv.data_ptr(), Ff.data_ptr(), x.data_ptr(),
-                                    float(opts["pcg_tol"]), int(opts["pcg_maxit"] or max(10 * I.n_free, 1000)),
-                                    C.byref(it), C.byref(rel), ws.data_ptr(), ws.numel(), st))
-        iters.append((it.value, rel.value))
+            if new_matrix and mat[0] == "jacobi":
+                _native.check(L.dfe_eliminate(nm.handle, vals.data_ptr(), F.data_ptr(), None, mat[1].data_ptr(), Ff.data_ptr(),
+                                              mat[2].data_ptr(), st))
+            else:                                 # only the lifted load is needed
+                if "dinv_scratch" not in opts or opts["dinv_scratch"].numel() != max(I.n_free, 1) or opts["dinv_scratch"].device != dev:
+                    opts["dinv_scratch"] = torch.empty(max(I.n_free, 1), dtype=torch.float64, device=dev)
+                _native.check(L.dfe_eliminate(nm.handle, vals.data_ptr(), F.data_ptr(), None, None, Ff.data_ptr(),
+                                              opts["dinv_scratch"].data_ptr(), st))
+        iters.append(_solve_general(L, nm, mat, Ff, x, opts, ws_j, ws_m, st, "last_pcg"))
         _native.check(L.dfe_scatter(nm.handle, x.data_ptr(), 0, u[b].data_ptr(), st))
-        if not shared or b == 0:
-            mats.append((sell, dinv))
+        if new_matrix:
+            mats.append(mat)
     opts["last_pcg"] = iters
+    opts["last_solver2d"] = mats[0][0] if mats else None
     return mats
 
 
@@ -619,7 +664,8 @@ def _general_backward(L, nm, gbar, u, kappa, mode, mats, gf, gk, opts):
     st = _stream(dev)
     shared = mode in (_native.KAPPA_SCALAR, _native.KAPPA_PER_ELEMENT)
     gmode = _native.KAPPA_SCALAR if mode in (_native.KAPPA_SCALAR, _native.KAPPA_PER_SAMPLE) else _native.KAPPA_PER_ELEMENT
-    ws = _ws(L.dfe_pcg_workspace_bytes(nm.handle), dev)
+    ws_j = _ws(L.dfe_pcg_workspace_bytes(nm.handle), dev)
+    ws_m = _ws(L.dfe_mg_workspace_bytes(nm.handle), dev) if any(m[0] == "mg" for m in mats) else None
     gws = _ws(L.dfe_grad_workspace_bytes(nm.handle), dev)
     gfree = torch.empty(max(I.n_free, 1), dtype=torch.float64, device=dev)
     lam_free = torch.empty(max(I.n_free, 1), dtype=torch.float64, device=dev)
@@ -628,14 +674,9 @@ def _general_backward(L, nm, gbar, u, kappa, mode, mats, gf, gk, opts):
     gk_b = torch.empty((B, nk), dtype=torch.float64, device=dev)
     iters = []
     for b in range(B):
-        sell, dinv = mats[0] if shared else mats[b]
+        mat = mats[0] if shared else mats[b]
         _native.check(L.dfe_gather_free(nm.handle, gbar[b].data_ptr(), gfree.data_ptr(), st))
-        it, rel = C.c_int64(0), C.c_double(0.0)
-        with _timed("pcg", dev):
-            _native.check(L.dfe_pcg(nm.handle, sell.data_ptr(), dinv.data_ptr(), gfree.data_ptr(), lam_free.data_ptr(),
-                                    float(opts["pcg_tol"]), int(opts["pcg_maxit"] or max(10 * I.n_free, 1000)),
-                                    C.byref(it), C.byref(rel), ws.data_ptr(), ws.numel(), st))
-        iters.append((it.value, rel.value))
+        iters.append(_solve_general(L, nm, mat, gfree, lam_free, opts, ws_j, ws_m, st, "last_pcg_adjoint"))
         _native.check(L.dfe_scatter(nm.handle, lam_free.data_ptr(), 1, lam.data_ptr(), st))
         with _timed("grad", dev):
             _native.check(L.dfe_grad(nm.handle, lam.data_ptr(), u[b].data_ptr(), None, gmode, gk_b[b].data_ptr(),
@@ -661,10 +702,16 @@ class DifferentiableFESolver(nn.Module):
         which keeps ``u`` and the gradients within 1e-9 of the reference's dense solve).
     n_refine : keyword-only
         1D fused path: number of Neumann sweeps after the structured solve (-1 = automatic).
+    solver2d, mg_nu : keyword-only
+        2D single-mesh solves: ``"auto"`` uses CG preconditioned by a multigrid V(mg_nu, mg_nu) cycle on meshes with
+        the structure of ``FEMesh.rectangle()`` and Jacobi-PCG elsewhere; ``"jacobi"`` / ``"mg"`` force one.
+    out_device : keyword-only
+        where ``u`` is returned (default: the device of ``f``).
     """
 
     def __init__(self, mesh: FEMesh, kappa: float = 1.0, *, pcg_tol: float = 1e-13,
-                 pcg_maxit: Optional[int] = None, n_refine: int = -1, out_device=None):
+                 pcg_maxit: Optional[int] = None, n_refine: int = -1, out_device=None, solver2d: str = "auto",
+                 mg_nu: int = 2):
         super().__init__()
         self.mesh = mesh
         # Same rule as the reference (solver.py:35-39): numbers become 0-dim float64 tensors, tensors are
@@ -674,7 +721,7 @@ class DifferentiableFESolver(nn.Module):
             self._kappa = torch.tensor(kappa, dtype=torch.float64)
         else:
             self._kappa = kappa.to(dtype=torch.float64)
-        self._opts = {"pcg_tol": pcg_tol, "pcg_maxit": pcg_maxit, "n_refine": n_refine}
+        self._opts = {"pcg_tol": pcg_tol, "pcg_maxit": pcg_maxit, "n_refine": n_refine, "solver2d": solver2d, "mg_nu": mg_nu}
         self._out_device = None if out_device is None else torch.device(out_device)
 
     @property

@@ -141,7 +141,7 @@ int dfe_mesh_fault(const dfe_mesh* m);
  *                kappa_mode SCALAR or PER_ELEMENT.  vals_full[nnz_full], F[n_nodes].
  * dfe_eliminate  replaces solver.py:162-171: F_free = F[free] - K[free,D] g (dict order),
  *                K_free = K[free][:,free] (CSR order into vals_free if non-NULL, and SELL-32 into
- *                sell_vals), dinv = 1/diag(K_free).
+ *                sell_vals if non-NULL), dinv = 1/diag(K_free).
  * dfe_pcg        replaces solver.py:174 (torch.linalg.solve) and, called on gbar_free, the adjoint
  *                solve of LinalgSolveExBackward0 (K symmetric): Jacobi-PCG in one cooperative
  *                kernel, deterministic dot products, stops when the recursive ||r||/||rhs|| <= tol.
@@ -167,6 +167,27 @@ int dfe_gather_free(const dfe_mesh* m, const double* v_full, double* v_free, voi
 size_t dfe_grad_workspace_bytes(const dfe_mesh* m);
 int dfe_grad(const dfe_mesh* m, const double* lam_full, const double* u, const double* kappa,
              int kappa_mode, double* gkappa, double* gf, void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------- structured 2-D meshes: multigrid-preconditioned CG
+ * For meshes with the topology of FEMesh.rectangle() (reference mesh.py:79-121: node id = row*(nx+1)+col, triangles
+ * [a,b,d], [b,c,d] per quad, every boundary node Dirichlet) K_free is numerically a 5-point operator on the grid of
+ * interior nodes, and Jacobi-PCG (dfe_pcg) needs O(nx) iterations (7435 at 1024 x 1024 with a 1e3 contrast).  These
+ * entry points replace solver.py:174 / the adjoint solve by CG preconditioned with a V(nu, nu) multigrid cycle
+ * (damped Jacobi, operator-dependent interpolation, Galerkin coarse operators): ~50 iterations, same stopping rule.
+ *   dfe_mg_supported   1 if the mesh has that structure (and >= 1024 unknowns)
+ *   dfe_mg_setup       vals_full from dfe_assemble -> hierarchy (dfe_mg_hierarchy_bytes(m) bytes of device memory;
+ *                      keep it for the adjoint solve).  Synchronises the stream.  DFE_ERR_UNSUPPORTED if the assembled
+ *                      matrix is not numerically 5-point (node coordinates moved off the grid): use dfe_pcg.
+ *   dfe_mg_pcg         like dfe_pcg (rhs / x on the free numbering, recursive ||r|| <= tol ||rhs||, synchronises,
+ *                      DFE_ERR_NOT_CONVERGED / _BREAKDOWN); nu = smoothing sweeps before and after each coarse-grid
+ *                      correction (1..4; 2 is the default of the host layer); ws: dfe_mg_workspace_bytes(m) bytes.
+ */
+int dfe_mg_supported(const dfe_mesh* m);
+size_t dfe_mg_hierarchy_bytes(const dfe_mesh* m);
+size_t dfe_mg_workspace_bytes(const dfe_mesh* m);
+int dfe_mg_setup(const dfe_mesh* m, const double* vals_full, void* hier, size_t hier_bytes, void* stream);
+int dfe_mg_pcg(const dfe_mesh* m, const void* hier, const double* rhs, double* x, double tol, int64_t maxit, int nu,
+               int64_t* iters_host, double* relres_host, void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------- batched small systems sharing one matrix
  * (BASELINE config 5b: many forcing samples, shared kappa, small 2-D mesh).  Replaces, for every sample b of the
