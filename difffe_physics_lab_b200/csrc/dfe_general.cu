@@ -10,6 +10,8 @@
 //                1/diag(K_free), CSR values of K_free;  k_fill_sell copies K_free into SELL-32.
 //   k_scatter / k_gather   solver.py:177-181 and the restriction of gbar to free rows.
 //   k_grad_elem / k_grad_f the closed-form backward of the assembly.
+#include <cstdlib>
+
 #include "dfe_internal.h"
 
 namespace {
@@ -42,11 +44,26 @@ __device__ __forceinline__ Elem2D elem2d(const MeshDev& M, int e, int n[3]) {
   return E;
 }
 
-__global__ void k_assemble(const MeshDev M, const double* __restrict__ kappa, int per_elem,
-                           const double* __restrict__ f, double* __restrict__ vals, double* __restrict__ F) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= M.n_nodes) return;
-  for (int k = M.rowptr[p]; k < M.rowptr[p + 1]; ++k) vals[k] = 0.0;
+// Row-owner assembly for arbitrary meshes.  The row is accumulated in a thread-local array (rows of up to ROWMAX
+// structural entries — every P1 mesh of reasonable quality) and written once; wider rows fall back to read-modify-write
+// in global memory.  Both orders of additions are the reference's.
+constexpr int ROWMAX = 16;
+
+template <bool LOCAL>
+__device__ __forceinline__ void assemble_row(const MeshDev& M, int p, const double* __restrict__ kappa, int per_elem,
+                                             const double* __restrict__ f, double* __restrict__ vals, double* __restrict__ F) {
+  const int r0 = M.rowptr[p], r1 = M.rowptr[p + 1];
+  double acc[ROWMAX];
+  if (LOCAL) {
+#pragma unroll
+    for (int k = 0; k < ROWMAX; ++k) acc[k] = 0.0;
+  } else {
+    for (int k = r0; k < r1; ++k) vals[k] = 0.0;
+  }
+  auto add = [&](int slot, double v) {
+    if (LOCAL) acc[slot - r0] = __dadd_rn(acc[slot - r0], v);
+    else vals[slot] = __dadd_rn(vals[slot], v);
+  };
   double Fp = 0.0;
   for (int a = M.adj_ptr[p]; a < M.adj_ptr[p + 1]; ++a) {
     const int e = M.adj_elem[a];
@@ -58,13 +75,8 @@ __global__ void k_assemble(const MeshDev M, const double* __restrict__ kappa, in
       const double ke = __ddiv_rn(kap, h);                  // :88
       // row `loc` of k_e [[1,-1],[-1,1]]  (:89-92: K[i,i]+k, K[i,j]-k, K[j,i]-k, K[j,j]+k)
       const int s0 = M.adj_slot[2 * a], s1 = M.adj_slot[2 * a + 1];
-      if (loc == 0) {
-        vals[s0] = __dadd_rn(vals[s0], ke);
-        vals[s1] = __dsub_rn(vals[s1], ke);
-      } else {
-        vals[s0] = __dsub_rn(vals[s0], ke);
-        vals[s1] = __dadd_rn(vals[s1], ke);
-      }
+      add(s0, loc == 0 ? ke : -ke);                         // x - k == x + (-k) bit for bit
+      add(s1, loc == 0 ? -ke : ke);
       Fp = __dadd_rn(Fp, __dmul_rn(__ddiv_rn(h, 2.0), f[p]));  // :95-96
     } else {
       int n[3];
@@ -75,8 +87,7 @@ __global__ void k_assemble(const MeshDev M, const double* __restrict__ kappa, in
       for (int q = 0; q < 3; ++q) {
         // k_pq = kappa*(b_p b_q + c_p c_q)/(4 area)   (:139)
         const double num = __dmul_rn(kap, __dadd_rn(__dmul_rn(E.b[loc], E.b[q]), __dmul_rn(E.c[loc], E.c[q])));
-        const int sl = M.adj_slot[3 * a + q];
-        vals[sl] = __dadd_rn(vals[sl], __ddiv_rn(num, den));
+        add(M.adj_slot[3 * a + q], __ddiv_rn(num, den));
       }
       // F_p += area/3 * (f_i+f_j+f_k)/3   (:143-145)
       const double fc = __ddiv_rn(__dadd_rn(__dadd_rn(f[n[0]], f[n[1]]), f[n[2]]), 3.0);
@@ -84,6 +95,103 @@ __global__ void k_assemble(const MeshDev M, const double* __restrict__ kappa, in
     }
   }
   F[p] = Fp;
+  if (LOCAL)
+    for (int k = r0; k < r1; ++k) vals[k] = acc[k - r0];
+}
+
+__global__ void k_assemble(const MeshDev M, const double* __restrict__ kappa, int per_elem,
+                           const double* __restrict__ f, double* __restrict__ vals, double* __restrict__ F) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= M.n_nodes) return;
+  if (M.rowptr[p + 1] - M.rowptr[p] <= ROWMAX) assemble_row<true>(M, p, kappa, per_elem, f, vals, F);
+  else assemble_row<false>(M, p, kappa, per_elem, f, vals, F);
+}
+
+// ---- structured variant for meshes with the element pattern of FEMesh.rectangle(gx, gy) (mesh.py:92-120).
+// The adjacency of a node is known in closed form there: node p = (r, c) touches, in ascending element id,
+//   quad (r-1, c-1) tri 1 = [S, C, W]      quad (r-1, c) tri 0 = [S, SE, C]   and tri 1 = [SE, E, C]
+//   quad (r, c-1)   tri 0 = [W, C, NW]     and tri 1 = [C, N, NW]             quad (r, c) tri 0 = [C, E, N]
+// (S = p-gx-1, SE = p-gx, W = p-1, E = p+1, NW = p+gx, N = p+gx+1 — which is also the ascending column order of the
+// CSR row), so the kernel needs no adjacency lists, no slot tables and no connectivity: it reads coordinates, kappa
+// and f (coalesced along a mesh line, neighbours from L1), accumulates the row in registers in the reference's
+// element order with the reference's operation order, and writes the row once — through shared memory, so that the
+// stores of a CTA are one contiguous coalesced stream.  Same bits as k_assemble (and as the reference's dense K, F).
+constexpr int AG_T = 256;
+
+__device__ __forceinline__ void tri_row(const double (&x)[3], const double (&y)[3], int loc, double kap, double (&k)[3],
+                                        double& area, bool& keep) {
+  const double t1 = __dmul_rn(__dsub_rn(x[1], x[0]), __dsub_rn(y[2], y[0]));
+  const double t2 = __dmul_rn(__dsub_rn(x[2], x[0]), __dsub_rn(y[1], y[0]));
+  area = __dmul_rn(0.5, fabs(__dsub_rn(t1, t2)));          // solver.py:119
+  keep = !(area < AREA_EPS);                                // :120-121
+  const double b[3] = {__dsub_rn(y[1], y[2]), __dsub_rn(y[2], y[0]), __dsub_rn(y[0], y[1])};
+  const double c[3] = {__dsub_rn(x[2], x[1]), __dsub_rn(x[0], x[2]), __dsub_rn(x[1], x[0])};
+  const double den = __dmul_rn(4.0, area);
+#pragma unroll
+  for (int q = 0; q < 3; ++q)   // k_pq = kappa*(b_p b_q + c_p c_q)/(4 area)   (:139)
+    k[q] = __ddiv_rn(__dmul_rn(kap, __dadd_rn(__dmul_rn(b[loc], b[q]), __dmul_rn(c[loc], c[q]))), den);
+}
+
+__global__ void __launch_bounds__(AG_T) k_assemble_grid(const MeshDev M, int gx, int gy, const double* __restrict__ kappa,
+                                                        int per_elem, const double* __restrict__ f,
+                                                        double* __restrict__ vals, double* __restrict__ F) {
+  __shared__ double stage[7 * AG_T];
+  const int p0 = blockIdx.x * AG_T;
+  const int p = p0 + threadIdx.x;
+  const int np1 = gx + 1;
+  const bool live = p < M.n_nodes;
+  const int pend = min(p0 + AG_T, M.n_nodes);
+  const int base0 = M.rowptr[p0], base1 = M.rowptr[pend];
+  if (live) {
+    const int r = p / np1, cc = p - r * np1;
+    const bool hasS = r > 0, hasN = r < gy, hasW = cc > 0, hasE = cc < gx;
+    // slots: 0 S, 1 SE, 2 W, 3 C, 4 E, 5 NW, 6 N
+    const int nid[7] = {p - np1, p - gx, p - 1, p, p + 1, p + gx, p + np1};
+    const bool ex[7] = {hasS, hasS && hasE, hasW, true, hasE, hasN && hasW, hasN};
+    double xs[7], ys[7], fs[7], v[7];
+    const double2* xy = reinterpret_cast<const double2*>(M.nodes);
+#pragma unroll
+    for (int s = 0; s < 7; ++s) {
+      v[s] = 0.0;
+      xs[s] = ys[s] = fs[s] = 0.0;
+      if (ex[s]) {
+        const double2 c2 = xy[nid[s]];
+        xs[s] = c2.x;
+        ys[s] = c2.y;
+        fs[s] = f[nid[s]];
+      }
+    }
+    double Fp = 0.0;
+    // (element exists, element id, node slots in element order, position of p)
+    const int qS = (r - 1) * gx + cc, qN = r * gx + cc;   // quads (r-1, c) and (r, c)
+    const bool eex[6] = {hasS && hasW, hasS && hasE, hasS && hasE, hasN && hasW, hasN && hasW, hasN && hasE};
+    const int eid[6] = {2 * (qS - 1) + 1, 2 * qS, 2 * qS + 1, 2 * (qN - 1), 2 * (qN - 1) + 1, 2 * qN};
+    const int en[6][3] = {{0, 3, 2}, {0, 1, 3}, {1, 4, 3}, {2, 3, 5}, {3, 6, 5}, {3, 4, 6}};
+    const int eloc[6] = {1, 2, 2, 1, 0, 0};
+#pragma unroll
+    for (int t = 0; t < 6; ++t) {
+      if (!eex[t]) continue;
+      const double kap = kappa[per_elem ? eid[t] : 0];
+      const double ex3[3] = {xs[en[t][0]], xs[en[t][1]], xs[en[t][2]]};
+      const double ey3[3] = {ys[en[t][0]], ys[en[t][1]], ys[en[t][2]]};
+      double k[3], area;
+      bool keep;
+      tri_row(ex3, ey3, eloc[t], kap, k, area, keep);
+      if (!keep) continue;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) v[en[t][q]] = __dadd_rn(v[en[t][q]], k[q]);
+      // F_p += area/3 * (f_i+f_j+f_k)/3   (:143-145)
+      const double fc = __ddiv_rn(__dadd_rn(__dadd_rn(fs[en[t][0]], fs[en[t][1]]), fs[en[t][2]]), 3.0);
+      Fp = __dadd_rn(Fp, __dmul_rn(__ddiv_rn(area, 3.0), fc));
+    }
+    F[p] = Fp;
+    int k = M.rowptr[p] - base0;
+#pragma unroll
+    for (int s = 0; s < 7; ++s)
+      if (ex[s]) stage[k++] = v[s];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < base1 - base0; i += AG_T) vals[base0 + i] = stage[i];
 }
 
 __global__ void k_eliminate(const MeshDev M, const double* __restrict__ vals, const double* __restrict__ F,
@@ -222,8 +330,13 @@ extern "C" int dfe_assemble(const dfe_mesh* m, const double* kappa, int kappa_mo
     dfe::set_error("dfe_assemble: kappa_mode must be SCALAR or PER_ELEMENT");
     rc = DFE_ERR_INVALID;
   } else {
-    k_assemble<<<blocks(m->dev.n_nodes, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-        m->dev, kappa, kappa_mode == DFE_KAPPA_PER_ELEMENT, f, vals_full, F);
+    static const bool no_grid = getenv("DFE_ASSEMBLE_GENERAL") != nullptr;   // A/B switch: general kernel on structured meshes
+    if (m->topo_nx > 0 && !no_grid)
+      k_assemble_grid<<<blocks(m->dev.n_nodes, AG_T), AG_T, 0, static_cast<cudaStream_t>(stream)>>>(
+          m->dev, m->topo_nx, m->topo_ny, kappa, kappa_mode == DFE_KAPPA_PER_ELEMENT, f, vals_full, F);
+    else
+      k_assemble<<<blocks(m->dev.n_nodes, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+          m->dev, kappa, kappa_mode == DFE_KAPPA_PER_ELEMENT, f, vals_full, F);
     rc = check_launch("dfe_assemble");
   }
   leave(m, prev);

@@ -80,6 +80,8 @@ struct dfe_mesh {
   // ---- structured 2-D mesh (topology of FEMesh.rectangle(gx, gy) with every boundary node Dirichlet): quads per side,
   // 0 when the mesh is anything else.  Enables the multigrid-preconditioned solver (dfe_mg_*).
   int grid_nx = 0, grid_ny = 0;
+  // element pattern of FEMesh.rectangle(topo_nx, topo_ny) alone (any Dirichlet set): enables the structured assembly kernel
+  int topo_nx = 0, topo_ny = 0;
   // ---- 1-D chain description
   bool chain = false;
   bool bc_left = false, bc_right = false, lift_left_first = true;

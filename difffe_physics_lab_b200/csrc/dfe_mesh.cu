@@ -257,12 +257,17 @@ extern "C" int dfe_mesh_create(int dim, int64_t n_nodes, int64_t n_el, const dou
   if (dim == 2 && ne >= 2 && h_elems[0] == 0 && h_elems[1] == 1 && h_elems[2] >= 2) {
     const long long gx = h_elems[2] - 1;
     const long long gy = (n % (gx + 1) == 0) ? n / (gx + 1) - 1 : 0;
-    bool ok = gx >= 2 && gy >= 2 && static_cast<long long>(ne) == 2 * gx * gy && nd == 2 * (gx + gy);
+    bool ok = gx >= 2 && gy >= 2 && static_cast<long long>(ne) == 2 * gx * gy;
     for (long long q = 0; ok && q < gx * gy; ++q) {
       const int a = static_cast<int>((q / gx) * (gx + 1) + q % gx), b = a + 1, c = a + static_cast<int>(gx) + 2, d = c - 1;
       const int* t = h_elems.data() + 6 * q;
       ok = t[0] == a && t[1] == b && t[2] == d && t[3] == b && t[4] == c && t[5] == d;
     }
+    if (ok) {
+      m->topo_nx = static_cast<int>(gx);
+      m->topo_ny = static_cast<int>(gy);
+    }
+    ok = ok && nd == 2 * (gx + gy);
     for (long long p = 0; ok && p < n; ++p) {
       const long long r = p / (gx + 1), cc = p % (gx + 1);
       const bool boundary = r == 0 || r == gy || cc == 0 || cc == gx;
