@@ -608,7 +608,8 @@ def run_b200_2d(args, w, rank, local_rank, world, dev):
 
     def step():
         kr = kappa.detach().requires_grad_(True)
-        s = DifferentiableFESolver(mesh, kappa=kr)
+        s = DifferentiableFESolver(mesh, kappa=kr, solver2d=os.environ.get("DFE_SOLVER2D", "auto"),
+                                   mg_nu=int(os.environ.get("DFE_MG_NU", "2")))
         u = s(f)
         u.sum().backward()
         its["fwd"] = s.last_pcg[0][0]

@@ -118,6 +118,23 @@ __global__ void k_assemble(const MeshDev M, const double* __restrict__ kappa, in
 // stores of a CTA are one contiguous coalesced stream.  Same bits as k_assemble (and as the reference's dense K, F).
 constexpr int AG_T = 256;
 
+// Correctly rounded a / b from y = RN(1 / b) with two Markstein corrections (fma residuals are exact): the first makes
+// the quotient faithful (error 2^-106 before its rounding), the second then rounds it correctly (Markstein 1990; round
+// to nearest, no under/overflow — the callers guard the range and fall back to the division instruction outside it).
+// A double-precision division costs ~25 FP64 issue slots on sm_100; the rows of an element matrix share one
+// reciprocal, which takes the structured assembly kernel from FP64-bound to memory-bound.  Same bits as __ddiv_rn.
+__device__ __forceinline__ double div_markstein(double a, double b, double y) {
+  const double q0 = __dmul_rn(a, y);
+  if (a == 0.0) return q0;                       // keeps the sign of a zero numerator
+  const double q1 = fma(fma(-b, q0, a), y, q0);
+  return fma(fma(-b, q1, a), y, q1);
+}
+__device__ __forceinline__ bool mid_range(double v) { return fabs(v) > 1e-140 && fabs(v) < 1e140; }
+__device__ __forceinline__ double div3(double a) {   // a / 3.0, correctly rounded
+  constexpr double third = 0.333333333333333314829616256247;   // RN(1/3)
+  return (a == 0.0 || mid_range(a)) ? div_markstein(a, 3.0, third) : __ddiv_rn(a, 3.0);
+}
+
 __device__ __forceinline__ void tri_row(const double (&x)[3], const double (&y)[3], int loc, double kap, double (&k)[3],
                                         double& area, bool& keep) {
   const double t1 = __dmul_rn(__dsub_rn(x[1], x[0]), __dsub_rn(y[2], y[0]));
@@ -127,9 +144,13 @@ __device__ __forceinline__ void tri_row(const double (&x)[3], const double (&y)[
   const double b[3] = {__dsub_rn(y[1], y[2]), __dsub_rn(y[2], y[0]), __dsub_rn(y[0], y[1])};
   const double c[3] = {__dsub_rn(x[2], x[1]), __dsub_rn(x[0], x[2]), __dsub_rn(x[1], x[0])};
   const double den = __dmul_rn(4.0, area);
+  const bool fast = mid_range(den);
+  const double rden = fast ? __drcp_rn(den) : 0.0;
 #pragma unroll
-  for (int q = 0; q < 3; ++q)   // k_pq = kappa*(b_p b_q + c_p c_q)/(4 area)   (:139)
-    k[q] = __ddiv_rn(__dmul_rn(kap, __dadd_rn(__dmul_rn(b[loc], b[q]), __dmul_rn(c[loc], c[q]))), den);
+  for (int q = 0; q < 3; ++q) {   // k_pq = kappa*(b_p b_q + c_p c_q)/(4 area)   (:139)
+    const double num = __dmul_rn(kap, __dadd_rn(__dmul_rn(b[loc], b[q]), __dmul_rn(c[loc], c[q])));
+    k[q] = (fast && (num == 0.0 || mid_range(num))) ? div_markstein(num, den, rden) : __ddiv_rn(num, den);
+  }
 }
 
 __global__ void __launch_bounds__(AG_T) k_assemble_grid(const MeshDev M, int gx, int gy, const double* __restrict__ kappa,
@@ -181,8 +202,8 @@ __global__ void __launch_bounds__(AG_T) k_assemble_grid(const MeshDev M, int gx,
 #pragma unroll
       for (int q = 0; q < 3; ++q) v[en[t][q]] = __dadd_rn(v[en[t][q]], k[q]);
       // F_p += area/3 * (f_i+f_j+f_k)/3   (:143-145)
-      const double fc = __ddiv_rn(__dadd_rn(__dadd_rn(fs[en[t][0]], fs[en[t][1]]), fs[en[t][2]]), 3.0);
-      Fp = __dadd_rn(Fp, __dmul_rn(__ddiv_rn(area, 3.0), fc));
+      const double fc = div3(__dadd_rn(__dadd_rn(fs[en[t][0]], fs[en[t][1]]), fs[en[t][2]]));
+      Fp = __dadd_rn(Fp, __dmul_rn(div3(area), fc));
     }
     F[p] = Fp;
     int k = M.rowptr[p] - base0;

@@ -153,7 +153,7 @@ def test_config4_full_size_1024():
     float64 system (bit-exact values through the ABI), bitwise symmetry, sign and Euler identity of the compliance
     gradient, and agreement of the multigrid route with the Jacobi route."""
     import scipy.sparse as sp
-    from test_gpu_parity import abi_assemble
+    from .test_gpu_parity import abi_assemble
 
     rng = np.random.default_rng(0)
     m = FEMesh.rectangle(1024, 1024)
