@@ -17,6 +17,8 @@
 namespace {
 
 using dfe::MeshDev;
+#include "dfe_1d_common.cuh"        // mbarrier / 1-D TMA bulk copy wrappers (used by the tensor-core band solve)
+
 constexpr double AREA_EPS = 1e-15;  // solver.py:120
 constexpr int BT = 256;             // threads per CTA (few warps: the per-warp scalar work of CG — reductions, alpha,
                                     // beta — is replicated in every warp, and this kernel is bound by instruction issue)
@@ -555,6 +557,187 @@ __global__ void __launch_bounds__(128) k_band_solve(int npad, long long B, const
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The same two triangular solves as a BLOCK-banded TRSM on the FP64 tensor cores (DMMA m8n8k4).
+//
+// With 32 x 32 blocks the band of L is block-bidiagonal: L y = b reads  y_k = H_k b_k + G_k y_{k-1}  with
+// H_k = L_kk^{-1} and G_k = -H_k L_{k,k-1}, and L^T x = y reads  x_k = H_k^T y_k + G'_k x_{k+1}  with
+// G'_k = -H_k^T L_{k+1,k}^T — two 32 x 32 products per block row and right-hand side instead of 32 dependent
+// shuffle / fma steps, i.e. a contraction: the one place of this library where tensor cores apply (the scalar kernel
+// above runs at ~2 TFLOP/s because every step waits for the previous one).  k_band_blocks builds H, G, G' once per
+// factorisation (one CTA per block row) and stores them in the register layout of the DMMA B operand.
+//
+// The solve works on the transposed problem (samples x rows), Y_k^T = B_k^T H_k^T + Y_{k-1}^T G_k^T, so that a warp's
+// 16 samples are the M dimension (two 8-row tiles) and the previous block's result is the A operand of the next
+// product.  The accumulator layout of m8n8k4 (thread t holds row t/4, columns 2(t%4), 2(t%4)+1 of an 8 x 8 tile) differs
+// from the A layout (row t/4, column t%4) — but a contraction may enumerate its k index in any order as long as both
+// operands agree: k-step (tile nt', half j) is DEFINED to cover the columns 8nt' + 2(t%4) + j, which are exactly the
+// accumulator registers the thread already holds.  The B fragments are stored with the matching permutation, and the
+// result of one block row feeds the next one without a single shuffle or shared-memory round trip.
+constexpr int FRAGD = 2048;   // doubles per block row and direction: H fragments (1024), then G fragments (1024)
+constexpr int MMA_W = 8;      // warps per CTA of the solve kernel
+constexpr int MMA_S = 16;     // samples per warp (two m8 tiles)
+
+__global__ void __launch_bounds__(256) k_band_blocks(int npad, const double* __restrict__ invd, const double* __restrict__ Lr,
+                                                     double* __restrict__ Ff, double* __restrict__ Bf) {
+  __shared__ double D[32][33], S[32][33], U[32][33], H[32][33], G2[32][33];
+  double (*G)[33] = D;   // L_kk is dead once H exists: G takes its place
+  const int k = blockIdx.x, nb = npad >> 5, tid = threadIdx.x;
+  for (int q = tid; q < 1024; q += 256) {
+    const int a = q >> 5, b = q & 31;
+    const size_t i = static_cast<size_t>(32 * k + a);
+    // Lr[i * 32 + d - 1] = L[i][i - d], d = 1..32
+    D[a][b] = b < a ? Lr[i * BW + (a - b) - 1] : (a == b ? 1.0 / invd[i] : 0.0);
+    S[a][b] = (k > 0 && a <= b) ? Lr[i * BW + (32 + a - b) - 1] : 0.0;                      // L[32k+a][32(k-1)+b]
+    U[a][b] = (k + 1 < nb && a <= b) ? Lr[(i + 32) * BW + (32 + a - b) - 1] : 0.0;           // L[32(k+1)+a][32k+b]
+    H[a][b] = 0.0;
+  }
+  __syncthreads();
+  if (tid < 32) {   // column tid of H = L_kk^{-1} by forward substitution (same pivots 1 / L_ii as the scalar solve)
+    const int c = tid;
+    double h[32];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) h[r] = 0.0;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+      if (r == c) h[r] = invd[32 * k + r];
+      else if (r > c) {
+        double sum = 0.0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j >= c && j < r) sum = fma(D[r][j], h[j], sum);
+        h[r] = -sum * invd[32 * k + r];
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 32; ++r) H[r][c] = h[r];
+  }
+  __syncthreads();
+  for (int q = tid; q < 1024; q += 256) {
+    const int r = q >> 5, c = q & 31;
+    double g = 0.0, g2 = 0.0;
+#pragma unroll 8
+    for (int a = 0; a < 32; ++a) {
+      g = fma(H[r][a], S[a][c], g);
+      g2 = fma(H[a][r], U[c][a], g2);
+    }
+    G[r][c] = -g;
+    G2[r][c] = -g2;
+  }
+  __syncthreads();
+  double* ff = Ff + static_cast<size_t>(k) * FRAGD;
+  double* bf = Bf + static_cast<size_t>(k) * FRAGD;
+  for (int q = tid; q < 1024; q += 256) {
+    const int f = q >> 5, t = q & 31;
+    const int nt = f & 3, j = (f >> 2) & 1, ntp = f >> 3;
+    const int cc = 8 * ntp + 2 * (t & 3) + j, rr = 8 * nt + (t >> 2);
+    ff[q] = H[rr][cc];            // forward:  out[s][r] += in[s][c] H[r][c]
+    ff[1024 + q] = G[rr][cc];
+    bf[q] = H[cc][rr];            // backward: out[s][r] += in[s][c] H[c][r]
+    bf[1024 + q] = G2[rr][cc];
+  }
+}
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(32 * MMA_W, 2) k_band_solve_mma(int npad, long long B, const double* __restrict__ Ff,
+                                                                  const double* __restrict__ Bf, double* __restrict__ X) {
+  __shared__ __align__(16) double stg[2][FRAGD];
+  __shared__ uint64_t bar[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const int nb = npad >> 5, nsteps = 2 * nb;
+  const long long s0 = (blockIdx.x * static_cast<long long>(MMA_W) + warp) * MMA_S;
+  double* row[2];
+  bool valid[2];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    const long long sidx = s0 + 8 * mt + g;
+    valid[mt] = sidx < B;
+    row[mt] = X + (valid[mt] ? sidx : B - 1) * npad + 2 * q;
+  }
+  auto frag_src = [&](int step) { return step < nb ? Ff + static_cast<size_t>(step) * FRAGD : Bf + static_cast<size_t>(nsteps - 1 - step) * FRAGD; };
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_arrive_expect_tx(&bar[0], FRAGD * 8u);
+    bulk_g2s(stg[0], frag_src(0), FRAGD * 8u, &bar[0]);
+  }
+  double R[2][4][2], P[2][4][2], acc[2][4][2];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const double2 v = *reinterpret_cast<const double2*>(row[mt] + 8 * nt);   // block 0
+      R[mt][nt][0] = v.x;
+      R[mt][nt][1] = v.y;
+      P[mt][nt][0] = P[mt][nt][1] = 0.0;
+    }
+  for (int step = 0; step < nsteps; ++step) {
+    const int k = step < nb ? step : nsteps - 1 - step;
+    __syncthreads();   // every warp has finished step - 1: the other stage is free (and, at step 0, the barriers exist)
+    if (tid == 0 && step + 1 < nsteps) {
+      mbar_arrive_expect_tx(&bar[(step + 1) & 1], FRAGD * 8u);
+      bulk_g2s(stg[(step + 1) & 1], frag_src(step + 1), FRAGD * 8u, &bar[(step + 1) & 1]);
+    }
+    mbar_wait(&bar[step & 1], (step >> 1) & 1);
+    const double* sH = stg[step & 1];
+    const double* sG = sH + 1024;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+    // ---- H_k applied to this block's right-hand side
+#pragma unroll
+    for (int ntp = 0; ntp < 4; ++ntp)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const double b = sH[((ntp * 2 + j) * 4 + nt) * 32 + lane];
+          dmma884(acc[0][nt][0], acc[0][nt][1], R[0][ntp][j], b);
+          dmma884(acc[1][nt][0], acc[1][nt][1], R[1][ntp][j], b);
+        }
+    // ---- the right-hand side of the next step is in flight while G_k is applied to the previous block's result
+    const int knext = step + 1 < nb ? step + 1 : nsteps - 2 - step;   // block of step + 1 (== k at the turn-around)
+    if (step + 1 < nsteps && knext != k) {
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const double2 v = *reinterpret_cast<const double2*>(row[mt] + 32 * knext + 8 * nt);
+          R[mt][nt][0] = v.x;
+          R[mt][nt][1] = v.y;
+        }
+    }
+    if (step != 0 && step != nb) {   // first block of a pass: nothing above / below it
+#pragma unroll
+      for (int ntp = 0; ntp < 4; ++ntp)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            const double b = sG[((ntp * 2 + j) * 4 + nt) * 32 + lane];
+            dmma884(acc[0][nt][0], acc[0][nt][1], P[0][ntp][j], b);
+            dmma884(acc[1][nt][0], acc[1][nt][1], P[1][ntp][j], b);
+          }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        P[mt][nt][0] = acc[mt][nt][0];
+        P[mt][nt][1] = acc[mt][nt][1];
+        if (knext == k) { R[mt][nt][0] = acc[mt][nt][0]; R[mt][nt][1] = acc[mt][nt][1]; }   // turn-around: y_{nb-1} is the next rhs
+        if (valid[mt]) *reinterpret_cast<double2*>(row[mt] + 32 * k + 8 * nt) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+      }
+  }
+}
+
 // forward: u = 0; u[d] = g; u[free] = x   (solver.py:177-181)
 __global__ void k_band_scatter(const MeshDev M, long long B, int npad, const double* __restrict__ X, double* __restrict__ u,
                                long long ldu) {
@@ -772,7 +955,7 @@ extern "C" int dfe_band_supported(const dfe_mesh* m) { return band_fits(m) ? 1 :
 extern "C" size_t dfe_band_factor_bytes(const dfe_mesh* m) {
   if (!m) return 0;
   const size_t np = static_cast<size_t>(band_npad(m));
-  return (np + 2 * np * BW + 8 * static_cast<size_t>(m->dev.n_el) + (np + 40) * (BW + 1)) * sizeof(double) + 256;
+  return (np + 2 * np * BW + 8 * static_cast<size_t>(m->dev.n_el) + (np + 40) * (BW + 1) + 2 * (np / 32) * FRAGD) * sizeof(double) + 512;
 }
 extern "C" size_t dfe_band_workspace_bytes(const dfe_mesh* m, int64_t B) {
   if (!m || B < 1) return 0;
@@ -781,7 +964,7 @@ extern "C" size_t dfe_band_workspace_bytes(const dfe_mesh* m, int64_t B) {
 
 namespace {
 struct BandPtrs {
-  double *invd, *Lc, *Lr, *geom, *Ab;
+  double *invd, *Lc, *Lr, *geom, *Ab, *Ff, *Bf;
   int* status;
 };
 BandPtrs band_ptrs(const dfe_mesh* m, void* factor) {
@@ -792,7 +975,10 @@ BandPtrs band_ptrs(const dfe_mesh* m, void* factor) {
   p.Lr = p.Lc + np * BW;
   p.geom = p.Lr + np * BW;
   p.Ab = p.geom + 8 * static_cast<size_t>(m->dev.n_el);
-  p.status = reinterpret_cast<int*>(p.Ab + (np + 40) * (BW + 1));
+  p.Ff = p.Ab + (np + 40) * (BW + 1);
+  p.Ff += (16 - (reinterpret_cast<uintptr_t>(p.Ff) & 15)) / 8 % 2;   // 16-byte alignment for the bulk copies
+  p.Bf = p.Ff + (np / 32) * FRAGD;
+  p.status = reinterpret_cast<int*>(p.Bf + (np / 32) * FRAGD);
   return p;
 }
 int band_enter(const dfe_mesh* m, const char* who, int* prev) {
@@ -813,6 +999,14 @@ int band_enter(const dfe_mesh* m, const char* who, int* prev) {
   return DFE_OK;
 }
 inline unsigned nblk(long long n, int t) { return static_cast<unsigned>((n + t - 1) / t > 0 ? (n + t - 1) / t : 1); }
+
+// L y = b, L^T x = y for the whole batch, in place on X: block TRSM on the FP64 tensor cores (default), or the scalar
+// warp-shuffle kernel (DFE_BAND_SCALAR=1: the bit-reference of the tensor-core path and an A/B switch)
+void band_solve(int np, long long B, const BandPtrs& p, double* X, cudaStream_t st) {
+  static const bool scalar = getenv("DFE_BAND_SCALAR") != nullptr;
+  if (scalar) k_band_solve<<<nblk((B + BS - 1) / BS, 4), 128, 0, st>>>(np, B, p.invd, p.Lc, p.Lr, X);
+  else k_band_solve_mma<<<nblk(B, MMA_W * MMA_S), 32 * MMA_W, 0, st>>>(np, B, p.Ff, p.Bf, X);
+}
 }  // namespace
 
 // K_free = L L^T from the assembled matrix (dfe_assemble); `factor` holds dfe_band_factor_bytes(m) bytes.  The status
@@ -834,6 +1028,7 @@ extern "C" int dfe_band_factor(const dfe_mesh* m, const double* vals_full, void*
     if (e == cudaSuccess) e = cudaMemsetAsync(p.Ab, 0, (np + 40) * (BW + 1) * sizeof(double), st);
     k_band_gather<<<nblk(m->dev.n_free, 128), 128, 0, st>>>(m->dev, vals_full, p.Ab);
     k_band_factor<<<1, 256, 0, st>>>(m->dev.n_free, band_npad(m), p.Ab, p.invd, p.Lc, p.Lr, p.status);
+    k_band_blocks<<<static_cast<unsigned>(np / 32), 256, 0, st>>>(band_npad(m), p.invd, p.Lr, p.Ff, p.Bf);
     k_band_geom<<<nblk(m->dev.n_el, 128), 128, 0, st>>>(m->dev, p.geom);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e == cudaSuccess && status_dev) e = cudaMemcpyAsync(status_dev, p.status, sizeof(int), cudaMemcpyDeviceToDevice, st);
@@ -867,7 +1062,7 @@ extern "C" int dfe_band_fwd(const dfe_mesh* m, int64_t B, const double* f, int64
     long long rgrid = 8LL * m->sm_count;
     if (rgrid > B) rgrid = B;
     k_band_rhs_fwd<<<static_cast<unsigned>(rgrid), BT, rsm, st>>>(m->dev, B, np, f, ldf, vals_full, p.geom, X);
-    k_band_solve<<<nblk((B + BS - 1) / BS, 4), 128, 0, st>>>(np, B, p.invd, p.Lc, p.Lr, X);
+    band_solve(np, B, p, X, st);
     k_band_scatter<<<nblk(B * (m->dev.n_free + m->dev.n_dir), 256), 256, 0, st>>>(m->dev, B, np, X, u, ldu);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -900,7 +1095,7 @@ extern "C" int dfe_band_bwd(const dfe_mesh* m, int64_t B, const double* gbar, in
     const BandPtrs p = band_ptrs(m, const_cast<void*>(factor));
     double* X = static_cast<double*>(ws);
     k_band_rhs_bwd<<<nblk(B * np, 256), 256, 0, st>>>(m->dev, B, np, gbar, ldg, X);
-    k_band_solve<<<nblk((B + BS - 1) / BS, 4), 128, 0, st>>>(np, B, p.invd, p.Lc, p.Lr, X);
+    band_solve(np, B, p, X, st);
     const size_t gsm = (2 * static_cast<size_t>(m->dev.n_nodes) + m->dev.n_el + 2 * BNW) * sizeof(double);
     if (gsm > 200 * 1024) {
       dfe::set_error("dfe_band_bwd: mesh too large for the gradient kernel (%zu bytes of shared memory)", gsm);

@@ -153,7 +153,7 @@ __device__ __forceinline__ void tri_row(const double (&x)[3], const double (&y)[
   }
 }
 
-__global__ void __launch_bounds__(AG_T) k_assemble_grid(const MeshDev M, int gx, int gy, const double* __restrict__ kappa,
+__global__ void __launch_bounds__(AG_T, 3) k_assemble_grid(const MeshDev M, int gx, int gy, const double* __restrict__ kappa,
                                                         int per_elem, const double* __restrict__ f,
                                                         double* __restrict__ vals, double* __restrict__ F) {
   __shared__ double stage[7 * AG_T];
@@ -169,17 +169,18 @@ __global__ void __launch_bounds__(AG_T) k_assemble_grid(const MeshDev M, int gx,
     // slots: 0 S, 1 SE, 2 W, 3 C, 4 E, 5 NW, 6 N
     const int nid[7] = {p - np1, p - gx, p - 1, p, p + 1, p + gx, p + np1};
     const bool ex[7] = {hasS, hasS && hasE, hasW, true, hasE, hasN && hasW, hasN};
-    double xs[7], ys[7], fs[7], v[7];
+    // (the kernel is bound by the latency of its dependent FP64 chains, ncu: FP64 pipe 37 %, 25 % occupancy at 96
+    // registers — f is therefore re-read per element from L1 instead of being held, and the register bound allows three CTAs per SM)
+    double xs[7], ys[7], v[7];
     const double2* xy = reinterpret_cast<const double2*>(M.nodes);
 #pragma unroll
     for (int s = 0; s < 7; ++s) {
       v[s] = 0.0;
-      xs[s] = ys[s] = fs[s] = 0.0;
+      xs[s] = ys[s] = 0.0;
       if (ex[s]) {
         const double2 c2 = xy[nid[s]];
         xs[s] = c2.x;
         ys[s] = c2.y;
-        fs[s] = f[nid[s]];
       }
     }
     double Fp = 0.0;
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(AG_T) k_assemble_grid(const MeshDev M, int gx,
 #pragma unroll
       for (int q = 0; q < 3; ++q) v[en[t][q]] = __dadd_rn(v[en[t][q]], k[q]);
       // F_p += area/3 * (f_i+f_j+f_k)/3   (:143-145)
-      const double fc = div3(__dadd_rn(__dadd_rn(fs[en[t][0]], fs[en[t][1]]), fs[en[t][2]]));
+      const double fc = div3(__dadd_rn(__dadd_rn(f[nid[en[t][0]]], f[nid[en[t][1]]]), f[nid[en[t][2]]]));
       Fp = __dadd_rn(Fp, __dmul_rn(div3(area), fc));
     }
     F[p] = Fp;

@@ -62,6 +62,7 @@ __device__ __forceinline__ void grid_sum2(const GridSync& gs, unsigned int& epoc
     constexpr int NSL = 5;
     double sa = 0.0, sb = 0.0;
     const long long t_start = clock64();
+    int spins = 0;
     for (int i0 = lane; i0 < G; i0 += 32 * NSL) {
       unsigned long long ua[NSL], ub[NSL];
       unsigned pending = 0;
@@ -81,7 +82,9 @@ __device__ __forceinline__ void grid_sum2(const GridSync& gs, unsigned int& epoc
           // microseconds on B200): hundreds of spinning lanes on a handful of L2 lines delay the stores they wait for
           const long long t0 = clock64();
           while (clock64() - t0 < gs.backoff) {}
-          if (t0 - t_start > 4000000000ll || grid_aborted(gs)) {   // ~2 s: a lost CTA / protocol bug must not hang the GPU
+          // ~2 s: a lost CTA / protocol bug must not hang the GPU (the abort word is looked at every 256 trips only:
+          // it is one more L2 round trip)
+          if (((++spins & 255) == 0) && (t0 - t_start > 4000000000ll || grid_aborted(gs))) {
             *reinterpret_cast<volatile int*>(gs.abort_flag) = 1;
 #pragma unroll
             for (int k = 0; k < NSL; ++k)
