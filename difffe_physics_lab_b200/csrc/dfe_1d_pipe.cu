@@ -211,7 +211,8 @@ __device__ __forceinline__ void phase_a(double* buf, const double* ub, const dou
 
 // SK (kappa shared by the batch): delta_i does not depend on the sample; it was computed once per thread and sits in
 // rh[i + 1] (the reciprocals are not needed any more), which takes 9 of the 15 flops per node out of this phase.
-template <bool BWD, int R, bool FULL, bool SK>
+// KEEP = false (no row is written by the call): z is not stored.
+template <bool BWD, int R, bool FULL, bool SK, bool KEEP>
 __device__ __forceinline__ void phase_b(double* buf, const double* ub, const double (&hs)[R + 1], const double (&rh)[R + 1],
                                         double X0, int nin, int nst, bool ownsL, double c0, double kaph, double a0,
                                         double b0, double& S1, double& W1, double& D) {
@@ -246,7 +247,7 @@ __device__ __forceinline__ void phase_b(double* buf, const double* ub, const dou
       const double uj = (FULL || j < nst) ? ub[j] : 0.0;
       D = fma(g + v1, uj, D);
     }
-    if (FULL || j < nst) buf[j] = fma(-c0, W1, x0);   // z = x0 - c*W1(thread-local), finished in phase C
+    if (KEEP && (FULL || j < nst)) buf[j] = fma(-c0, W1, x0);   // z = x0 - c*W1(thread-local), finished in phase C
     S1 += v1;
     W1 = fma(hs[j + 1], S1, W1);
   }
@@ -434,12 +435,17 @@ __device__ __forceinline__ void fold_warp(const PP& p, Ctl<W, NR>* ctl, double2*
 }
 
 // Warps 0..W-1 compute; warp W / W+1 = fold warps of sweep 0 / 1; warp W+2 = I/O warp (TMA loads and stores).
-template <bool BWD, int R, int W, int LB, int LC, bool SK, bool MF>
+// OUT = false (adjoint without dL/df): no row is written, phase C has nothing to do and a ring slot is released at the
+// end of phase B — LC fewer ring slots, i.e. room for a larger chunk per CTA.
+// PF = ring slots beyond the LB + LC + 1 a row occupies from phase A to phase C plus the one being stored / refilled:
+// 1 (default) gives a refill two iterations to land, 0 gives it one and leaves room for a larger chunk.
+template <bool BWD, int R, int W, int LB, int LC, bool SK, bool MF, bool OUT, int PF>
 __global__ void __launch_bounds__(32 * (W + 3), (W >= 8 ? 1 : 2)) k1d_pipe(const PP p) {
-  constexpr int NR = LB + LC + 3;           // ring slots of the in-place chain: prefetch, A..C, store drain
+  constexpr int LCO = OUT ? LC : 0;         // iterations a ring slot lives on after phase B
+  constexpr int NR = LB + LCO + 2 + PF;     // ring slots of the in-place chain: prefetch, A..C, store drain
   // ring slots of the u row (backward): read by phase B only, or — misfit adjoint — by phase A and phase B
   constexpr int NRU = MF ? LB + 2 : 2;
-  static_assert(W <= 16 && LB >= 1 && LC >= 1 && NRU <= 4 && (!MF || BWD), "layout");
+  static_assert(W <= 16 && LB >= 1 && LC >= 1 && NRU <= 4 && (!MF || BWD) && (OUT || BWD), "layout");
   static_assert(sizeof(Ctl<W, NR>) <= MISC_BYTES, "misc region");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Ctl<W, NR>* ctl = reinterpret_cast<Ctl<W, NR>*>(smem_raw);
@@ -456,7 +462,7 @@ __global__ void __launch_bounds__(32 * (W + 3), (W >= 8 ? 1 : 2)) k1d_pipe(const
   const int len = min(nn, n0 + p.chg) - n0;
   const int nIt = static_cast<int>((p.B - grp + p.NG - 1) / p.NG);
   const int nTot = nIt + LB + LC;
-  const bool have_out = (p.out != nullptr);
+  const bool have_out = OUT && (p.out != nullptr);
   const int slotd = p.slotd;
   // 16-byte phase of a row chunk: element j of the chunk lives at slot[mis + j]; mis depends on the sample only
   // through its parity (when the leading dimension is odd)
@@ -565,8 +571,9 @@ __global__ void __launch_bounds__(32 * (W + 3), (W >= 8 ? 1 : 2)) k1d_pipe(const
             ub = uring + us * slotd + mis1_of(jB) + tb;
             mbar_wait_b(&ctl->ufull[us], (jB / NRU) & 1, p.err, &ctl->dead);
           }
-          if (full) phase_b<BWD, R, true, SK>(buf, ub, hs, rh, X0, nin, nst, ownsL, c0, kaph, a0, b0, S1, W1, D);
-          else phase_b<BWD, R, false, SK>(buf, ub, hs, rh, X0, nin, nst, ownsL, c0, kaph, a0, b0, S1, W1, D);
+          if (full) phase_b<BWD, R, true, SK, OUT>(buf, ub, hs, rh, X0, nin, nst, ownsL, c0, kaph, a0, b0, S1, W1, D);
+          else phase_b<BWD, R, false, SK, OUT>(buf, ub, hs, rh, X0, nin, nst, ownsL, c0, kaph, a0, b0, S1, W1, D);
+          if (!OUT && MF) fence_async_smem();   // phase A wrote gbar into the slot the next TMA load overwrites
         }
         {   // the prefix of the sample phase A handled in the previous iteration is ready (cf[0] of this iteration
             // is signalled after the fold warp finished that iteration): keep it for phase B of iteration it-1+LB
@@ -586,13 +593,14 @@ __global__ void __launch_bounds__(32 * (W + 3), (W >= 8 ? 1 : 2)) k1d_pipe(const
         if (lane == 0) {
           mbar_arrive(&ctl->tot[1][par]);
           if (BWD && act) mbar_arrive(&ctl->ufree[jB % NRU]);
+          if (!OUT && act) mbar_arrive(&ctl->outr[slotB]);   // nothing is written back: the slot can be refilled
         }
       }
       // ---------------------------------------------------------------- phase C (sample it-LB-LC)
       {
         const int jC = it - LB - LC;
         mbar_wait_b(&ctl->cf[1][par], ph, p.err, &ctl->dead);
-        if (jC >= 0 && jC < nIt) {
+        if (OUT && jC >= 0 && jC < nIt) {
           int slotC = slotA - LB - LC;
           if (slotC < 0) slotC += NR;
           if (have_out) {
@@ -662,7 +670,7 @@ __global__ void __launch_bounds__(32 * (W + 3), (W >= 8 ? 1 : 2)) k1d_pipe(const
         }
       }
       // ---- store the row phase C finished in this iteration, then refill its slot
-      const int jc = it - LB - LC;
+      const int jc = it - LB - LCO;
       if (jc >= 0 && jc < nIt) {
         mbar_wait_b(&ctl->outr[slotC], roundC, p.err, &ctl->dead);
         if (have_out) {
@@ -804,11 +812,11 @@ struct Geo {
   size_t smem;
 };
 
-template <bool BWD, int R, int W, int LB, int LC, bool SK = false, bool MF = false>
+template <bool BWD, int R, int W, int LB, int LC, bool SK = false, bool MF = false, bool OUT = true, int PF = 1>
 int run_cfg(const dfe_mesh* m, PP p, cudaStream_t st, int gbound, int* G_used, unsigned* ticket) {
-  constexpr int NR = LB + LC + 3, NRU = BWD ? (MF ? LB + 2 : 2) : 0;
+  constexpr int NR = LB + (OUT ? LC : 0) + 2 + PF, NRU = BWD ? (MF ? LB + 2 : 2) : 0;
   constexpr int CAP = R * 32 * W, THREADS = 32 * (W + 3);
-  auto kern = k1d_pipe<BWD, R, W, LB, LC, SK, MF>;
+  auto kern = k1d_pipe<BWD, R, W, LB, LC, SK, MF, OUT, PF>;
   const int nn = p.nn;
   // per device / context, so set on every call (a process may drive several GPUs); it is a host-side table update
   DFE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -978,6 +986,8 @@ int pipe1d_run(const dfe_mesh* m, long long B, bool bwd, const double* in0, long
     switch (id) {
       case 1: rc = run_cfg<false, 11, 10, 2, 2>(m, p, st, gb, &G, ticket); break;
       case 4: rc = run_cfg<false, 9, 10, 3, 2>(m, p, st, gb, &G, ticket); break;
+      // (PF = 0, one ring slot less: measured slower — config 2 forward 1.44 -> 1.64 ms at the same (9, 12) geometry and
+      // 1.74 ms with the larger (11, 12) chunk it makes room for: a refill needs more than one iteration to land)
       default:
         // (the shared-kappa specialisation is used by the adjoint only: measured on config 5a it makes the forward
         // kernel slower and erratic, 3.94 -> 4.4-5.1 ms — its shorter phase B moves the fold latency onto the critical path)
@@ -985,11 +995,32 @@ int pipe1d_run(const dfe_mesh* m, long long B, bool bwd, const double* in0, long
         break;
     }
   } else if (misfit) {
-    // 9 nodes per thread: the misfit adjoint holds LB + 2 u-row slots next to the 7 ring slots, and with 11 nodes per
-    // thread the chunk that still fits the shared memory fills only 6 of the 8 compute warps (measured on config 5a:
-    // 6.0 ms per launch; the groups-per-iteration-time figure NG / (R + overhead) decides, not the bytes per CTA)
-    rc = !sk ? run_cfg<true, 9, 8, 2, 2, false, true>(m, p, st, gb, &G, ticket)
-             : run_cfg<true, 9, 8, 2, 2, true, true>(m, p, st, gb, &G, ticket);
+    // The misfit adjoint holds LB + 2 u-row slots next to the ring.  Without dL/df nothing is written back and a ring
+    // slot is released after phase B (5 ring slots): 11 nodes per thread fit.  With dL/df (7 ring slots) the chunk that
+    // still fits the shared memory at 11 nodes per thread fills only 6 of the 8 compute warps (measured on config 5a:
+    // 6.0 ms per launch vs 5.4 ms with 9; the groups-per-iteration-time figure NG / (R + overhead) decides).
+    if (!out) {
+      switch (id) {
+        case 1: rc = !sk ? run_cfg<true, 9, 10, 2, 2, false, true, false>(m, p, st, gb, &G, ticket)
+                         : run_cfg<true, 9, 10, 2, 2, true, true, false>(m, p, st, gb, &G, ticket); break;
+        case 2: rc = !sk ? run_cfg<true, 9, 8, 2, 2, false, true>(m, p, st, gb, &G, ticket)
+                         : run_cfg<true, 9, 8, 2, 2, true, true>(m, p, st, gb, &G, ticket); break;
+        default: rc = !sk ? run_cfg<true, 11, 8, 2, 2, false, true, false>(m, p, st, gb, &G, ticket)
+                          : run_cfg<true, 11, 8, 2, 2, true, true, false>(m, p, st, gb, &G, ticket); break;
+      }
+    } else {
+      rc = !sk ? run_cfg<true, 9, 8, 2, 2, false, true>(m, p, st, gb, &G, ticket)
+               : run_cfg<true, 9, 8, 2, 2, true, true>(m, p, st, gb, &G, ticket);
+    }
+  } else if (!out) {
+    switch (id) {
+      case 2: rc = !sk ? run_cfg<true, 11, 8, 2, 2>(m, p, st, gb, &G, ticket)
+                       : run_cfg<true, 11, 8, 2, 2, true>(m, p, st, gb, &G, ticket); break;
+      case 1: rc = !sk ? run_cfg<true, 11, 10, 2, 2, false, false, false>(m, p, st, gb, &G, ticket)
+                       : run_cfg<true, 11, 10, 2, 2, true, false, false>(m, p, st, gb, &G, ticket); break;
+      default: rc = !sk ? run_cfg<true, 11, 8, 2, 2, false, false, false>(m, p, st, gb, &G, ticket)
+                        : run_cfg<true, 11, 8, 2, 2, true, false, false>(m, p, st, gb, &G, ticket); break;
+    }
   } else {
     switch (id) {
       case 1: rc = run_cfg<true, 9, 11, 2, 2>(m, p, st, gb, &G, ticket); break;

@@ -149,6 +149,18 @@ def test_pipe_many_iterations_vs_oracle_and_split(n, B, bcs, klay):
         assert float((kr.grad.reshape(-1) - gks).abs().max()) <= 1e-11 * mag / B
     else:
         assert abs(float(kr.grad) - float(gks)) <= TOL1D * mag
+    # ---- adjoint without dL/df (f is data): the kernel variant that writes no row and frees its ring slots after phase B
+    kn2 = kap.clone().requires_grad_(True)
+    DifferentiableFESolver(m, kappa=kn2)(f).backward(gbar)
+    torch.cuda.synchronize()
+    assert _native.lib().dfe_mesh_fault(m._native(torch.cuda.current_device()).handle) == 0
+    if klay == "per_sample":
+        for b in rows:
+            gko, _, _ = O.adjoint_and_grads(nodes, el, bc, float(kn[b]), O.forward(nodes, el, bc, float(kn[b]), fn[b]), gn[b])
+            assert abs(float(kn2.grad[b, 0]) - gko.sum()) <= TOL1D * np.abs(gko).sum(), f"dL/dkappa (no dL/df), sample {b}"
+        assert float((kn2.grad - kr.grad).abs().max()) <= 1e-11 * mag / B
+    else:
+        assert abs(float(kn2.grad) - float(kr.grad)) <= TOL1D * mag
 
 
 @pytest.mark.parametrize("n,B,klay", [(2000, 600, "shared"), (2001, 500, "per_sample"), (16384, 300, "shared")])
@@ -199,17 +211,23 @@ def test_fused_misfit_adjoint(n, B, klay):
         if klay == "per_sample":
             assert abs(float(k1.grad[b, 0]) - gko.sum()) <= 1e-11 * np.abs(gko).sum()
         tot += ((uo - d) ** 2).sum() / nn
-    # without dL/df (the inverse-problem step): same loss and dL/dkappa bits, no gf written
+    # without dL/df (the inverse-problem step): no row is written and the kernel runs with a different chunk geometry
+    # (ring slots are released after phase B), so the sums are the same numbers in a different fixed order
     k3 = k0.clone().requires_grad_(True)
     loss3 = DifferentiableFESolver(m, kappa=k3).misfit(f, u_data)
     loss3.backward()
-    assert torch.equal(loss3.detach(), loss1.detach()) and torch.equal(k3.grad, k1.grad)
+    assert abs(float(loss3) - float(loss1)) <= 1e-13 * abs(float(loss1))
+    assert float((k3.grad - k1.grad).abs().max()) <= 1e-10 * gmag / max(1, k2.grad.numel())
+    k3b = k0.clone().requires_grad_(True)
+    loss3b = DifferentiableFESolver(m, kappa=k3b).misfit(f, u_data)
+    loss3b.backward()
+    assert torch.equal(loss3b.detach(), loss3.detach()) and torch.equal(k3b.grad, k3.grad)     # bit-reproducible
     # shared kappa: the two words land in a caller-provided buffer (the all-reduce buffer of the sharded step)
     if klay == "shared":
         out2 = torch.zeros(2, dtype=torch.float64, device=dev)
         k4 = k0.clone().requires_grad_(True)
         loss4 = DifferentiableFESolver(m, kappa=k4).misfit(f, u_data, out2=out2)
-        assert float(out2[1]) == float(loss4) == float(loss1) and float(out2[0]) == float(k1.grad)
+        assert float(out2[1]) == float(loss4) == float(loss3) and float(out2[0]) == float(k3.grad)
 
 
 def test_misfit_demo_step0(golden):
