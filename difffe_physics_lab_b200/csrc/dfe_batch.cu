@@ -12,12 +12,15 @@
 //   forward   F_b (node-centred gather in ascending element order, the arithmetic of k_assemble) -> lifting in
 //             dict order (the arithmetic of k_eliminate) -> Jacobi-PCG to the recursive tolerance -> scatter
 //   adjoint   lambda_b = K_free^{-1} gbar_b[free] -> dL/dkappa (per element, or summed per sample) and dL/df_b
+#include <cstdlib>
+
 #include "dfe_internal.h"
 
 namespace {
 
 using dfe::MeshDev;
 #include "dfe_1d_common.cuh"        // mbarrier / 1-D TMA bulk copy wrappers (used by the tensor-core band solve)
+#include "dfe_exact.cuh"            // div3: correctly rounded x / 3.0 without the division instruction
 
 constexpr double AREA_EPS = 1e-15;  // solver.py:120
 constexpr int BT = 256;             // threads per CTA (few warps: the per-warp scalar work of CG — reductions, alpha,
@@ -477,6 +480,407 @@ __global__ void __launch_bounds__(BT) k_band_rhs_fwd(const MeshDev M, long long 
     }
     __syncthreads();
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Register-resident variant of the gradient kernel (2-D meshes with n_el <= EPT * BT, n_nodes <= NPT * BT — config 5b:
+// 2048 / 1089), used when dL/dkappa is wanted PER ELEMENT (a shared per-element kappa field).  k_band_grad above fetches
+// connectivity, adjacency and 7 per-element constants from global memory for EVERY sample (launch list: 2.1 ms of a
+// 6.4 ms step, 10x its HBM floor).  Here a thread owns the same EPT elements and NPT nodes for the whole batch: their
+// indices and constants live in registers, the next sample's rows arrive by cp.async while the current one is processed,
+// and a sample costs two CTA barriers.
+
+constexpr int EPT = 8, RPT = 4, NPT = 5;
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// per-factorisation tables: liftp[t] = K[row, d_t] * g_t (the products of the lifting, solver.py:169 — sample
+// independent), geom2 = [k01 | k02 | k12 | area/9][n_el] with k_pq = (b_p b_q + c_p c_q) / (4 area), the off-diagonal
+// entries of the element matrix at kappa = 1 (zeros for a skipped element)
+__global__ void k_band_tables(const MeshDev M, const double* __restrict__ vals_full, int n_lift, double* __restrict__ liftp,
+                              double* __restrict__ geom2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_lift) liftp[i] = __dmul_rn(vals_full[M.lift_src[i]], M.lift_g[i]);
+  if (i < M.n_el && M.dim == 2) {
+    int nd[3];
+    const Elem2D E = elem2d(M, i, nd);
+    const bool skip = E.area < AREA_EPS;
+    const double den = 4.0 * E.area;
+    const size_t ne = static_cast<size_t>(M.n_el);
+    geom2[i] = skip ? 0.0 : (E.b[0] * E.b[1] + E.c[0] * E.c[1]) / den;
+    geom2[ne + i] = skip ? 0.0 : (E.b[0] * E.b[2] + E.c[0] * E.c[2]) / den;
+    geom2[2 * ne + i] = skip ? 0.0 : (E.b[1] * E.b[2] + E.c[1] * E.c[2]) / den;
+    geom2[3 * ne + i] = skip ? 0.0 : E.area / 9.0;
+  }
+}
+
+// Where element e keeps its per-sample term in shared memory: even and odd element ids in separate halves, so that the
+// rows of consecutive nodes (whose adjacent elements have ids two apart on a rectangle() mesh) hit consecutive banks.
+__device__ __forceinline__ int st_slot(int e, int half) { return (e & 1) * half + (e >> 1); }
+
+// The (at most ADJ6) adjacent elements of node `node` in ascending element order as three packed pairs of shared-memory
+// slots; missing entries point at the dummy slot `zslot`, which holds +0.0: x + (+0.0) == x bit for bit for every x that
+// an accumulation started from +0.0 can reach (it never produces -0.0), so the padded sum has the reference's bits.
+constexpr int ADJ6 = 6;
+__device__ __forceinline__ void pack_adj(const MeshDev& M, int node, int half, int zslot, unsigned (&pk)[3]) {
+  int id[ADJ6];
+#pragma unroll
+  for (int j = 0; j < ADJ6; ++j) id[j] = zslot;
+  if (node >= 0) {
+    const int a0 = M.adj_ptr[node], cnt = M.adj_ptr[node + 1] - a0;
+    for (int j = 0; j < cnt && j < ADJ6; ++j) id[j] = st_slot(M.adj_elem[a0 + j], half);
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) pk[j] = static_cast<unsigned>(id[2 * j]) | (static_cast<unsigned>(id[2 * j + 1]) << 16);
+}
+
+// adjoint gradients from lambda = X: dL/dkappa_e = sum_{p<q} k_pq (lam_p - lam_q)(u_p - u_q)  (= -lam^T K_e^0 u for a
+// symmetric element matrix with zero row sums), dL/df_q = sum_{e∋q} (area_e / 9) (lam_i + lam_j + lam_k)
+__global__ void __launch_bounds__(BT, 2) k_band_grad2(const MeshDev M, long long B, int npad, const double* __restrict__ X,
+                                                      const double* __restrict__ ufull, long long ldu,
+                                                      const double* __restrict__ geom2, double* __restrict__ gk,
+                                                      int gk_per_elem, double* __restrict__ gf, long long ldgf, int nnp) {
+  extern __shared__ double sg[];
+  double* slam0 = sg;                 // [2][nnp]
+  double* su0 = sg + 2 * nnp;         // [2][nnp]
+  double* st = sg + 4 * nnp;          // [n_el + 2] (area/9) (lam_i + lam_j + lam_k), then the 0.0 dummy
+  const int half = (M.n_el + 1) >> 1, zslot = 2 * half;
+  double* sred = st + zslot + 1;      // [2 * BNW]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t ne = static_cast<size_t>(M.n_el);
+  if (tid == 0) st[zslot] = 0.0;
+  unsigned e01[EPT], e2[EPT];
+  double k01[EPT], k02[EPT], k12[EPT], w9[EPT];
+#pragma unroll
+  for (int k = 0; k < EPT; ++k) {
+    const int e = tid + k * BT;
+    const bool ex = e < M.n_el;
+    e01[k] = ex ? (static_cast<unsigned>(M.elems[3 * e]) | (static_cast<unsigned>(M.elems[3 * e + 1]) << 16)) : 0u;
+    e2[k] = ex ? static_cast<unsigned>(M.elems[3 * e + 2]) : 0u;
+    k01[k] = ex ? geom2[e] : 0.0;
+    k02[k] = ex ? geom2[ne + e] : 0.0;
+    k12[k] = ex ? geom2[2 * ne + e] : 0.0;
+    w9[k] = ex ? geom2[3 * ne + e] : 0.0;
+  }
+  unsigned na[NPT][3];         // adjacent element slots of the thread's nodes
+  int rk[NPT];
+#pragma unroll
+  for (int k = 0; k < NPT; ++k) {
+    const int p = tid + k * BT;
+    rk[k] = -1;
+    pack_adj(M, p < M.n_nodes ? p : -1, half, zslot, na[k]);
+    if (p < M.n_nodes) {
+      rk[k] = M.free_rank[p];
+      slam0[p] = 0.0;            // lambda is zero on Dirichlet nodes, in both buffers, for every sample
+      slam0[nnp + p] = 0.0;
+    }
+  }
+  long long b = blockIdx.x;
+  if (b < B) {
+#pragma unroll
+    for (int k = 0; k < NPT; ++k) {
+      const int p = tid + k * BT;
+      if (p < M.n_nodes) {
+        su0[p] = ufull[b * ldu + p];
+        if (rk[k] >= 0) slam0[p] = X[b * npad + rk[k]];
+      }
+    }
+  }
+  __syncthreads();
+  int cur = 0;
+  for (; b < B; b += gridDim.x) {
+    const long long bn = b + gridDim.x;
+    const double* lam = slam0 + cur * nnp;
+    const double* u = su0 + cur * nnp;
+    if (bn < B) {
+      double* ln = slam0 + (cur ^ 1) * nnp;
+      double* un = su0 + (cur ^ 1) * nnp;
+      const double* ug = ufull + bn * ldu;
+      const double* xg = X + bn * npad;
+#pragma unroll
+      for (int k = 0; k < NPT; ++k) {
+        const int p = tid + k * BT;
+        if (p < M.n_nodes) {
+          cp_async8(un + p, ug + p);
+          if (rk[k] >= 0) cp_async8(ln + p, xg + rk[k]);
+        }
+      }
+    }
+    double gsum = 0.0, dummy = 0.0;
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+      const int e = tid + k * BT;
+      if (e < M.n_el) {
+        const int n0 = e01[k] & 0xffffu, n1 = e01[k] >> 16, n2 = e2[k];
+        const double l0 = lam[n0], l1 = lam[n1], l2 = lam[n2];
+        const double u0 = u[n0], u1 = u[n1], u2 = u[n2];
+        st[st_slot(e, half)] = w9[k] * ((l0 + l1) + l2);
+        const double g = fma(k12[k] * (l1 - l2), u1 - u2, fma(k02[k] * (l0 - l2), u0 - u2, k01[k] * (l0 - l1) * (u0 - u1)));
+        if (gk_per_elem) gk[b * M.n_el + e] = g;
+        else gsum += g;
+      }
+    }
+    if (!gk_per_elem) {
+      block_sum2(gsum, dummy, sred, lane, warp);   // (contains the barrier that completes st)
+      if (tid == 0) gk[b] = gsum;
+    } else {
+      __syncthreads();
+    }
+    if (gf) {
+#pragma unroll
+      for (int k = 0; k < NPT; ++k) {
+        const int p = tid + k * BT;
+        if (p < M.n_nodes) {
+          double g = 0.0;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) g += st[na[k][j] & 0xffffu] + st[na[k][j] >> 16];
+          gf[b * ldgf + p] = g;
+        }
+      }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    cur ^= 1;
+  }
+}
+
+int band_npad(const dfe_mesh* m);
+// ---------------------------------------------------------------------------------------------------------------------
+// Stencil form of the same two kernels for a SCALAR shared kappa (config 5b's own mode): no per-sample CTA barrier at all.
+//   forward   F = M_F f with (M_F)_pq = sum_{e∋p,q} area_e / 9 — the load vector of solver.py:143-145 written as a sparse
+//             matrix with the pattern of K (<= 7 entries per row on a rectangle() mesh) — minus a per-row lifting constant.
+//             (Not the reference's rounding order: u needs 1e-9, and F only enters through the solve; dfe_assemble keeps
+//             the bit-exact F.)
+//   adjoint   dL/df = M_F lambda (same matrix: it is symmetric), and, because lambda vanishes on Dirichlet nodes,
+//             dL/dkappa = -lambda^T K^0 u = -sum_p lambda_p (K^0 u)_p with K^0 the matrix at kappa = 1.
+// A thread owns the same SR rows for the whole batch with the row's weights and columns in registers; the rows of f / u /
+// lambda are read straight from global memory (each value is used by the 7 rows around it: L1), a CTA loops over samples,
+// and the only cross-thread step is a warp-shuffle sum of the dL/dkappa partials (fixed order: k_band_gksum adds the
+// per-warp partials of a sample in warp order).
+constexpr int SW = 7;          // entries per row
+constexpr int SR = 2;          // rows per thread
+constexpr int SBT_MAX = 640;   // threads per CTA (=> n_nodes <= 1280)
+
+// ELL tables, one thread per node p: row p of K^0 and of M_F on the full pattern (column-major [j][nnp]), the columns as
+// node ids and as free ranks, M_F with the Dirichlet columns zeroed (applied to lambda in free numbering)
+__global__ void k_band_ell(const MeshDev M, int nnp, double* __restrict__ ellK, double* __restrict__ ellM,
+                           double* __restrict__ ellMr, unsigned* __restrict__ ellc) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= M.n_nodes) return;
+  double wk[SW], wm[SW];
+#pragma unroll
+  for (int j = 0; j < SW; ++j) wk[j] = wm[j] = 0.0;
+  const int r0 = M.rowptr[p], cnt = M.rowptr[p + 1] - r0;
+  for (int a = M.adj_ptr[p]; a < M.adj_ptr[p + 1]; ++a) {
+    int nd[3];
+    const Elem2D E = elem2d(M, M.adj_elem[a], nd);
+    if (E.area < AREA_EPS) continue;
+    const int loc = M.adj_loc[a];
+    const double den = 4.0 * E.area, w9 = E.area / 9.0;
+    for (int q = 0; q < 3; ++q) {
+      const int j = M.adj_slot[3 * a + q] - r0;
+      const double kv = (E.b[loc] * E.b[q] + E.c[loc] * E.c[q]) / den;
+#pragma unroll
+      for (int t = 0; t < SW; ++t)
+        if (t == j) { wk[t] += kv; wm[t] += w9; }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < SW; ++j) {
+    const int c = j < cnt ? M.col[r0 + j] : p;
+    const int rk = M.free_rank[c];
+    ellK[static_cast<size_t>(j) * nnp + p] = j < cnt ? wk[j] : 0.0;
+    ellM[static_cast<size_t>(j) * nnp + p] = j < cnt ? wm[j] : 0.0;
+    ellMr[static_cast<size_t>(j) * nnp + p] = (j < cnt && rk >= 0) ? wm[j] : 0.0;
+    ellc[static_cast<size_t>(j) * nnp + p] = static_cast<unsigned>(c) | (static_cast<unsigned>(rk >= 0 ? rk : 0) << 16);
+  }
+}
+// liftc[r] = sum_t K[r, d_t] g_t (solver.py:166-169 summed once: it does not depend on the sample)
+__global__ void k_band_liftc(const MeshDev M, int npad, const double* __restrict__ liftp, double* __restrict__ liftc) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= npad) return;
+  double a = 0.0;
+  if (r < M.n_free)
+    for (int t = M.lift_ptr[r]; t < M.lift_ptr[r + 1]; ++t) a += liftp[t];
+  liftc[r] = a;
+}
+
+// The rows of the batch stream through an NST-deep ring in shared memory (cp.async, 8 bytes per element: row starts are
+// only 8-byte aligned when n_nodes is odd).  Depth matters more than anything else here: with one row in flight per CTA
+// these kernels ran at the latency of a DRAM access per sample (measured 1.05 ms for 1.07 GB); ~64 KB in flight per SM
+// are needed to cover it.
+constexpr int NST_F = 8, NST_G = 6;
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async8_u32(uint32_t dst, const double* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16_u32(uint32_t dst, const double* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gsrc) : "memory");
+}
+// Copy the n doubles at src (8-byte aligned) to shared memory so that element p lands at dst16 + 8 * (mis + p), where
+// mis = 0 / 1 is the 16-byte phase of src and dst16 is 16-byte aligned: one 8-byte head / tail, 16-byte pairs between.
+// Returns mis (the reader's row starts at element `mis` of the stage).
+__device__ __forceinline__ int row_to_smem(uint32_t dst16, const double* src, int n, int tid, int nt) {
+  const int mis = static_cast<int>((reinterpret_cast<uintptr_t>(src) >> 3) & 1);
+  const int npair = (n - mis) >> 1;
+  const double* s2 = src + mis;
+  const uint32_t d2 = dst16 + 16u * mis;
+  for (int q = tid; q < npair; q += nt) cp_async16_u32(d2 + 16u * q, s2 + 2 * q);
+  if (tid == 0 && mis) cp_async8_u32(dst16 + 8u, src);
+  if (tid == 32 && ((n - mis) & 1)) cp_async8_u32(dst16 + 8u * (mis + n - 1), src + n - 1);
+  return mis;
+}
+
+__global__ void __launch_bounds__(512) k_band_rhs_fwd3(const MeshDev M, long long B, int npad, int nnp,
+                                                       const double* __restrict__ f, long long ldf,
+                                                       const double* __restrict__ ellM, const unsigned* __restrict__ ellc,
+                                                       const double* __restrict__ liftc, double* __restrict__ X) {
+  extern __shared__ __align__(16) double sg[];   // [NST_F][nnp + 2]
+  const int tid = threadIdx.x, nt = blockDim.x;
+  double w[SR][SW], lc[SR];
+  int c[SR][SW];
+#pragma unroll
+  for (int k = 0; k < SR; ++k) {
+    const int r = tid + k * nt;
+    const int p = r < M.n_free ? M.free_nodes[r] : -1;
+    lc[k] = r < npad ? liftc[r] : 0.0;
+#pragma unroll
+    for (int j = 0; j < SW; ++j) {
+      w[k][j] = p >= 0 ? ellM[static_cast<size_t>(j) * nnp + p] : 0.0;
+      c[k][j] = p >= 0 ? static_cast<int>(ellc[static_cast<size_t>(j) * nnp + p] & 0xffffu) : 0;
+    }
+  }
+  const long long b0 = blockIdx.x, bs = gridDim.x;
+  const int pitch = nnp + 2;                          // (room for the 16-byte phase of a row)
+  const uint32_t sg32 = smem_u32(sg);
+  int st_in = 0;                                      // stage the next row goes to
+  long long b_in = b0;                                // ... and its sample
+  auto issue = [&]() {
+    if (b_in < B) row_to_smem(sg32 + 8u * (st_in * pitch), f + b_in * ldf, M.n_nodes, tid, nt);
+    cp_async_commit();
+    b_in += bs;
+    st_in = st_in + 1 == NST_F ? 0 : st_in + 1;
+  };
+  for (int i = 0; i < NST_F - 1; ++i) issue();
+  int st = 0;
+  for (long long b = b0; b < B; b += bs) {
+    cp_async_wait<NST_F - 2>();
+    __syncthreads();               // every thread's part of this row has landed, and everybody is done with the previous one
+    issue();
+    const double* fb = sg + st * pitch + ((reinterpret_cast<uintptr_t>(f + b * ldf) >> 3) & 1);
+    double* xb = X + b * npad;
+#pragma unroll
+    for (int k = 0; k < SR; ++k) {
+      const int r = tid + k * nt;
+      double v[SW];
+#pragma unroll
+      for (int j = 0; j < SW; ++j) v[j] = fb[c[k][j]];
+      double a = -lc[k];
+#pragma unroll
+      for (int j = 0; j < SW; ++j) a = fma(w[k][j], v[j], a);
+      if (r < npad) xb[r] = a;
+    }
+    st = st + 1 == NST_F ? 0 : st + 1;
+  }
+  cp_async_wait<0>();
+}
+
+__global__ void __launch_bounds__(SBT_MAX) k_band_grad3(const MeshDev M, long long B, int npad, int nnp,
+                                                        const double* __restrict__ X, const double* __restrict__ ufull,
+                                                        long long ldu, const double* __restrict__ ellK,
+                                                        const double* __restrict__ ellMr, const unsigned* __restrict__ ellc,
+                                                        double* __restrict__ gkpart, double* __restrict__ gf, long long ldgf) {
+  extern __shared__ __align__(16) double sg[];   // [NST_G][nnp + 2 + npad]: u row, lambda row (free numbering)
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  const int pitch = nnp + 2 + npad;        // u row (with room for its 16-byte phase) | lambda row
+  double wk[SR][SW], wm[SR][SW];
+  unsigned c[SR][SW];
+  int rk[SR];
+#pragma unroll
+  for (int k = 0; k < SR; ++k) {
+    const int p = tid + k * nt;
+    const bool ex = p < M.n_nodes;
+    rk[k] = ex ? M.free_rank[p] : -1;
+#pragma unroll
+    for (int j = 0; j < SW; ++j) {
+      wk[k][j] = ex ? ellK[static_cast<size_t>(j) * nnp + p] : 0.0;
+      wm[k][j] = ex ? ellMr[static_cast<size_t>(j) * nnp + p] : 0.0;
+      c[k][j] = ex ? ellc[static_cast<size_t>(j) * nnp + p] : 0u;
+    }
+  }
+  const long long b0 = blockIdx.x, bs = gridDim.x;
+  const uint32_t sg32 = smem_u32(sg);
+  int st_in = 0;
+  long long b_in = b0;
+  auto issue = [&]() {
+    if (b_in < B) {
+      const uint32_t du = sg32 + 8u * (st_in * pitch);
+      row_to_smem(du, ufull + b_in * ldu, M.n_nodes, tid, nt);
+      const double* sl = X + b_in * npad;      // 16-byte aligned rows (npad is a multiple of 32)
+      for (int q = tid; q < (npad >> 1); q += nt) cp_async16_u32(du + 8u * (nnp + 2) + 16u * q, sl + 2 * q);
+    }
+    cp_async_commit();
+    b_in += bs;
+    st_in = st_in + 1 == NST_G ? 0 : st_in + 1;
+  };
+  for (int i = 0; i < NST_G - 1; ++i) issue();
+  int st = 0;
+  for (long long b = b0; b < B; b += bs) {
+    cp_async_wait<NST_G - 2>();
+    __syncthreads();
+    issue();
+    const double* ub = sg + st * pitch + ((reinterpret_cast<uintptr_t>(ufull + b * ldu) >> 3) & 1);
+    const double* lb = sg + st * pitch + nnp + 2;
+    double part = 0.0;
+#pragma unroll
+    for (int k = 0; k < SR; ++k) {
+      const int p = tid + k * nt;
+      double uv[SW], lv[SW];
+#pragma unroll
+      for (int j = 0; j < SW; ++j) {
+        uv[j] = ub[c[k][j] & 0xffffu];
+        lv[j] = lb[c[k][j] >> 16];
+      }
+      const double lam = rk[k] >= 0 ? lb[rk[k]] : 0.0;
+      double ku = 0.0, ml = 0.0;
+#pragma unroll
+      for (int j = 0; j < SW; ++j) {
+        ku = fma(wk[k][j], uv[j], ku);
+        ml = fma(wm[k][j], lv[j], ml);
+      }
+      part = fma(lam, ku, part);
+      if (gf && p < M.n_nodes) gf[b * ldgf + p] = ml;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+    if (lane == 0) gkpart[b * nw + warp] = part;
+    st = st + 1 == NST_G ? 0 : st + 1;
+  }
+  cp_async_wait<0>();
+}
+// dL/dkappa of sample b = -(sum of its per-warp partials, in warp order)
+__global__ void k_band_gksum(long long B, int nw, const double* __restrict__ gkpart, double* __restrict__ gk) {
+  const long long b = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (b >= B) return;
+  double a = 0.0;
+  for (int w = 0; w < nw; ++w) a += gkpart[b * nw + w];
+  gk[b] = -a;
+}
+
+bool band_stencil_fits(const dfe_mesh* m) {
+  return m->dev.dim == 2 && m->info.max_row_nnz <= SW && m->dev.n_nodes <= SR * SBT_MAX && m->dev.n_nodes < 65536 &&
+         band_npad(m) <= SR * 512 && static_cast<size_t>(NST_G) * (2 * m->dev.n_nodes + 34) * sizeof(double) <= 200 * 1024;
+}
+
+bool band_reg_fits(const dfe_mesh* m) {
+  return m->dev.dim == 2 && m->dev.n_el <= EPT * BT && m->dev.n_free <= RPT * BT && m->dev.n_nodes <= NPT * BT &&
+         m->dev.n_nodes < 65536 && m->dev.n_el < 65536 && m->n_adj < (1 << 24) && m->n_lift < (1 << 24) &&
+         m->dev.n_nodes > 0 && m->n_lift <= 8192 && m->max_adj <= ADJ6;
 }
 
 // L y = b, then L^T x = y, in place on X; one warp per BS samples.
@@ -955,16 +1359,20 @@ extern "C" int dfe_band_supported(const dfe_mesh* m) { return band_fits(m) ? 1 :
 extern "C" size_t dfe_band_factor_bytes(const dfe_mesh* m) {
   if (!m) return 0;
   const size_t np = static_cast<size_t>(band_npad(m));
-  return (np + 2 * np * BW + 8 * static_cast<size_t>(m->dev.n_el) + (np + 40) * (BW + 1) + 2 * (np / 32) * FRAGD) * sizeof(double) + 512;
+  const size_t nnp = (static_cast<size_t>(m->dev.n_nodes) + 1) & ~static_cast<size_t>(1);
+  return (np + 2 * np * BW + 12 * static_cast<size_t>(m->dev.n_el) + static_cast<size_t>(m->n_lift) + (np + 40) * (BW + 1) +
+          2 * (np / 32) * FRAGD + 8 + (3 * SW + SW / 2 + 1) * nnp + np) * sizeof(double) + 512;
 }
 extern "C" size_t dfe_band_workspace_bytes(const dfe_mesh* m, int64_t B) {
   if (!m || B < 1) return 0;
-  return static_cast<size_t>(B) * band_npad(m) * sizeof(double);
+  return static_cast<size_t>(B) * (band_npad(m) + 32) * sizeof(double);   // X (B, npad) | per-warp dL/dkappa partials (B, <= 32)
 }
 
 namespace {
 struct BandPtrs {
-  double *invd, *Lc, *Lr, *geom, *Ab, *Ff, *Bf;
+  double *invd, *Lc, *Lr, *geom, *geom2, *liftp, *Ab, *Ff, *Bf, *ellK, *ellM, *ellMr, *liftc;
+  unsigned* ellc;
+  int nnp;
   int* status;
 };
 BandPtrs band_ptrs(const dfe_mesh* m, void* factor) {
@@ -974,11 +1382,19 @@ BandPtrs band_ptrs(const dfe_mesh* m, void* factor) {
   p.Lc = p.invd + np;
   p.Lr = p.Lc + np * BW;
   p.geom = p.Lr + np * BW;
-  p.Ab = p.geom + 8 * static_cast<size_t>(m->dev.n_el);
+  p.geom2 = p.geom + 8 * static_cast<size_t>(m->dev.n_el);
+  p.liftp = p.geom2 + 4 * static_cast<size_t>(m->dev.n_el);
+  p.Ab = p.liftp + m->n_lift;
   p.Ff = p.Ab + (np + 40) * (BW + 1);
   p.Ff += (16 - (reinterpret_cast<uintptr_t>(p.Ff) & 15)) / 8 % 2;   // 16-byte alignment for the bulk copies
   p.Bf = p.Ff + (np / 32) * FRAGD;
-  p.status = reinterpret_cast<int*>(p.Bf + (np / 32) * FRAGD);
+  p.nnp = (m->dev.n_nodes + 1) & ~1;
+  p.ellK = p.Bf + (np / 32) * FRAGD;
+  p.ellM = p.ellK + static_cast<size_t>(SW) * p.nnp;
+  p.ellMr = p.ellM + static_cast<size_t>(SW) * p.nnp;
+  p.liftc = p.ellMr + static_cast<size_t>(SW) * p.nnp;
+  p.ellc = reinterpret_cast<unsigned*>(p.liftc + np);
+  p.status = reinterpret_cast<int*>(p.ellc + static_cast<size_t>(SW) * p.nnp + 2);
   return p;
 }
 int band_enter(const dfe_mesh* m, const char* who, int* prev) {
@@ -1030,6 +1446,14 @@ extern "C" int dfe_band_factor(const dfe_mesh* m, const double* vals_full, void*
     k_band_factor<<<1, 256, 0, st>>>(m->dev.n_free, band_npad(m), p.Ab, p.invd, p.Lc, p.Lr, p.status);
     k_band_blocks<<<static_cast<unsigned>(np / 32), 256, 0, st>>>(band_npad(m), p.invd, p.Lr, p.Ff, p.Bf);
     k_band_geom<<<nblk(m->dev.n_el, 128), 128, 0, st>>>(m->dev, p.geom);
+    {
+      const int nt = m->dev.n_el > m->n_lift ? m->dev.n_el : m->n_lift;
+      k_band_tables<<<nblk(nt, 128), 128, 0, st>>>(m->dev, vals_full, m->n_lift, p.liftp, p.geom2);
+      if (band_stencil_fits(m)) {
+        k_band_ell<<<nblk(m->dev.n_nodes, 128), 128, 0, st>>>(m->dev, p.nnp, p.ellK, p.ellM, p.ellMr, p.ellc);
+        k_band_liftc<<<nblk(band_npad(m), 128), 128, 0, st>>>(m->dev, band_npad(m), p.liftp, p.liftc);
+      }
+    }
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e == cudaSuccess && status_dev) e = cudaMemcpyAsync(status_dev, p.status, sizeof(int), cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) {
@@ -1057,11 +1481,24 @@ extern "C" int dfe_band_fwd(const dfe_mesh* m, int64_t B, const double* f, int64
     const int np = band_npad(m);
     const BandPtrs p = band_ptrs(m, const_cast<void*>(factor));
     double* X = static_cast<double*>(ws);
-    const size_t rsm = (static_cast<size_t>(m->dev.n_nodes) + m->dev.n_el) * sizeof(double);
-    cudaFuncSetAttribute(k_band_rhs_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rsm));
-    long long rgrid = 8LL * m->sm_count;
-    if (rgrid > B) rgrid = B;
-    k_band_rhs_fwd<<<static_cast<unsigned>(rgrid), BT, rsm, st>>>(m->dev, B, np, f, ldf, vals_full, p.geom, X);
+    static const bool old_kernels = getenv("DFE_BAND_OLD") != nullptr;   // A/B switch: general per-sample kernels
+    static const bool reg_kernels = getenv("DFE_BAND_REG") != nullptr;   // A/B switch: no stencil-form kernels
+    if (band_stencil_fits(m) && !old_kernels && !reg_kernels) {
+      const int nt = ((np + SR - 1) / SR + 31) & ~31;
+      const size_t sm3 = static_cast<size_t>(NST_F) * (p.nnp + 2) * sizeof(double);
+      cudaFuncSetAttribute(k_band_rhs_fwd3, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm3));
+      int occ = 1;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_band_rhs_fwd3, nt, sm3);
+      long long rgrid = static_cast<long long>(occ > 0 ? occ : 1) * m->sm_count;   // persistent: one wave
+      if (rgrid > B) rgrid = B;
+      k_band_rhs_fwd3<<<static_cast<unsigned>(rgrid), nt, sm3, st>>>(m->dev, B, np, p.nnp, f, ldf, p.ellM, p.ellc, p.liftc, X);
+    } else {
+      const size_t rsm = (static_cast<size_t>(m->dev.n_nodes) + m->dev.n_el) * sizeof(double);
+      cudaFuncSetAttribute(k_band_rhs_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rsm));
+      long long rgrid = 8LL * m->sm_count;
+      if (rgrid > B) rgrid = B;
+      k_band_rhs_fwd<<<static_cast<unsigned>(rgrid), BT, rsm, st>>>(m->dev, B, np, f, ldf, vals_full, p.geom, X);
+    }
     band_solve(np, B, p, X, st);
     k_band_scatter<<<nblk(B * (m->dev.n_free + m->dev.n_dir), 256), 256, 0, st>>>(m->dev, B, np, X, u, ldu);
     cudaError_t e = cudaGetLastError();
@@ -1097,7 +1534,29 @@ extern "C" int dfe_band_bwd(const dfe_mesh* m, int64_t B, const double* gbar, in
     k_band_rhs_bwd<<<nblk(B * np, 256), 256, 0, st>>>(m->dev, B, np, gbar, ldg, X);
     band_solve(np, B, p, X, st);
     const size_t gsm = (2 * static_cast<size_t>(m->dev.n_nodes) + m->dev.n_el + 2 * BNW) * sizeof(double);
-    if (gsm > 200 * 1024) {
+    static const bool old_kernels = getenv("DFE_BAND_OLD") != nullptr;
+    static const bool reg_kernels = getenv("DFE_BAND_REG") != nullptr;
+    if (kappa_mode == DFE_KAPPA_SCALAR && band_stencil_fits(m) && !old_kernels && !reg_kernels) {
+      const int nt = ((m->dev.n_nodes + SR - 1) / SR + 31) & ~31;
+      double* gkpart = X + static_cast<size_t>(B) * np;
+      const size_t sm3 = static_cast<size_t>(NST_G) * (p.nnp + 2 + np) * sizeof(double);
+      cudaFuncSetAttribute(k_band_grad3, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm3));
+      int occ = 1;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_band_grad3, nt, sm3);
+      long long grid = static_cast<long long>(occ > 0 ? occ : 1) * m->sm_count;
+      if (grid > B) grid = B;
+      k_band_grad3<<<static_cast<unsigned>(grid), nt, sm3, st>>>(m->dev, B, np, p.nnp, X, u, ldu, p.ellK, p.ellMr, p.ellc, gkpart,
+                                                                  gf, ldgf);
+      k_band_gksum<<<nblk(B, 256), 256, 0, st>>>(B, nt / 32, gkpart, gkappa);
+    } else if (band_reg_fits(m) && !old_kernels) {
+      const int nnp = (m->dev.n_nodes + 1) & ~1;
+      const size_t gsm2 = (4 * static_cast<size_t>(nnp) + m->dev.n_el + 4 + 2 * BNW) * sizeof(double);
+      cudaFuncSetAttribute(k_band_grad2, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(gsm2));
+      long long grid = 2LL * m->sm_count;
+      if (grid > B) grid = B;
+      k_band_grad2<<<static_cast<unsigned>(grid), BT, gsm2, st>>>(m->dev, B, np, X, u, ldu, p.geom2, gkappa,
+                                                                   kappa_mode == DFE_KAPPA_PER_ELEMENT, gf, ldgf, nnp);
+    } else if (gsm > 200 * 1024) {
       dfe::set_error("dfe_band_bwd: mesh too large for the gradient kernel (%zu bytes of shared memory)", gsm);
       rc = DFE_ERR_UNSUPPORTED;
     } else {

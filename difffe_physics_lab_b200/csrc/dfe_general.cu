@@ -10,6 +10,7 @@
 //                1/diag(K_free), CSR values of K_free;  k_fill_sell copies K_free into SELL-32.
 //   k_scatter / k_gather   solver.py:177-181 and the restriction of gbar to free rows.
 //   k_grad_elem / k_grad_f the closed-form backward of the assembly.
+#include <cstdint>
 #include <cstdlib>
 
 #include "dfe_internal.h"
@@ -118,22 +119,7 @@ __global__ void k_assemble(const MeshDev M, const double* __restrict__ kappa, in
 // stores of a CTA are one contiguous coalesced stream.  Same bits as k_assemble (and as the reference's dense K, F).
 constexpr int AG_T = 256;
 
-// Correctly rounded a / b from y = RN(1 / b) with two Markstein corrections (fma residuals are exact): the first makes
-// the quotient faithful (error 2^-106 before its rounding), the second then rounds it correctly (Markstein 1990; round
-// to nearest, no under/overflow — the callers guard the range and fall back to the division instruction outside it).
-// A double-precision division costs ~25 FP64 issue slots on sm_100; the rows of an element matrix share one
-// reciprocal, which takes the structured assembly kernel from FP64-bound to memory-bound.  Same bits as __ddiv_rn.
-__device__ __forceinline__ double div_markstein(double a, double b, double y) {
-  const double q0 = __dmul_rn(a, y);
-  if (a == 0.0) return q0;                       // keeps the sign of a zero numerator
-  const double q1 = fma(fma(-b, q0, a), y, q0);
-  return fma(fma(-b, q1, a), y, q1);
-}
-__device__ __forceinline__ bool mid_range(double v) { return fabs(v) > 1e-140 && fabs(v) < 1e140; }
-__device__ __forceinline__ double div3(double a) {   // a / 3.0, correctly rounded
-  constexpr double third = 0.333333333333333314829616256247;   // RN(1/3)
-  return (a == 0.0 || mid_range(a)) ? div_markstein(a, 3.0, third) : __ddiv_rn(a, 3.0);
-}
+#include "dfe_exact.cuh"   // div_markstein, mid_range, div3
 
 __device__ __forceinline__ void tri_row(const double (&x)[3], const double (&y)[3], int loc, double kap, double (&k)[3],
                                         double& area, bool& keep) {
@@ -214,6 +200,162 @@ __global__ void __launch_bounds__(AG_T, 3) k_assemble_grid(const MeshDev M, int 
   }
   __syncthreads();
   for (int i = threadIdx.x; i < base1 - base0; i += AG_T) vals[base0 + i] = stage[i];
+}
+
+// ---- element-parallel structured assembly (default on rectangle() patterns).
+// k_assemble_grid above computes every triangle three times (once per vertex row) and every row needs 18 divisions:
+// ncu showed it FP64-latency bound (FP64 pipe 35 %, 24 % occupancy, 86 us for the 134 MB of config 4).  Here a CTA owns a
+// tile of AQ_R x AQ_C QUADS and the (AQ_R - 1) x (AQ_C - 1) nodes whose six triangles all lie in the tile (tiles overlap
+// by one quad row / column: 18 % redundant element work instead of 200 %).  Phase 1: one thread per quad computes the two
+// element matrices ONCE — six entries each (the reference's K is bitwise symmetric: b_p b_q + c_p c_q commutes), one
+// reciprocal and Markstein-corrected quotients — plus the load term, into shared memory.  Phase 2: one thread per node
+// adds the entries of its row in ascending element order (the reference's accumulation order), stages the row, and
+// the CTA writes its CSR values as contiguous streams.  Same bits as k_assemble (tests: bit-exact vs the dense reference).
+constexpr int AQ_R = 8, AQ_C = 32, AQ_T = AQ_R * AQ_C;       // quads per tile = threads
+constexpr int AN_R = AQ_R - 1, AN_C = AQ_C - 1, AN_T = AN_R * AN_C;   // nodes per tile
+
+// is v exactly zero, or safely inside the range where the Markstein residuals neither overflow nor underflow?
+__device__ __forceinline__ bool zero_or_mid(double v) {
+  const unsigned hi = static_cast<unsigned>(__double2hiint(v)) & 0x7fffffffu;
+  const unsigned e = hi >> 20;
+  return (e - 558u) <= 930u || (hi | static_cast<unsigned>(__double2loint(v))) == 0u;   // 2^-465 .. 2^465, or +-0
+}
+// a / b from y = RN(1/b), correctly rounded (see dfe_exact.cuh); a zero numerator may lose its sign, which no
+// accumulation that starts from +0 can observe
+__device__ __forceinline__ double div_m(double a, double b, double y) {
+  const double q0 = __dmul_rn(a, y);
+  const double q1 = fma(fma(-b, q0, a), y, q0);
+  return fma(fma(-b, q1, a), y, q1);
+}
+
+// element matrix (k00 k01 k02 k11 k12 k22) and load term (area/3) * (f_i + f_j + f_k)/3 of one triangle, solver.py:119-145
+__device__ __forceinline__ void tri_full(const double (&x)[3], const double (&y)[3], double kap, const double (&fv)[3],
+                                         double (&k)[6], double& fterm) {
+  const double t1 = __dmul_rn(__dsub_rn(x[1], x[0]), __dsub_rn(y[2], y[0]));
+  const double t2 = __dmul_rn(__dsub_rn(x[2], x[0]), __dsub_rn(y[1], y[0]));
+  const double area = __dmul_rn(0.5, fabs(__dsub_rn(t1, t2)));   // :119
+  const double b[3] = {__dsub_rn(y[1], y[2]), __dsub_rn(y[2], y[0]), __dsub_rn(y[0], y[1])};
+  const double c[3] = {__dsub_rn(x[2], x[1]), __dsub_rn(x[0], x[2]), __dsub_rn(x[1], x[0])};
+  const double den = __dmul_rn(4.0, area);
+  double num[6];
+  num[0] = __dmul_rn(kap, __dadd_rn(__dmul_rn(b[0], b[0]), __dmul_rn(c[0], c[0])));   // :139
+  num[1] = __dmul_rn(kap, __dadd_rn(__dmul_rn(b[0], b[1]), __dmul_rn(c[0], c[1])));
+  num[2] = __dmul_rn(kap, __dadd_rn(__dmul_rn(b[0], b[2]), __dmul_rn(c[0], c[2])));
+  num[3] = __dmul_rn(kap, __dadd_rn(__dmul_rn(b[1], b[1]), __dmul_rn(c[1], c[1])));
+  num[4] = __dmul_rn(kap, __dadd_rn(__dmul_rn(b[1], b[2]), __dmul_rn(c[1], c[2])));
+  num[5] = __dmul_rn(kap, __dadd_rn(__dmul_rn(b[2], b[2]), __dmul_rn(c[2], c[2])));
+  const double fsum = __dadd_rn(__dadd_rn(fv[0], fv[1]), fv[2]);
+  bool ok = zero_or_mid(den) && den != 0.0 && zero_or_mid(fsum) && zero_or_mid(area);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) ok = ok && zero_or_mid(num[i]);
+  if (area < AREA_EPS) {                                          // :120-121 — contributes nothing (adds +0)
+#pragma unroll
+    for (int i = 0; i < 6; ++i) k[i] = 0.0;
+    fterm = 0.0;
+  } else if (ok) {
+    const double rden = __drcp_rn(den);
+    constexpr double third = 0.333333333333333314829616256247;   // RN(1/3)
+#pragma unroll
+    for (int i = 0; i < 6; ++i) k[i] = div_m(num[i], den, rden);
+    fterm = __dmul_rn(div_m(area, 3.0, third), div_m(fsum, 3.0, third));   // :143-145
+  } else {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) k[i] = __ddiv_rn(num[i], den);
+    fterm = __dmul_rn(__ddiv_rn(area, 3.0), __ddiv_rn(fsum, 3.0));
+  }
+}
+
+__global__ void __launch_bounds__(AQ_T, 4) k_assemble_tile(const MeshDev M, int gx, int gy, const double* __restrict__ kappa,
+                                                        int per_elem, const double* __restrict__ f,
+                                                        double* __restrict__ vals, double* __restrict__ F) {
+  __shared__ double tri[2][7][AQ_T];          // [triangle of the quad][k00 k01 k02 k11 k12 k22 fterm][quad]
+  __shared__ double stage[AN_R][AN_C * 7];    // CSR values of one node-row segment, compact
+  __shared__ int segbase[AN_R], seglen[AN_R];
+  const int tid = threadIdx.x;
+  const int np1 = gx + 1;
+  const int R0 = blockIdx.y * AN_R, C0 = blockIdx.x * AN_C;   // first node of the tile
+  // ---------------- phase 1: quad (R0 - 1 + qr, C0 - 1 + qc)
+  {
+    const int qr = tid / AQ_C, qc = tid % AQ_C;
+    const int gr = R0 - 1 + qr, gc = C0 - 1 + qc;
+    if (gr >= 0 && gr < gy && gc >= 0 && gc < gx) {
+      const int a = gr * np1 + gc;            // corners a, b = a + 1, c = a + gx + 2, d = a + gx + 1  (mesh.py:105-113)
+      const double2* xy = reinterpret_cast<const double2*>(M.nodes);
+      const double2 pa = xy[a], pb = xy[a + 1], pc = xy[a + np1 + 1], pd = xy[a + np1];
+      const double fa = f[a], fb = f[a + 1], fc = f[a + np1 + 1], fd = f[a + np1];
+      const int e0 = 2 * (gr * gx + gc);
+      double k0 = kappa[0], k1 = k0;
+      if (per_elem) {
+        const double2 kk = *reinterpret_cast<const double2*>(kappa + e0);
+        k0 = kk.x;
+        k1 = kk.y;
+      }
+      double k[6], ft;
+      {   // triangle 0 = [a, b, d]
+        const double x[3] = {pa.x, pb.x, pd.x}, y[3] = {pa.y, pb.y, pd.y}, fv[3] = {fa, fb, fd};
+        tri_full(x, y, k0, fv, k, ft);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) tri[0][i][tid] = k[i];
+        tri[0][6][tid] = ft;
+      }
+      {   // triangle 1 = [b, c, d]
+        const double x[3] = {pb.x, pc.x, pd.x}, y[3] = {pb.y, pc.y, pd.y}, fv[3] = {fb, fc, fd};
+        tri_full(x, y, k1, fv, k, ft);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) tri[1][i][tid] = k[i];
+        tri[1][6][tid] = ft;
+      }
+    }
+  }
+  // ---------------- phase 2: node (R0 + nr, C0 + nc)
+  const int nr = tid / AN_C, nc = tid - nr * AN_C;
+  const int r = R0 + nr, cc = C0 + nc;
+  const bool live = tid < AN_T && r <= gy && cc <= gx;
+  const int p = r * np1 + cc;
+  int rp = 0;
+  if (live) rp = M.rowptr[p];
+  if (tid < AN_T && nc == 0) {
+    const bool rowlive = r <= gy && C0 <= gx;
+    const int last = min(C0 + AN_C, np1);   // one past the last node of the segment
+    segbase[nr] = rowlive ? rp : 0;
+    seglen[nr] = rowlive ? M.rowptr[r * np1 + last] - rp : 0;
+  }
+  __syncthreads();
+  if (live) {
+    const bool hasS = r > 0, hasN = r < gy, hasW = cc > 0, hasE = cc < gx;
+    // row slots: 0 S, 1 SE, 2 W, 3 C, 4 E, 5 NW, 6 N (ascending column order of the CSR row)
+    const bool ex[7] = {hasS, hasS && hasE, hasW, true, hasE, hasN && hasW, hasN};
+    double v[7];
+#pragma unroll
+    for (int s = 0; s < 7; ++s) v[s] = 0.0;
+    double Fp = 0.0;
+    // adjacent triangles in ascending element id: (quad in the tile, triangle, slots of its three nodes, row of p)
+    const int qSW = nr * AQ_C + nc, qSE = qSW + 1, qNW = qSW + AQ_C, qNE = qNW + 1;
+    const bool eex[6] = {hasS && hasW, hasS && hasE, hasS && hasE, hasN && hasW, hasN && hasW, hasN && hasE};
+    const int eq[6] = {qSW, qSE, qSE, qNW, qNW, qNE};
+    const int et[6] = {1, 0, 1, 0, 1, 0};
+    const int en[6][3] = {{0, 3, 2}, {0, 1, 3}, {1, 4, 3}, {2, 3, 5}, {3, 6, 5}, {3, 4, 6}};
+    const int eloc[6] = {1, 2, 2, 1, 0, 0};
+    const int sym[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+#pragma unroll
+    for (int t = 0; t < 6; ++t) {
+      if (!eex[t]) continue;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) v[en[t][q]] = __dadd_rn(v[en[t][q]], tri[et[t]][sym[eloc[t]][q]][eq[t]]);
+      Fp = __dadd_rn(Fp, tri[et[t]][6][eq[t]]);
+    }
+    F[p] = Fp;
+    int k = rp - segbase[nr];
+#pragma unroll
+    for (int s = 0; s < 7; ++s)
+      if (ex[s]) stage[nr][k++] = v[s];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int sr = 0; sr < AN_R; ++sr) {
+    const int len = seglen[sr];
+    if (tid < len) vals[segbase[sr] + tid] = stage[sr][tid];
+  }
 }
 
 __global__ void k_eliminate(const MeshDev M, const double* __restrict__ vals, const double* __restrict__ F,
@@ -352,8 +494,15 @@ extern "C" int dfe_assemble(const dfe_mesh* m, const double* kappa, int kappa_mo
     dfe::set_error("dfe_assemble: kappa_mode must be SCALAR or PER_ELEMENT");
     rc = DFE_ERR_INVALID;
   } else {
-    static const bool no_grid = getenv("DFE_ASSEMBLE_GENERAL") != nullptr;   // A/B switch: general kernel on structured meshes
-    if (m->topo_nx > 0 && !no_grid)
+    // A/B switches, read per call so that the tests can compare the three kernels bit for bit in one process
+    const bool no_grid = getenv("DFE_ASSEMBLE_GENERAL") != nullptr;   // general kernel on structured meshes
+    const bool row_grid = getenv("DFE_ASSEMBLE_ROWS") != nullptr;     // row-owner structured kernel
+    const bool k16 = (reinterpret_cast<uintptr_t>(kappa) & 15) == 0;         // per-element kappa is read as pairs
+    if (m->topo_nx > 0 && !no_grid && !row_grid && k16) {
+      cudaFuncSetAttribute(k_assemble_tile, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      k_assemble_tile<<<dim3(blocks(m->topo_nx + 1, AN_C), blocks(m->topo_ny + 1, AN_R)), AQ_T, 0, static_cast<cudaStream_t>(stream)>>>(
+          m->dev, m->topo_nx, m->topo_ny, kappa, kappa_mode == DFE_KAPPA_PER_ELEMENT, f, vals_full, F);
+    } else if (m->topo_nx > 0 && !no_grid)
       k_assemble_grid<<<blocks(m->dev.n_nodes, AG_T), AG_T, 0, static_cast<cudaStream_t>(stream)>>>(
           m->dev, m->topo_nx, m->topo_ny, kappa, kappa_mode == DFE_KAPPA_PER_ELEMENT, f, vals_full, F);
     else

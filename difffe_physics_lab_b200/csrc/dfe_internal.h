@@ -99,6 +99,9 @@ struct dfe_mesh {
   int* d_fault_dev = nullptr;
   // ---- device
   dfe::MeshDev dev{};
+  int n_lift = 0;             // entries of the lifting lists (lift_src / lift_g)
+  int n_adj = 0;              // entries of the node -> element adjacency (adj_elem)
+  int max_adj = 0;            // most elements around one node
   std::vector<void*> allocs;  // every cudaMalloc owned by the handle
   int sm_count = 0;
 };

@@ -325,6 +325,9 @@ extern "C" int dfe_mesh_create(int dim, int64_t n_nodes, int64_t n_el, const dou
     UP(lift_ptr, lift_ptr); UP(lift_src, lift_src); UP(lift_g, lift_g); UP(slice_ptr, slice_ptr);
     UP(sell_col, sell_col); UP(sell_src, sell_src);
 #undef UP
+    m->n_lift = static_cast<int>(lift_src.size());
+    m->n_adj = nadj;
+    for (int q = 0; q < n; ++q) m->max_adj = std::max(m->max_adj, adj_ptr[q + 1] - adj_ptr[q]);
     if (rc == DFE_OK && chain) {
       // half element lengths and their reciprocals for the fused 1-D kernels (IEEE double on the host)
       std::vector<double> hsv(ne), rhv(ne);

@@ -343,6 +343,34 @@ def test_assembly_bit_exact_large_per_element_kappa():
     assert np.array_equal(np.sort(vals), np.sort(ovals))
 
 
+@pytest.mark.parametrize("nx,ny,scalar", [(300, 70, False), (31, 7, True), (32, 8, False), (1, 1, False), (95, 130, True)])
+def test_assembly_three_kernels_same_bits(monkeypatch, nx, ny, scalar):
+    """The element-parallel tile kernel (default on rectangle() patterns), the row-owner structured kernel and the general
+    adjacency-list kernel produce the same K and F bit for bit — tile edges, mesh edges, partial Dirichlet sets, and (on the
+    small cases) the oracle's reference-order accumulation."""
+    rng = np.random.default_rng(nx * 1000 + ny)
+    m = FEMesh.rectangle(nx, ny, x_range=(-0.7, 1.9), y_range=(0.1, 0.9), bc_value=0.25)
+    if nx > 4:                                   # a partial Dirichlet set keeps the structured pattern
+        for k in list(m.dirichlet_nodes)[::3]:
+            del m.dirichlet_nodes[k]
+    kap = 1.7 if scalar else np.exp(rng.uniform(np.log(1e-3), 0.0, m.n_elements))
+    f = rng.uniform(-1, 1, m.n_nodes)
+    out = {}
+    for name, env in (("tile", None), ("rows", "DFE_ASSEMBLE_ROWS"), ("general", "DFE_ASSEMBLE_GENERAL")):
+        monkeypatch.delenv("DFE_ASSEMBLE_ROWS", raising=False)
+        monkeypatch.delenv("DFE_ASSEMBLE_GENERAL", raising=False)
+        if env:
+            monkeypatch.setenv(env, "1")
+        _, vals, F, vf, Ff, dinv = abi_assemble(m, kap, f)
+        out[name] = (vals, F, vf, Ff, dinv)
+    for name in ("rows", "general"):
+        for a, b in zip(out["tile"], out[name]):
+            assert np.array_equal(a, b), name
+    if m.n_nodes < 30000:
+        orp, ocol, ovals, oF = O.assemble_csr(m.nodes.numpy(), m.elements.numpy(), kap, f)
+        assert np.array_equal(out["tile"][0], ovals) and np.array_equal(out["tile"][1], oF)
+
+
 @pytest.mark.parametrize("name", CASES_2D)
 def test_2d_golden(golden, name):
     c = golden.case(name)
