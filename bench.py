@@ -42,6 +42,9 @@ WORKLOADS = {
     # name: (n_elements, batch per rank, kappa layout, scaling)
     "c2": dict(n_elements=100000, batch=4096, kappa="per_sample", scaling="weak",
                desc="1D Poisson batch of 4096 random forcing/kappa samples, n_elements=100000, fwd+adjoint"),
+    "c2e": dict(n_elements=100000, batch=4096, kappa="per_sample_element", scaling="weak",
+                desc="1D Poisson batch of 4096 samples, n_elements=100000, per-sample PER-ELEMENT kappa (4096, 100000) ~ logU[0.1,10], "
+                     "fwd+adjoint with dL/df and dL/dkappa_e (SURVEY 8(d) C2 variant, 64 B/node accounting)"),
     "c5a": dict(n_elements=16384, batch=65536, kappa="shared", scaling="strong",
                 desc="kappa inverse-problem sweep: 65536 1D solves (n_elements=16384), shared kappa, NCCL grad allreduce"),
     # 2-D configs (one mesh per GPU; N > 1 = replicas only).  Not the default bench line.
@@ -129,6 +132,68 @@ def cpu_port_rate(n_elements, seconds_target, steps=1, warmup=0, seed=0):
     sample = (f"{S * reps} fwd+adjoint solves per step ({S} distinct samples x {reps} passes) of the n_elements="
               f"{n_elements} workload, OpenMP over samples, {cores} threads")
     return rate, cores, sample, per_step * 1e3
+
+
+
+def cpu_rate_2d(mesh, kappa_np, f_np, iters_step, seconds_target=10.0):
+    """CPU baseline of one 2-D fwd+adjoint step: the oracle's vectorised assembly + Dirichlet elimination (numpy, one
+    thread) and the port's Jacobi-PCG (OpenMP, all host threads).  The PCG is timed on a BOUNDED number of iterations
+    and scaled to the `iters_step` iterations (forward + adjoint) the same Jacobi-PCG needs on this system."""
+    from oracle import oracle as O
+    from oracle import port as P
+
+    cores = len(os.sched_getaffinity(0))
+    nodes, el, bc = mesh.nodes.numpy(), mesh.elements.numpy(), mesh.dirichlet_nodes
+    t0 = time.perf_counter()
+    rp, col, vals, F = O.assemble_csr(nodes, el, kappa_np, f_np)
+    _, frp, fcol, fvals, Ff = O.apply_bc(rp, col, vals, F, bc)
+    t_asm = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    P.pcg_csr(frp, fcol, fvals, Ff, tol=0.0, maxit=20, nthreads=cores)
+    t_it = (time.perf_counter() - t0) / 20
+    n_run = int(max(20, min(4 * iters_step, seconds_target / max(t_it, 1e-9))))
+    t0 = time.perf_counter()
+    P.pcg_csr(frp, fcol, fvals, Ff, tol=0.0, maxit=n_run, nthreads=cores)
+    t_it = (time.perf_counter() - t0) / n_run
+    t_step = t_asm + iters_step * t_it
+    return {"value": 1.0 / t_step, "unit": "solves/s", "cores": cores, "kind": "port",
+            "sample": f"assembly + elimination once ({t_asm:.2f} s, numpy, 1 thread) + {n_run} timed Jacobi-PCG iterations "
+                      f"({t_it * 1e3:.3f} ms each, OpenMP, {cores} threads) scaled to the {iters_step} iterations of one "
+                      f"forward + adjoint solve at tol 1e-13 (count taken from the same Jacobi-PCG on the GPU)"}
+
+
+def cpu_rate_2d_batch(mesh, kappa, S, seed=0):
+    """CPU baseline of config 5b on S samples: shared matrix assembled once (oracle, numpy), per-sample load vectors
+    (vectorised numpy), then forward and adjoint Jacobi-PCG solves of every sample (port, OpenMP over the samples)."""
+    from oracle import oracle as O
+    from oracle import port as P
+
+    cores = len(os.sched_getaffinity(0))
+    nodes, el, bc = mesh.nodes.numpy(), mesh.elements.numpy(), mesh.dirichlet_nodes
+    nn = len(nodes)
+    rng = np.random.default_rng(seed)
+    f = rng.uniform(0.5, 1.5, (S, nn))
+    gbar = rng.standard_normal((S, nn))
+    rp, col, vals, F0 = O.assemble_csr(nodes, el, kappa, f[0])
+    free, frp, fcol, fvals, Ff0 = O.apply_bc(rp, col, vals, F0, bc)
+    lift = F0[free] - Ff0                                   # sample independent
+    x, y = nodes[:, 0], nodes[:, 1]
+    i, j, k = el[:, 0], el[:, 1], el[:, 2]
+    area = 0.5 * np.abs((x[j] - x[i]) * (y[k] - y[i]) - (x[k] - x[i]) * (y[j] - y[i]))
+    t0 = time.perf_counter()
+    term = (area / 3.0) * ((f[:, i] + f[:, j] + f[:, k]) / 3.0)            # (S, n_el), solver.py:143-145
+    F = np.zeros((S, nn))
+    for loc in (i, j, k):
+        for b in range(S):
+            F[b] += np.bincount(loc, weights=term[b], minlength=nn)
+    rhs = F[:, free] - lift
+    u_free, _ = P.pcg_csr_batch(frp, fcol, fvals, rhs, nthreads=cores)
+    lam, _ = P.pcg_csr_batch(frp, fcol, fvals, gbar[:, free], nthreads=cores)
+    t = time.perf_counter() - t0
+    return {"value": S / t, "unit": "solves/s", "cores": cores, "kind": "port",
+            "sample": f"{S} samples of the 65536: load vectors (numpy) + forward and adjoint Jacobi-PCG per sample "
+                      f"(oracle/fem_port.c, OpenMP over samples, {cores} threads, tol 1e-13); matrix assembled once; "
+                      f"gradient evaluation not included"}
 
 
 def run_reference(args):
@@ -238,7 +303,7 @@ def bind_to_gpu_numa_node(local_rank):
 
 
 # ------------------------------------------------------------------------------- GPU arm
-def parity_block(mesh, rows, f, kappa, gbar, u, gf, gk, shared_kappa):
+def parity_block(mesh, rows, f, kappa, gbar, u, gf, gk, shared_kappa, per_elem=False):
     """Max relative error of sampled rows of the TIMED output against the exact oracle (oracle/oracle.py: the same
     float64 system solved in 50-digit arithmetic).  Checker use of oracle/ — the rows were produced by the kernels."""
     from oracle import oracle as O
@@ -246,16 +311,21 @@ def parity_block(mesh, rows, f, kappa, gbar, u, gf, gk, shared_kappa):
     nodes, el, bc = mesh.nodes.numpy(), mesh.elements.numpy(), mesh.dirichlet_nodes
     worst = {"u": 0.0, "gf": 0.0, "gkappa": 0.0}
     for b in rows:
-        kb = float(kappa.reshape(-1)[0 if shared_kappa else b])
+        kb = kappa[b].cpu().numpy() if per_elem else float(kappa.reshape(-1)[0 if shared_kappa else b])
         uo = O.forward(nodes, el, bc, kb, f[b].cpu().numpy())
         gko, gfo, _ = O.adjoint_and_grads(nodes, el, bc, kb, uo, gbar[b].cpu().numpy())
         worst["u"] = max(worst["u"], float(np.abs(u[b].cpu().numpy() - uo).max() / np.abs(uo).max()))
         if gf is not None:
             worst["gf"] = max(worst["gf"], float(np.abs(gf[b].cpu().numpy() - gfo).max() / np.abs(gfo).max()))
-        if not shared_kappa:
+        if per_elem:      # dL/dkappa_e relative to sum_e |dL/dkappa_e| (L1), the entry-wise maximum beside it
+            gkb = gk[b].cpu().numpy()
+            worst["gkappa"] = max(worst["gkappa"], float(np.abs(gkb - gko).sum() / np.abs(gko).sum()))
+            worst["gkappa_entry"] = max(worst.get("gkappa_entry", 0.0), float(np.abs(gkb - gko).max() / np.abs(gko).max()))
+        elif not shared_kappa:
             worst["gkappa"] = max(worst["gkappa"], float(abs(float(gk.reshape(-1)[b]) - gko.sum()) / np.abs(gko).sum()))
-    return {"rows": [int(r) for r in rows], "max_rel": max(worst.values()), "max_rel_u": worst["u"], "max_rel_gf": worst["gf"],
-            "max_rel_gkappa": worst["gkappa"] if not shared_kappa else None, "tol": 1e-12,
+    return {"rows": [int(r) for r in rows], "max_rel": max(worst["u"], worst["gf"], worst["gkappa"]), "max_rel_u": worst["u"],
+            "max_rel_gf": worst["gf"], "max_rel_gkappa": worst["gkappa"] if not shared_kappa else None,
+            "max_rel_gkappa_entrywise": worst.get("gkappa_entry"), "tol": 1e-12,
             "oracle": "oracle/oracle.py exact (50-digit Thomas on the bit-exact float64 system)",
             "note": "rows of the last timed step, chosen from the first, a middle and the last pipeline iteration"}
 
@@ -370,7 +440,12 @@ def run_b200(args):
     mesh = FEMesh.line(n_el)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     f = torch.rand((B, nn), dtype=torch.float64, device=dev, generator=gen)
-    kappa = torch.exp(torch.empty((B, 1), dtype=torch.float64, device=dev).uniform_(float(np.log(0.5)), float(np.log(2.0)), generator=gen))
+    per_elem = w["kappa"] == "per_sample_element"
+    if per_elem:
+        kappa = torch.exp(torch.empty((B, n_el), dtype=torch.float64, device=dev).uniform_(float(np.log(0.1)), float(np.log(10.0)), generator=gen))
+        args.no_e2e = args.no_sweep = args.no_cpu = True   # the variant line carries the device-resident numbers only
+    else:
+        kappa = torch.exp(torch.empty((B, 1), dtype=torch.float64, device=dev).uniform_(float(np.log(0.5)), float(np.log(2.0)), generator=gen))
     gbar = torch.randn((B, nn), dtype=torch.float64, device=dev, generator=gen)
     keep = {}
 
@@ -417,14 +492,15 @@ def run_b200(args):
     if rank == 0 and not args.no_parity:
         try:
             rows = sorted({0, B // 2 + 1, B - 1})
-            parity = parity_block(mesh, rows, f.detach(), kappa, gbar, keep["u"].detach(), f.grad, keep["gk"], False)
+            parity = parity_block(mesh, rows, f.detach(), kappa, gbar, keep["u"].detach(), f.grad, keep["gk"], False, per_elem)
         except Exception as exc:
             parity = {"max_rel": None, "error": f"{type(exc).__name__}: {exc}"}
 
     # ---------------- roofline of the dominant kernel (algorithmic bytes, SURVEY §8d: fwd 16N, adjoint 24N with gf)
     peak, peak_src = measured_peak()
     kern = {}
-    for name, bytes_per_node in (("solve1d_fwd", 16), ("solve1d_bwd", 24)):
+    # per-element kappa adds the kappa row to both directions and the dL/dkappa_e row to the adjoint (24 / 40 B per node)
+    for name, bytes_per_node in (("solve1d_fwd", 24 if per_elem else 16), ("solve1d_bwd", 40 if per_elem else 24)):
         if name in ksum:
             calls, ms = ksum[name]
             alg = bytes_per_node * nn * B
@@ -435,6 +511,9 @@ def run_b200(args):
     if dom:
         knames = {"solve1d_fwd": "dfe_solve1d_fwd = k1d_pipe<fwd> (+ k1d_pipe_ck, k1d_pipe_poison, exchange-buffer memset)",
                   "solve1d_bwd": "dfe_solve1d_bwd = k1d_pipe<bwd> (+ k1d_pipe_ck, k1d_pipe_gk, k1d_pipe_poison, exchange-buffer memset)"}
+        if per_elem:
+            knames = {"solve1d_fwd": "dfe_solve1d_fwd = k1d_pass1<fwd> + fold + k1d_pass2<fwd> (two-pass split kernels: per-element kappa)",
+                      "solve1d_bwd": "dfe_solve1d_bwd = k1d_pass1<bwd> + fold + k1d_pass2<bwd> (two-pass split kernels: per-element kappa)"}
         roofline = {"bound": "hbm", "kernel": knames[dom],
                     "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                     "frac": kern[dom]["achieved_gbs"] / peak,
@@ -445,7 +524,7 @@ def run_b200(args):
                     "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": kern[dom]["algorithmic_bytes"],
                     "ms_per_launch": kern[dom]["ms_per_launch"], "kernels": kern,
-                    "step_frac_of_peak": (40 * nn * B) / (ms_step * 1e-3) / 1e9 / peak}
+                    "step_frac_of_peak": ((64 if per_elem else 40) * nn * B) / (ms_step * 1e-3) / 1e9 / peak}
 
     # ---------------- end to end through the product API with HOST buffers: u = solver(f_host); u.backward(gbar)
     # The row streaming (pinned chunks on a copy stream overlapped with the kernels) is the product's, not bench code.
@@ -544,6 +623,7 @@ def run_b200(args):
             "dof_per_s": value * (n_el - 1),
             "config": {"workload": w["desc"], "n_elements": n_el, "batch_per_gpu": B, "global_batch": B * world,
                        "kappa": w["kappa"], "grads": "dL/dkappa and dL/df", "l2": "inputs (3.28 GB/array) larger than L2; no flush",
+                       "accounting_bytes_per_node": 64 if per_elem else 40,
                        "parallelism": f"batch-sharded x{world}, mesh replicated, no collective (per-sample kappa); the config-5 sweep "
                                       "with its NCCL all-reduce is timed in the same run: see `sweep`"},
             "roofline": roofline, "parity": parity, "cpu_baseline": cpu, "e2e": e2e, "e2e_full": e2e_full, "sweep": sweep,
@@ -563,6 +643,13 @@ def run_b200_sweep(args, w, rank, local_rank, world, dev):
     r = time_sweep(args, rank, world, dev, args.n_elements or w["n_elements"], args.batch or w["batch"], args.steps, args.warmup)
     clocks = sampler.stop()
     peak, peak_src = measured_peak()
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            rate, cores, sample, _ = cpu_port_rate(r["n_elements"], seconds_target=8.0)
+            cpu = {"value": rate, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample}
+        except Exception as exc:
+            cpu = {"value": None, "unit": "solves/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc}"}
     if rank == 0:
         dom = max((k for k in r["kernels"] if "achieved_gbs" in r["kernels"][k]), key=lambda k: r["kernels"][k]["ms_per_launch"])
         kd = r["kernels"][dom]
@@ -577,7 +664,10 @@ def run_b200_sweep(args, w, rank, local_rank, world, dev):
                              "frac": kd["frac"], "traffic": None, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": kd["algorithmic_bytes"], "ms_per_launch": kd["ms_per_launch"],
                              "kernels": r["kernels"], "step_frac_of_peak": r["step_frac_of_peak"]},
-                "cpu_baseline": None, "e2e": None, "gpu_launches": r["gpu_launches"], "clocks": clocks,
+                "cpu_baseline": cpu, "e2e": None,
+                "e2e_note": "the sweep's f and u_data stay resident on the GPU across optimisation steps; only kappa (8 B) and the "
+                            "reduced [dL/dkappa, loss] (16 B) would cross per step",
+                "gpu_launches": r["gpu_launches"], "clocks": clocks,
                 "loss_first_step": r["loss_first_step"], "loss_last_step": r["loss_last_step"], "kappa_after": r["kappa_after"]}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -659,6 +749,63 @@ def run_b200_2d(args, w, rank, local_rank, world, dev):
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "ms_per_launch": ms_launch,
                     "bytes_per_iteration": bytes_iter, "iterations": its, "us_per_iteration": 1e3 * ms_pcg / calls / (iters_step / 2.0),
                     "kernels": {k: {"calls": c, "ms_per_launch": m / c} for k, (c, m) in ksum.items()}}
+    if roofline is not None and solver2d == "mg":
+        tr = measured_traffic("k_mgpcg") if args.workload == "c4" and not args.n_elements else None
+        roofline["traffic"] = tr
+        roofline["traffic_source"] = ("REPLAYED from profiles/r*_traffic.json (one earlier `ncu --set full` capture of k_mgpcg on this "
+                                      "workload), not measured in this run")
+        roofline["note"] = ("achieved = SURVEY 8(d) Jacobi-PCG accounting bytes per iteration x MG-PCG iterations / time: the "
+                            "multigrid cycle does ~10x the arithmetic of a Jacobi iteration per CG step and needs 170x fewer "
+                            "steps, so this figure measures nothing useful; achieved_dram = measured DRAM bytes / time is the "
+                            "honest utilisation (the hierarchy is largely L2-resident; the kernel is bound by its grid barriers)")
+        if tr:
+            roofline["achieved_dram"] = tr / (roofline["ms_per_launch"] * 1e-3) / 1e9
+            roofline["frac_dram"] = roofline["achieved_dram"] / peak
+    # ---------------- CPU baseline (rank 0, N = 1): same Jacobi-PCG the reference-faithful route runs, on the host cores
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            kr = kappa.detach().requires_grad_(True)
+            sj = DifferentiableFESolver(mesh, kappa=kr, solver2d="jacobi")
+            sj(f).sum().backward()
+            itj = int(sj.last_pcg[0][0] + sj._opts["last_pcg_adjoint"][0][0])
+            knp = kappa.detach().cpu().numpy()
+            cpu = cpu_rate_2d(mesh, float(knp) if knp.ndim == 0 else knp, f.cpu().numpy(), itj)
+            cpu["jacobi_iterations_fwd_plus_adjoint"] = itj
+        except Exception as exc:
+            cpu = {"value": None, "unit": "solves/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc}"}
+    # ---------------- end to end through the module with HOST tensors (CPU in -> CPU out, the reference's convention)
+    e2e = None
+    if not args.no_e2e:
+        k_host = kappa.detach().cpu()
+        f_host = f.cpu().pin_memory()
+        n_e2e = max(2, min(args.steps, 5))
+
+        def step_host():
+            kr = k_host.clone().requires_grad_(True)
+            s = DifferentiableFESolver(mesh, kappa=kr, solver2d=os.environ.get("DFE_SOLVER2D", "auto"),
+                                       mg_nu=int(os.environ.get("DFE_MG_NU", "2")))
+            u = s(f_host)
+            u.sum().backward()
+            return u, kr.grad
+
+        for _ in range(2):
+            step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            uh, gh = step_host()
+        barrier()
+        wall = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([wall], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            wall = float(t[0])
+        e2e = {"value": world * n_e2e / wall, "unit": "solves/s", "ms_per_step": 1e3 * wall / n_e2e, "steps": n_e2e,
+               "h2d_bytes_per_step": int(8 * (f_host.numel() + k_host.numel() + uh.numel())),
+               "d2h_bytes_per_step": int(8 * (uh.numel() + gh.numel())),
+               "call": "u_host = DifferentiableFESolver(mesh, kappa_host)(f_host); u_host.sum().backward(): f, kappa and the upstream "
+                       "gradient cross to the device, u and dL/dkappa come back (host clock; includes the host-side set-up of the call)"}
     if rank == 0:
         line = {"metric": "fem_fwd_adjoint_solves_per_s", "value": world * args.steps / (ms_total * 1e-3), "unit": "solves/s",
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
@@ -667,7 +814,7 @@ def run_b200_2d(args, w, rank, local_rank, world, dev):
                 "config": {"workload": w["desc"], "nx": nx, "n_free": int(N), "nnz_free": int(nnz), "pcg_tol": 1e-13,
                            "l2": "config 4 working set ~0.2 GB > L2; config 3 (3 MB) is L2/latency-bound by construction",
                            "mesh_setup_s": t_setup, "parallelism": f"replicas only x{world} (a single mesh stays on one GPU)"},
-                "roofline": roofline, "cpu_baseline": None, "e2e": None, "gpu_launches": kt.launches, "clocks": clocks}
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": kt.launches, "clocks": clocks}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -736,8 +883,9 @@ def run_b200_small2d(args, w, rank, local_rank, world, dev):
     peak, peak_src = measured_peak()
     kern = {k: {"calls": c, "ms_per_launch": m / c} for k, (c, m) in ksum.items()}
     roofline = None
-    for key, kname, note in (("band_bwd", "dfe_band_bwd = k_band_rhs + k_band_solve + k_band_grad (banded Cholesky, a warp per 4 samples)",
-                              "two banded triangular solves per sample; bound by instruction issue / L2 reads of the shared factor, not by HBM"),
+    for key, kname, note in (("band_bwd", "dfe_band_bwd = k_band_rhs_bwd + k_band_solve_mma (block TRSM on the FP64 tensor cores) + k_band_grad3 + k_band_gksum",
+                              "achieved = 24 B/node accounting (read gbar, read u, write dL/df) / time; the call itself moves more: the "
+                              "right-hand sides are gathered to (B, npad), solved in place and read back by the gradient kernel"),
                              ("batch_bwd", "k_batch<adjoint> (one CTA per sample, matrix in shared memory)",
                               "shared-memory resident PCG: bound by the SpMV's shared-memory traffic, not by HBM")):
         if key in kern:
@@ -748,6 +896,44 @@ def run_b200_small2d(args, w, rank, local_rank, world, dev):
                         "algorithmic_bytes_per_launch": alg, "ms_per_launch": ms, "note": note, "max_iterations": its,
                         "kernels": kern}
             break
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            cpu = cpu_rate_2d_batch(mesh, 1.0, 64 * len(os.sched_getaffinity(0)))
+        except Exception as exc:
+            cpu = {"value": None, "unit": "solves/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc}"}
+    e2e = None
+    if not args.no_e2e:
+        f_host = torch.empty((B, nn), dtype=torch.float64, pin_memory=True)
+        f_host.copy_(f.detach())
+        g_host = torch.empty((B, nn), dtype=torch.float64, pin_memory=True)
+        g_host.copy_(gbar)
+        k_host = kappa.detach().cpu()
+        n_e2e = max(2, min(args.steps, 5))
+
+        def step_host():
+            kr = k_host.clone().requires_grad_(True)
+            u = DifferentiableFESolver(mesh, kappa=kr)(f_host)
+            u.backward(g_host)
+            return u, kr.grad
+
+        for _ in range(2):
+            step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            uh, gh = step_host()
+        barrier()
+        wall = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([wall], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            wall = float(t[0])
+        e2e = {"value": B * world * n_e2e / wall, "unit": "solves/s", "ms_per_step": 1e3 * wall / n_e2e, "steps": n_e2e,
+               "h2d_bytes_per_step": int(8 * (2 * f_host.numel() + 1)), "d2h_bytes_per_step": int(8 * (f_host.numel() + 1)),
+               "call": "u_host = DifferentiableFESolver(mesh, kappa_host)(f_host_pinned); u_host.backward(gbar_host_pinned): f and gbar "
+                       "cross to the device, u and dL/dkappa come back (host clock; f is data, dL/df is not requested)"}
+        del f_host, g_host
     if rank == 0:
         I = mesh._native(dev.index).info
         line = {"metric": "fem_fwd_adjoint_solves_per_s", "value": value, "unit": "solves/s", "n_gpus": world,
@@ -757,7 +943,7 @@ def run_b200_small2d(args, w, rank, local_rank, world, dev):
                 "config": {"workload": w["desc"], "nx": nx, "n_free": int(I.n_free), "batch_per_gpu": B, "global_batch": B * world,
                            "kappa": "shared", "pcg_tol": 1e-13, "l2": "inputs 0.57 GB/array larger than L2; no flush",
                            "parallelism": f"batch-sharded x{world}, mesh replicated" + (", NCCL allreduce of [dL/dkappa, loss]" if world > 1 else "")},
-                "roofline": roofline, "cpu_baseline": None, "e2e": None, "gpu_launches": kt.launches, "clocks": clocks}
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": kt.launches, "clocks": clocks}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -177,3 +177,18 @@ long port_pcg_csr(long n, const long* rowptr, const long* col, const double* val
   free(dinv);
   return it;
 }
+
+/* Many right-hand sides on ONE matrix (config 5b): OpenMP over the samples, every sample solved by the single-thread
+   Jacobi-PCG above.  rhs, x are (B, n) row-major; returns the largest iteration count. */
+long port_pcg_csr_batch(long n, const long* rowptr, const long* col, const double* val, long B, const double* rhs,
+                        double* x, double tol, long maxit, int nthreads) {
+  const int nt = nthreads > 0 ? nthreads : port_max_threads();
+  long worst = 0;
+#pragma omp parallel for num_threads(nt) schedule(dynamic, 1) reduction(max : worst)
+  for (long b = 0; b < B; ++b) {
+    double rel;
+    const long it = port_pcg_csr(n, rowptr, col, val, rhs + b * (size_t)n, x + b * (size_t)n, tol, maxit, &rel, 1);
+    if (it > worst) worst = it;
+  }
+  return worst;
+}

@@ -26,6 +26,9 @@ def lib():
         L.port_pcg_csr.restype = C.c_long
         L.port_pcg_csr.argtypes = [C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                    C.c_long, C.POINTER(C.c_double), C.c_int]
+        L.port_pcg_csr_batch.restype = C.c_long
+        L.port_pcg_csr_batch.argtypes = [C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p,
+                                         C.c_double, C.c_long, C.c_int]
         _lib = L
     return _lib
 
@@ -68,3 +71,15 @@ def pcg_csr(rowptr, col, vals, b, tol=1e-13, maxit=100000, nthreads=0):
     it = lib().port_pcg_csr(len(b), rowptr.ctypes.data, col.ctypes.data, vals.ctypes.data, b.ctypes.data,
                             x.ctypes.data, tol, maxit, C.byref(rel), nthreads)
     return x, int(it), rel.value
+
+
+def pcg_csr_batch(rowptr, col, vals, rhs, tol=1e-13, maxit=100000, nthreads=0):
+    """Jacobi-PCG for many right-hand sides (B, n) on one matrix, OpenMP over the samples."""
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+    col = np.ascontiguousarray(col, dtype=np.int64)
+    vals = np.ascontiguousarray(vals, dtype=np.float64)
+    rhs = np.ascontiguousarray(rhs, dtype=np.float64)
+    x = np.empty_like(rhs)
+    it = lib().port_pcg_csr_batch(rhs.shape[1], rowptr.ctypes.data, col.ctypes.data, vals.ctypes.data, rhs.shape[0],
+                                  rhs.ctypes.data, x.ctypes.data, tol, maxit, nthreads)
+    return x, int(it)
