@@ -83,14 +83,15 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def measured_traffic(prefix):
-    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernel whose name starts with
-    `prefix`, from the latest `ncu --set full` capture summarised under profiles/ (tools/make_profiles.py)."""
+def measured_traffic(workload, kernel):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of `kernel` in the `ncu --set full` capture of
+    `workload`, from the latest summary under profiles/ (tools/make_profiles.py; keys are "<workload>:<kernel name>")."""
     best = None
     for fp in sorted((ROOT / "profiles").glob("r*_traffic.json")):
         try:
             for k, v in json.loads(fp.read_text()).items():
-                if prefix in k.replace(" ", ""):
+                k = k.replace(" ", "")
+                if kernel in k and (k.startswith(workload + ":") or ":" not in k.split("<")[0].split("(")[0]):
                     best = float(v)
         except Exception:
             pass
@@ -517,7 +518,8 @@ def run_b200(args):
         roofline = {"bound": "hbm", "kernel": knames[dom],
                     "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                     "frac": kern[dom]["achieved_gbs"] / peak,
-                    "traffic": (measured_traffic("k1d_pipe<0" if dom == "solve1d_fwd" else "k1d_pipe<1")
+                    # <BWD, R, W, LB, LC, SK, MF, OUT, PF> of the two kernels this workload launches
+                    "traffic": (measured_traffic("c2", "k1d_pipe<0,9,12,2,2,0,0,1,1>" if dom == "solve1d_fwd" else "k1d_pipe<1,11,8,2,2,0,0,1,1>")
                                 if args.workload == "c2" and not args.batch and not args.n_elements else None),
                     "traffic_source": "REPLAYED from the tracked file profiles/r*_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of "
                                       "one earlier `ncu --set full` capture of this kernel on this workload) — not measured in this run",
@@ -743,14 +745,14 @@ def run_b200_2d(args, w, rank, local_rank, world, dev):
         alg = bytes_iter * iters_step / 2.0                     # per PCG launch (forward and adjoint solves average)
         roofline = {"bound": "hbm", "kernel": "k_mgpcg (cooperative multigrid-preconditioned CG)" if solver2d == "mg" else "k_pcg (cooperative Jacobi-PCG)", "achieved": alg / (ms_launch * 1e-3) / 1e9,
                     "peak": peak, "unit": "GB/s", "frac": alg / (ms_launch * 1e-3) / 1e9 / peak,
-                    "traffic": measured_traffic("k_pcg") if args.workload == "c4" and not args.n_elements else None,
+                    "traffic": measured_traffic("c4", "k_pcg(") if args.workload == "c4" and not args.n_elements else None,
                     "note": "achieved = SURVEY 8(d) accounting bytes / time; the gathered vectors stay in the 126 MB L2 "
                             "(matrix loads are evict-first), so the DRAM traffic in `traffic` is lower than the accounting",
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "ms_per_launch": ms_launch,
                     "bytes_per_iteration": bytes_iter, "iterations": its, "us_per_iteration": 1e3 * ms_pcg / calls / (iters_step / 2.0),
                     "kernels": {k: {"calls": c, "ms_per_launch": m / c} for k, (c, m) in ksum.items()}}
     if roofline is not None and solver2d == "mg":
-        tr = measured_traffic("k_mgpcg") if args.workload == "c4" and not args.n_elements else None
+        tr = measured_traffic("c4", "k_mgpcg") if args.workload == "c4" and not args.n_elements else None
         roofline["traffic"] = tr
         roofline["traffic_source"] = ("REPLAYED from profiles/r*_traffic.json (one earlier `ncu --set full` capture of k_mgpcg on this "
                                       "workload), not measured in this run")

@@ -473,13 +473,14 @@ __global__ void __launch_bounds__(32 * (W + 3), (W >= 8 ? 1 : 2)) k1d_pipe(const
   auto mis1_of = [&](int j) { return mis1c ^ (ld1p & (grpp ^ (j & ngp))); };
 
   if (tid == 0) {
-    for (int k = 0; k < NR; ++k) { mbar_init(&ctl->full[k], 1); mbar_init(&ctl->outr[k], W); }
+    for (int k = 0; k < NR; ++k) { mbar_init_raw(&ctl->full[k], 1); mbar_init_raw(&ctl->outr[k], W); }
     for (int k = 0; k < 4; ++k) {
-      mbar_init(&ctl->ufull[k], 1);
-      mbar_init(&ctl->ufree[k], W);
+      mbar_init_raw(&ctl->ufull[k], 1);
+      mbar_init_raw(&ctl->ufree[k], W);
     }
     for (int k = 0; k < 2; ++k)
-      for (int s = 0; s < 2; ++s) { mbar_init(&ctl->tot[s][k], W); mbar_init(&ctl->cf[s][k], 1); }
+      for (int s = 0; s < 2; ++s) { mbar_init_raw(&ctl->tot[s][k], W); mbar_init_raw(&ctl->cf[s][k], 1); }
+    fence_mbar_init();
     ctl->dead = 0;
   }
   __syncthreads();

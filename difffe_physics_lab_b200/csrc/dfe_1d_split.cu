@@ -145,8 +145,9 @@ __global__ void __launch_bounds__(ST, 2) k1d_pass1(const PS p) {
   const Chunk ck = make_chunk(p, c, tid);
   load_mesh_chunk(p, ck, hsS, rhS, tid);
   if (tid == 0) {
-    mbar_init(bar, 1);
-    mbar_init(bar + 1, 1);
+    mbar_init_raw(bar, 1);
+    mbar_init_raw(bar + 1, 1);
+    fence_mbar_init();
   }
   __syncthreads();
   const double* hsT = hsS + ck.tb;
@@ -393,8 +394,9 @@ __global__ void __launch_bounds__(ST, 2) k1d_pass2(const PS p) {
   const Chunk ck = make_chunk(p, c, tid);
   load_mesh_chunk(p, ck, hsS, rhS, tid);
   if (tid == 0) {
-    mbar_init(bar, 1);
-    mbar_init(bar + 1, 1);
+    mbar_init_raw(bar, 1);
+    mbar_init_raw(bar + 1, 1);
+    fence_mbar_init();
   }
   __syncthreads();
   const double* hsT = hsS + ck.tb;

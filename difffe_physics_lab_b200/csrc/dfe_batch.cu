@@ -1066,8 +1066,9 @@ __global__ void __launch_bounds__(32 * MMA_W, 2) k_band_solve_mma(int npad, long
   }
   auto frag_src = [&](int step) { return step < nb ? Ff + static_cast<size_t>(step) * FRAGD : Bf + static_cast<size_t>(nsteps - 1 - step) * FRAGD; };
   if (tid == 0) {
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
+    mbar_init_raw(&bar[0], 1);
+    mbar_init_raw(&bar[1], 1);
+    fence_mbar_init();
     mbar_arrive_expect_tx(&bar[0], FRAGD * 8u);
     bulk_g2s(stg[0], frag_src(0), FRAGD * 8u, &bar[0]);
   }
@@ -1095,17 +1096,32 @@ __global__ void __launch_bounds__(32 * MMA_W, 2) k_band_solve_mma(int npad, long
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
-    // ---- H_k applied to this block's right-hand side
+    // ---- H_k applied to this block's right-hand side.  H_k = L_kk^{-1} is lower triangular (its transpose, used on the
+    // way back, upper triangular): 6 of the 16 8 x 8 tiles are zero and are skipped (the kernel is bound by the FP64 MMA
+    // pipe: ncu `math` 43 % of the stall samples)
+    if (step < nb) {
 #pragma unroll
-    for (int ntp = 0; ntp < 4; ++ntp)
+      for (int ntp = 0; ntp < 4; ++ntp)
 #pragma unroll
-      for (int j = 0; j < 2; ++j)
+        for (int j = 0; j < 2; ++j)
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-          const double b = sH[((ntp * 2 + j) * 4 + nt) * 32 + lane];
-          dmma884(acc[0][nt][0], acc[0][nt][1], R[0][ntp][j], b);
-          dmma884(acc[1][nt][0], acc[1][nt][1], R[1][ntp][j], b);
-        }
+          for (int nt = ntp; nt < 4; ++nt) {      // out[s][r] += in[s][c] H[r][c], zero for c > r
+            const double b = sH[((ntp * 2 + j) * 4 + nt) * 32 + lane];
+            dmma884(acc[0][nt][0], acc[0][nt][1], R[0][ntp][j], b);
+            dmma884(acc[1][nt][0], acc[1][nt][1], R[1][ntp][j], b);
+          }
+    } else {
+#pragma unroll
+      for (int ntp = 0; ntp < 4; ++ntp)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int nt = 0; nt <= ntp; ++nt) {     // out[s][r] += in[s][c] H[c][r], zero for c < r
+            const double b = sH[((ntp * 2 + j) * 4 + nt) * 32 + lane];
+            dmma884(acc[0][nt][0], acc[0][nt][1], R[0][ntp][j], b);
+            dmma884(acc[1][nt][0], acc[1][nt][1], R[1][ntp][j], b);
+          }
+    }
     // ---- the right-hand side of the next step is in flight while G_k is applied to the previous block's result
     const int knext = step + 1 < nb ? step + 1 : nsteps - 2 - step;   // block of step + 1 (== k at the turn-around)
     if (step + 1 < nsteps && knext != k) {

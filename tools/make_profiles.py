@@ -25,14 +25,16 @@ def raw_page(rep):
 
 
 def stall_page(rep, pat):
-    out = subprocess.run(["ncu", "-i", str(rep), "--page", "source", "--print-source", "cuda,sass", "--csv"],
+    """Warp-stall samples per kernel from the SASS view of the source page (one block per captured launch, headed by a
+    "Kernel Name" row; the stall_* columns are per instruction)."""
+    out = subprocess.run(["ncu", "-i", str(rep), "--page", "source", "--print-source", "sass", "--csv"],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     func, hdr, res = None, None, {}
     for r in rows:
-        if len(r) == 2 and r[0] == "Function Name": func = r[1]; continue
-        if len(r) > 5 and r[0] == "Line No": hdr = r; continue
-        if hdr is None or len(r) < len(hdr) or r[0] == "" or pat not in (func or ""): continue
+        if len(r) >= 2 and r[0] == "Kernel Name": func = r[1]; continue
+        if len(r) > 5 and r[0] == "Address": hdr = r; continue
+        if hdr is None or func is None or len(r) < len(hdr) or pat not in func: continue
         agg = res.setdefault(func, collections.Counter())
         for h, v in zip(hdr, r):
             if h.startswith("stall_") and "Not" not in h and v.isdigit(): agg[h[6:]] += int(v)
@@ -55,8 +57,13 @@ def launches(src, dst):
 
 
 summary, traffic = [], {}
-for name, rep, pat, src, key in (("config 2 (1-D pipelined kernels)", "prof_pipe_final.ncu-rep", "k1d_pipe<", "launches_c2.csv", "c2"),
-                                 ("config 4 (cooperative PCG)", "prof_pcg_final.ncu-rep", "k_pcg", "launches_c4.csv", "c4")):
+SETS = {"r01": (("config 2 (1-D pipelined kernels)", "prof_pipe_final.ncu-rep", "k1d_pipe<", "launches_c2.csv", "c2"),
+                ("config 4 (cooperative PCG)", "prof_pcg_final.ncu-rep", "k_pcg", "launches_c4.csv", "c4")),
+        "r02": (("config 2 (1-D pipelined kernels; default bench line)", "prof_pipe_r2.ncu-rep", "k1d_pipe<", "launches_c2.csv", "c2"),
+                ("config 5a (sweep: forward + fused misfit adjoint)", "prof_c5a_r2.ncu-rep", "k1d_pipe<", "launches_c5a.csv", "c5a"),
+                ("config 4 (multigrid-preconditioned CG, structured assembly)", "prof_c4_r2.ncu-rep", "k_", "launches_c4.csv", "c4"),
+                ("config 5b (banded batch: block TRSM on the FP64 tensor cores, stencil load / gradient kernels)", "prof_c5b_r2.ncu-rep", "k_band", "launches_c5b.csv", "c5b"))}
+for name, rep, pat, src, key in SETS.get(TAG, SETS["r02"]):
     summary.append(f"## {name}\n")
     if (G / src).exists():
         summary.append(f"Launch list `{TAG}_{key}_launches.csv` (ncu --metrics gpu__time_duration.sum, serialised, cold cache):\n")
@@ -71,19 +78,20 @@ for name, rep, pat, src, key in (("config 2 (1-D pipelined kernels)", "prof_pipe
             summary.append(f"`{kn[:100]}` (ncu --set full --clock-control none):\n")
             for k in WANT:
                 if k in d and d[k] not in ("", "n/a"): summary.append(f"    {k:90s} {d[k]} {units.get(k, '')}")
-            norm = lambda x: x.replace("(bool)", "").replace("(int)", "").replace(" ", "")
+            norm = lambda x: x.replace("(bool)", "").replace("(int)", "").replace(" ", "").replace("void", "").split("(")[0]
             for f, agg in stalls.items():
-                if norm(f)[:40] == norm(kn)[:40]:
+                if norm(f)[:70] == norm(kn)[:70]:
                     t = sum(agg.values())
                     summary.append("    warp stall samples: " + ", ".join(f"{a} {100 * b / t:.1f}%" for a, b in agg.most_common(8)))
             summary.append("")
             rd, wr = float(d["dram__bytes_read.sum"]), float(d["dram__bytes_write.sum"])
             scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
-            traffic[kn[:60]] = rd * scale[units["dram__bytes_read.sum"]] + wr * scale[units["dram__bytes_write.sum"]]
+            traffic[f"{key}:{kn[:110]}"] = rd * scale[units["dram__bytes_read.sum"]] + wr * scale[units["dram__bytes_write.sum"]]
 (P / f"{TAG}_ncu_summary.md").write_text("# ncu summaries generated by tools/make_profiles.py from the round's final gpurun call\n\n" + "\n".join(summary) + "\n")
 (P / f"{TAG}_traffic.json").write_text(json.dumps(traffic, indent=1) + "\n")
 lines = []
-for f in ("bench", "bench_ref", "bench_c5a", "bench_c3", "bench_c4", "bench_c5b", "bench_n2", "bench_n8", "bench_c5a_n2", "bench_c5b_n2"):
+for f in ("bench", "bench_ref", "bench_c5a", "bench_c3", "bench_c4", "bench_c4_jacobi", "bench_c5b", "bench_c2e", "bench_n2", "bench_n4", "bench_n8",
+          "bench_ref_n2", "bench_c5a_n2", "bench_c5a_n8", "bench_c5b_n2"):
     fp = G / f"{f}.json"
     if fp.exists():
         for ln in fp.read_text().splitlines():
