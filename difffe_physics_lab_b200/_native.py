@@ -38,6 +38,7 @@ SYMBOLS = [
     "dfe_mg_supported", "dfe_mg_hierarchy_bytes", "dfe_mg_workspace_bytes", "dfe_mg_setup", "dfe_mg_pcg",
     "dfe_batch_supported", "dfe_batch_fwd", "dfe_batch_bwd",
     "dfe_band_supported", "dfe_band_factor_bytes", "dfe_band_workspace_bytes", "dfe_band_factor", "dfe_band_fwd", "dfe_band_bwd",
+    "dfe_band_npad", "dfe_band_solve",
 ]
 
 
@@ -204,6 +205,10 @@ def lib() -> C.CDLL:
     L.dfe_band_fwd.argtypes = [vp, i64, vp, i64, vp, vp, vp, i64, vp, sz, vp]
     L.dfe_band_bwd.restype = ci
     L.dfe_band_bwd.argtypes = [vp, i64, vp, i64, vp, i64, vp, ci, vp, i64, vp, vp, sz, vp]
+    L.dfe_band_npad.restype = i64
+    L.dfe_band_npad.argtypes = [vp]
+    L.dfe_band_solve.restype = ci
+    L.dfe_band_solve.argtypes = [vp, i64, vp, vp, vp]
     if L.dfe_abi_version() != 1:
         raise RuntimeError("libdfe_b200.so ABI version mismatch")
     _lib = L

@@ -1591,3 +1591,26 @@ extern "C" int dfe_band_bwd(const dfe_mesh* m, int64_t B, const double* gbar, in
   if (prev != m->info.device) cudaSetDevice(prev);
   return rc;
 }
+
+extern "C" int64_t dfe_band_npad(const dfe_mesh* m) { return (m && band_fits(m)) ? band_npad(m) : 0; }
+
+// X <- A_free^{-1} X for B right-hand sides in free numbering, in place (the two triangular solves alone)
+extern "C" int dfe_band_solve(const dfe_mesh* m, int64_t B, double* X, const void* factor, void* stream) {
+  int prev;
+  int rc = band_enter(m, "dfe_band_solve", &prev);
+  if (rc) return rc;
+  if (!X || !factor || B < 1 || (reinterpret_cast<uintptr_t>(X) & 15)) {
+    dfe::set_error("dfe_band_solve: null / invalid argument (X must be 16-byte aligned)");
+    rc = DFE_ERR_INVALID;
+  } else {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    band_solve(band_npad(m), B, band_ptrs(m, const_cast<void*>(factor)), X, st);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      dfe::set_error("dfe_band_solve: kernel launch failed: %s", cudaGetErrorString(e));
+      rc = DFE_ERR_CUDA;
+    }
+  }
+  if (prev != m->info.device) cudaSetDevice(prev);
+  return rc;
+}

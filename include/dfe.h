@@ -221,6 +221,13 @@ int dfe_batch_bwd(const dfe_mesh* m, int64_t B, const double* gbar, int64_t ldg,
  *                     status_dev (optional, device int32): 0 ok, 5 = pivot <= 0 (K_free not SPD)
  *   dfe_band_fwd/bwd  like dfe_batch_fwd/bwd with `factor` instead of the SELL matrix;
  *                     ws: dfe_band_workspace_bytes(m, B) bytes.  All calls are asynchronous on `stream`.
+ *   dfe_band_npad     leading dimension of a block of right-hand sides in free numbering (n_free rounded up to 32)
+ *   dfe_band_solve    X <- A_free^{-1} X for B right-hand sides, X (B, npad) row-major in FREE numbering (row r of a sample
+ *                     = free node dfe_mesh_free_nodes_host()[r]; entries r >= n_free must be 0 and stay 0), in place, with
+ *                     a factor from dfe_band_factor.  `vals_full` given to dfe_band_factor may be ANY symmetric positive
+ *                     definite matrix on the pattern of K (e.g. M + dt K): this is the operator-reuse entry point for
+ *                     time stepping (reference README.md:139-143 roadmap: heat equation; examples/heat_2d.py).  Default:
+ *                     block TRSM on the FP64 tensor cores (mma.sync m8n8k4.f64), DFE_BAND_SCALAR=1: warp-shuffle kernel.
  */
 int dfe_band_supported(const dfe_mesh* m);
 size_t dfe_band_factor_bytes(const dfe_mesh* m);
@@ -231,6 +238,8 @@ int dfe_band_fwd(const dfe_mesh* m, int64_t B, const double* f, int64_t ldf, con
 int dfe_band_bwd(const dfe_mesh* m, int64_t B, const double* gbar, int64_t ldg, const double* u, int64_t ldu,
                  const void* factor, int kappa_mode, double* gf, int64_t ldgf, double* gkappa, void* ws,
                  size_t ws_bytes, void* stream);
+int64_t dfe_band_npad(const dfe_mesh* m);
+int dfe_band_solve(const dfe_mesh* m, int64_t B, double* X, const void* factor, void* stream);
 
 #ifdef __cplusplus
 }
