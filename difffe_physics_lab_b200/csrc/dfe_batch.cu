@@ -405,6 +405,132 @@ __global__ void __launch_bounds__(256) k_band_factor(int n, int npad, const doub
   if (tid == 0) *status = sbad ? 5 : 0;
 }
 
+// Blocked variant of the factorisation (default).  k_band_factor above pays ~1500 cycles for each of its n dependent
+// pivot steps (two CTA barriers, a shared-memory round trip and a double-precision rsqrt per step: 0.72 ms at 961 unknowns —
+// 18 % of a config-5b step and, replicated on every rank, the part that does not scale over GPUs).  With 32 x 32 blocks the
+// band is block tridiagonal:
+//     L_kk L_kk^T = A_kk - L_{k,k-1} L_{k,k-1}^T,      L_{k+1,k} = A_{k+1,k} L_kk^{-T}.
+// The dense Cholesky of a diagonal block runs in ONE warp out of registers (lane i holds row i; pivots and multipliers
+// move by shuffles with compile-time register indices, no barrier and no shared-memory latency in the pivot chain), the
+// triangular solve for L_{k+1,k} in the same warp (lane a holds row a; L_kk is read from shared memory as broadcasts),
+// and the rank-32 update of the next diagonal block by the whole CTA — three CTA barriers per BLOCK instead of two per row.
+// Same outputs and the same pivot test as k_band_factor.
+__global__ void __launch_bounds__(256) k_band_factor_blk(int n, int npad, const double* __restrict__ Ab,
+                                                         double* __restrict__ invd, double* __restrict__ Lc,
+                                                         double* __restrict__ Lr, int* __restrict__ status) {
+  __shared__ double Ls[32][33];   // L_kk (lower triangle, diagonal included)
+  __shared__ double Xs[32][33];   // L_{k+1,k}: Xs[a][b] = L[32(k+1)+a][32k+b] (zero for b < a)
+  __shared__ double Ns[2][32][33];   // diagonal blocks k / k+1 (ping-pong): raw, then minus the rank-32 update (lower triangle)
+  __shared__ double Ss[32][33];   // A_{k+1,k}: Ss[a][b] = A[32(k+1)+a][32k+b] (zero for b < a)
+  __shared__ double sinv[32];
+  __shared__ int sbad;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nb = npad >> 5;
+  constexpr unsigned FULL = 0xffffffffu;
+  auto load_diag = [&](int k) {   // Ns <- A_kk (lower; identity on the padding rows), by every thread of the CTA
+    for (int q = tid; q < 1024; q += 256) {
+      const int a = q >> 5, b = q & 31;
+      const int r = 32 * k + a;
+      double v = 0.0;
+      if (b <= a) v = r < n ? Ab[static_cast<size_t>(r) * (BW + 1) + (a - b)] : (a == b ? 1.0 : 0.0);
+      Ns[k & 1][a][b] = v;
+    }
+  };
+  if (tid == 0) sbad = 0;
+  load_diag(0);
+  for (int k = 0; k < nb; ++k) {
+    const int cur = k & 1;
+    __syncthreads();   // [B1] Ns[cur] = diagonal block k, updated
+    if (warp == 0) {
+      // ---- dense Cholesky of the block, row `lane` in registers
+      double a[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) a[c] = Ns[cur][lane][c];
+      const int r = 32 * k + lane;
+      const double d0 = r < n ? Ab[static_cast<size_t>(r) * (BW + 1)] : 1.0;   // diagonal entry before elimination
+      bool bad = false;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const double pj = __shfl_sync(FULL, a[j], j);
+        const double dj = __shfl_sync(FULL, d0, j);
+        // SPD check: a pivot that lost 12 digits against its diagonal entry means K_free is (numerically) singular
+        const bool ok = pj > 1e-12 * dj;
+        bad = bad || !ok;
+        const double inv = ok ? rsqrt(pj) : 1.0;
+        const double lij = a[j] * inv;        // L[i][j] for i >= j (lane j: L_jj = p_j / sqrt(p_j))
+        a[j] = lij;
+        if (lane == j) sinv[j] = inv;
+#pragma unroll
+        for (int m = j + 1; m < 32; ++m) {
+          const double lmj = __shfl_sync(FULL, lij, m);
+          a[m] = fma(-lij, lane >= m ? lmj : 0.0, a[m]);   // (a select, not a predicated store: keeps a[] in registers)
+        }
+      }
+      if (bad && lane == 0) sbad = 1;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) Ls[lane][c] = c <= lane ? a[c] : 0.0;
+    } else {
+      // ---- meanwhile: the blocks of the next block row
+      for (int q = tid - 32; q < 1024; q += 224) {
+        const int aa = q >> 5, b = q & 31;
+        const int r = 32 * (k + 1) + aa;
+        Ss[aa][b] = (k + 1 < nb && b >= aa && r < n) ? Ab[static_cast<size_t>(r) * (BW + 1) + (32 + aa - b)] : 0.0;
+        double v = 0.0;
+        if (k + 1 < nb && b <= aa) v = r < n ? Ab[static_cast<size_t>(r) * (BW + 1) + (aa - b)] : (aa == b ? 1.0 : 0.0);
+        Ns[cur ^ 1][aa][b] = v;
+      }
+    }
+    __syncthreads();   // [B2] Ls, sinv, Ss, raw Ns[cur ^ 1] ready
+    if (warp == 0) {
+      // ---- X = S L^{-T}: row `lane` of S in registers, forward substitution along the row
+      double x[32];
+#pragma unroll
+      for (int b = 0; b < 32; ++b) x[b] = Ss[lane][b];
+#pragma unroll
+      for (int b = 0; b < 32; ++b) {
+        double acc = x[b];   // (four partial accumulators were measured: 383 -> 410 us, the chain is not the limiter)
+#pragma unroll
+        for (int c = 0; c < b; ++c) acc = fma(-x[c], Ls[b][c], acc);
+        x[b] = acc * sinv[b];
+      }
+#pragma unroll
+      for (int b = 0; b < 32; ++b) Xs[lane][b] = x[b];
+    } else {
+      // ---- meanwhile: the factor entries inside the diagonal block
+      for (int q = tid - 32; q < 1024; q += 224) {
+        const int i = q >> 5, j = q & 31;
+        const size_t gi = static_cast<size_t>(32 * k + i), gj = static_cast<size_t>(32 * k + j);
+        if (i == j) invd[gi] = sinv[i];
+        if (i > j) {
+          const double l = Ls[i][j];
+          Lc[gj * BW + (i - j) - 1] = l;
+          Lr[gi * BW + (i - j) - 1] = l;
+        }
+      }
+    }
+    __syncthreads();   // [B3] Xs ready
+    if (k + 1 < nb) {
+      for (int q = tid; q < 1024; q += 256) {
+        const int aa = q >> 5, b = q & 31;
+        if (b <= aa) {   // A_{k+1,k+1} -= L_{k+1,k} L_{k+1,k}^T (lower triangle)
+          double acc = Ns[cur ^ 1][aa][b];
+#pragma unroll 8
+          for (int c = 0; c < 32; ++c) acc = fma(-Xs[aa][c], Xs[b][c], acc);
+          Ns[cur ^ 1][aa][b] = acc;
+        }
+        if (b >= aa) {   // factor entries that cross the block boundary: row 32(k+1)+aa, column 32k+b
+          const double l = Xs[aa][b];
+          const size_t gr = static_cast<size_t>(32 * (k + 1) + aa), gc = static_cast<size_t>(32 * k + b);
+          Lc[gc * BW + (32 + aa - b) - 1] = l;
+          Lr[gr * BW + (32 + aa - b) - 1] = l;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) *status = sbad ? 5 : 0;
+}
+
 // Per-element constants shared by every sample of the batch (8 doubles per element):
 //   [0] area/3 (load weight, solver.py:143-145; -1 marks a skipped / degenerate element)   [1] area/9 (dL/df weight)
 //   [2..4] b_p   [5..7] c_p  (2-D);   1-D: [0] h/2 as the reference rounds it  [1] h/2  [2] h
@@ -1048,8 +1174,16 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
                : "d"(a), "d"(b));
 }
 
+// GIN: the right-hand sides are gathered from a (B, n_nodes) array in node numbering (gsrc[b * ldg + free_nodes[r]], the
+// adjoint's gbar restricted to the free rows) instead of being read from X; SOUT: the solution is scattered straight into
+// u (u[b * ldu + free_nodes[r]], solver.py:180-181) instead of being written back to X.  Either removes a pass over the
+// batch (k_band_rhs_bwd / k_band_scatter: 0.25 + 0.27 ms of pure copies at config 5b); X still holds y between the passes.
+template <bool GIN, bool SOUT>
 __global__ void __launch_bounds__(32 * MMA_W, 2) k_band_solve_mma(int npad, long long B, const double* __restrict__ Ff,
-                                                                  const double* __restrict__ Bf, double* __restrict__ X) {
+                                                                  const double* __restrict__ Bf, double* __restrict__ X,
+                                                                  const int* __restrict__ fnode, int nfree,
+                                                                  const double* __restrict__ gsrc, long long ldg,
+                                                                  double* __restrict__ uout, long long ldu) {
   __shared__ __align__(16) double stg[2][FRAGD];
   __shared__ uint64_t bar[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1057,13 +1191,40 @@ __global__ void __launch_bounds__(32 * MMA_W, 2) k_band_solve_mma(int npad, long
   const int nb = npad >> 5, nsteps = 2 * nb;
   const long long s0 = (blockIdx.x * static_cast<long long>(MMA_W) + warp) * MMA_S;
   double* row[2];
+  const double* grow[2];
+  double* urow[2];
   bool valid[2];
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt) {
     const long long sidx = s0 + 8 * mt + g;
     valid[mt] = sidx < B;
-    row[mt] = X + (valid[mt] ? sidx : B - 1) * npad + 2 * q;
+    const long long sc = valid[mt] ? sidx : B - 1;
+    row[mt] = X + sc * npad + 2 * q;
+    grow[mt] = GIN ? gsrc + sc * ldg : nullptr;
+    urow[mt] = SOUT ? uout + sc * ldu : nullptr;
   }
+  // right-hand side of block row kb, columns 8 nt + 2 q + {0, 1}: from X, or gathered through the free-node table
+  auto load_rhs = [&](int kb, double (&Rr)[2][4][2]) {
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      if (GIN) {
+        const int c0 = 32 * kb + 8 * nt + 2 * q;
+        const int n0 = c0 < nfree ? fnode[c0] : -1, n1 = c0 + 1 < nfree ? fnode[c0 + 1] : -1;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          Rr[mt][nt][0] = n0 >= 0 ? grow[mt][n0] : 0.0;
+          Rr[mt][nt][1] = n1 >= 0 ? grow[mt][n1] : 0.0;
+        }
+      } else {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const double2 v = *reinterpret_cast<const double2*>(row[mt] + 32 * kb + 8 * nt);
+          Rr[mt][nt][0] = v.x;
+          Rr[mt][nt][1] = v.y;
+        }
+      }
+    }
+  };
   auto frag_src = [&](int step) { return step < nb ? Ff + static_cast<size_t>(step) * FRAGD : Bf + static_cast<size_t>(nsteps - 1 - step) * FRAGD; };
   if (tid == 0) {
     mbar_init_raw(&bar[0], 1);
@@ -1073,15 +1234,11 @@ __global__ void __launch_bounds__(32 * MMA_W, 2) k_band_solve_mma(int npad, long
     bulk_g2s(stg[0], frag_src(0), FRAGD * 8u, &bar[0]);
   }
   double R[2][4][2], P[2][4][2], acc[2][4][2];
+  load_rhs(0, R);
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      const double2 v = *reinterpret_cast<const double2*>(row[mt] + 8 * nt);   // block 0
-      R[mt][nt][0] = v.x;
-      R[mt][nt][1] = v.y;
-      P[mt][nt][0] = P[mt][nt][1] = 0.0;
-    }
+    for (int nt = 0; nt < 4; ++nt) P[mt][nt][0] = P[mt][nt][1] = 0.0;
   for (int step = 0; step < nsteps; ++step) {
     const int k = step < nb ? step : nsteps - 1 - step;
     __syncthreads();   // every warp has finished step - 1: the other stage is free (and, at step 0, the barriers exist)
@@ -1125,14 +1282,18 @@ __global__ void __launch_bounds__(32 * MMA_W, 2) k_band_solve_mma(int npad, long
     // ---- the right-hand side of the next step is in flight while G_k is applied to the previous block's result
     const int knext = step + 1 < nb ? step + 1 : nsteps - 2 - step;   // block of step + 1 (== k at the turn-around)
     if (step + 1 < nsteps && knext != k) {
+      if (GIN && step + 1 < nb) {
+        load_rhs(knext, R);               // forward pass: the next block of the gathered right-hand side
+      } else {
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
+        for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-          const double2 v = *reinterpret_cast<const double2*>(row[mt] + 32 * knext + 8 * nt);
-          R[mt][nt][0] = v.x;
-          R[mt][nt][1] = v.y;
-        }
+          for (int nt = 0; nt < 4; ++nt) {
+            const double2 v = *reinterpret_cast<const double2*>(row[mt] + 32 * knext + 8 * nt);
+            R[mt][nt][0] = v.x;
+            R[mt][nt][1] = v.y;
+          }
+      }
     }
     if (step != 0 && step != nb) {   // first block of a pass: nothing above / below it
 #pragma unroll
@@ -1153,7 +1314,13 @@ __global__ void __launch_bounds__(32 * MMA_W, 2) k_band_solve_mma(int npad, long
         P[mt][nt][0] = acc[mt][nt][0];
         P[mt][nt][1] = acc[mt][nt][1];
         if (knext == k) { R[mt][nt][0] = acc[mt][nt][0]; R[mt][nt][1] = acc[mt][nt][1]; }   // turn-around: y_{nb-1} is the next rhs
-        if (valid[mt]) *reinterpret_cast<double2*>(row[mt] + 32 * k + 8 * nt) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+        if (SOUT && step >= nb) {          // backward pass: x_k is final — straight into u
+          const int c0 = 32 * k + 8 * nt + 2 * q;
+          if (valid[mt] && c0 < nfree) urow[mt][fnode[c0]] = acc[mt][nt][0];
+          if (valid[mt] && c0 + 1 < nfree) urow[mt][fnode[c0 + 1]] = acc[mt][nt][1];
+        } else if (valid[mt]) {
+          *reinterpret_cast<double2*>(row[mt] + 32 * k + 8 * nt) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+        }
       }
   }
 }
@@ -1437,7 +1604,20 @@ inline unsigned nblk(long long n, int t) { return static_cast<unsigned>((n + t -
 void band_solve(int np, long long B, const BandPtrs& p, double* X, cudaStream_t st) {
   static const bool scalar = getenv("DFE_BAND_SCALAR") != nullptr;
   if (scalar) k_band_solve<<<nblk((B + BS - 1) / BS, 4), 128, 0, st>>>(np, B, p.invd, p.Lc, p.Lr, X);
-  else k_band_solve_mma<<<nblk(B, MMA_W * MMA_S), 32 * MMA_W, 0, st>>>(np, B, p.Ff, p.Bf, X);
+  else k_band_solve_mma<false, false><<<nblk(B, MMA_W * MMA_S), 32 * MMA_W, 0, st>>>(np, B, p.Ff, p.Bf, X, nullptr, 0, nullptr, 0, nullptr, 0);
+}
+// the fused variants exist for the tensor-core kernel only
+bool band_fused_io() {
+  static const bool off = getenv("DFE_BAND_SCALAR") != nullptr || getenv("DFE_BAND_NOFUSE") != nullptr;
+  return !off;
+}
+// u[d] = g on the Dirichlet nodes of every sample (solver.py:177-179) when the solve scatters the free rows itself
+__global__ void k_band_dirichlet(const MeshDev M, long long B, double* __restrict__ u, long long ldu) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= B * M.n_dir) return;
+  const long long b = idx / M.n_dir;
+  const int d = static_cast<int>(idx - b * M.n_dir);
+  u[b * ldu + M.dir_idx[d]] = M.dir_val[d];
 }
 }  // namespace
 
@@ -1459,7 +1639,9 @@ extern "C" int dfe_band_factor(const dfe_mesh* m, const double* vals_full, void*
     cudaError_t e = cudaMemsetAsync(p.invd, 0, (np + 2 * np * BW) * sizeof(double), st);
     if (e == cudaSuccess) e = cudaMemsetAsync(p.Ab, 0, (np + 40) * (BW + 1) * sizeof(double), st);
     k_band_gather<<<nblk(m->dev.n_free, 128), 128, 0, st>>>(m->dev, vals_full, p.Ab);
-    k_band_factor<<<1, 256, 0, st>>>(m->dev.n_free, band_npad(m), p.Ab, p.invd, p.Lc, p.Lr, p.status);
+    static const bool unblocked = getenv("DFE_BAND_FACTOR_ROWS") != nullptr;   // A/B switch: the row-by-row kernel
+    if (unblocked) k_band_factor<<<1, 256, 0, st>>>(m->dev.n_free, band_npad(m), p.Ab, p.invd, p.Lc, p.Lr, p.status);
+    else k_band_factor_blk<<<1, 256, 0, st>>>(m->dev.n_free, band_npad(m), p.Ab, p.invd, p.Lc, p.Lr, p.status);
     k_band_blocks<<<static_cast<unsigned>(np / 32), 256, 0, st>>>(band_npad(m), p.invd, p.Lr, p.Ff, p.Bf);
     k_band_geom<<<nblk(m->dev.n_el, 128), 128, 0, st>>>(m->dev, p.geom);
     {
@@ -1515,8 +1697,14 @@ extern "C" int dfe_band_fwd(const dfe_mesh* m, int64_t B, const double* f, int64
       if (rgrid > B) rgrid = B;
       k_band_rhs_fwd<<<static_cast<unsigned>(rgrid), BT, rsm, st>>>(m->dev, B, np, f, ldf, vals_full, p.geom, X);
     }
-    band_solve(np, B, p, X, st);
-    k_band_scatter<<<nblk(B * (m->dev.n_free + m->dev.n_dir), 256), 256, 0, st>>>(m->dev, B, np, X, u, ldu);
+    if (band_fused_io()) {
+      if (m->dev.n_dir > 0) k_band_dirichlet<<<nblk(B * m->dev.n_dir, 256), 256, 0, st>>>(m->dev, B, u, ldu);
+      k_band_solve_mma<false, true><<<nblk(B, MMA_W * MMA_S), 32 * MMA_W, 0, st>>>(np, B, p.Ff, p.Bf, X, m->dev.free_nodes,
+                                                                                   m->dev.n_free, nullptr, 0, u, ldu);
+    } else {
+      band_solve(np, B, p, X, st);
+      k_band_scatter<<<nblk(B * (m->dev.n_free + m->dev.n_dir), 256), 256, 0, st>>>(m->dev, B, np, X, u, ldu);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
       dfe::set_error("dfe_band_fwd: kernel launch failed: %s", cudaGetErrorString(e));
@@ -1547,8 +1735,13 @@ extern "C" int dfe_band_bwd(const dfe_mesh* m, int64_t B, const double* gbar, in
     const int np = band_npad(m);
     const BandPtrs p = band_ptrs(m, const_cast<void*>(factor));
     double* X = static_cast<double*>(ws);
-    k_band_rhs_bwd<<<nblk(B * np, 256), 256, 0, st>>>(m->dev, B, np, gbar, ldg, X);
-    band_solve(np, B, p, X, st);
+    if (band_fused_io()) {
+      k_band_solve_mma<true, false><<<nblk(B, MMA_W * MMA_S), 32 * MMA_W, 0, st>>>(np, B, p.Ff, p.Bf, X, m->dev.free_nodes,
+                                                                                   m->dev.n_free, gbar, ldg, nullptr, 0);
+    } else {
+      k_band_rhs_bwd<<<nblk(B * np, 256), 256, 0, st>>>(m->dev, B, np, gbar, ldg, X);
+      band_solve(np, B, p, X, st);
+    }
     const size_t gsm = (2 * static_cast<size_t>(m->dev.n_nodes) + m->dev.n_el + 2 * BNW) * sizeof(double);
     static const bool old_kernels = getenv("DFE_BAND_OLD") != nullptr;
     static const bool reg_kernels = getenv("DFE_BAND_REG") != nullptr;
