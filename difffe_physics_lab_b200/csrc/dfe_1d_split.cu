@@ -56,6 +56,7 @@ struct PS {
   long long ldk;
   double* gke_out;       // backward PE, per-sample field: (B, n_el) output rows
   double* gk_cols;       // backward PE, shared field: [NG][n_el] per-column partial sums
+  int sup0, sup1, supk;  // PE kernels: in0 / in1 / kap_row start on a 16-byte boundary (aligned-superset row loads)
 };
 
 // chunk-static bookkeeping shared by both passes
@@ -94,6 +95,45 @@ __device__ __forceinline__ void issue_row(double* sbuf, const double* g, int len
 }
 __device__ __forceinline__ int mis_of(const double* g) {
   return static_cast<int>((reinterpret_cast<uintptr_t>(g) >> 3) & 1);
+}
+
+// Row loads of the per-element kernels (thread 0).  [g, g + len) goes to sbuf with element j at sbuf[mis + j].  When the
+// array starts on a 16-byte boundary (`sup`) the 16-byte aligned SUPERSET [g - mis, ...) is fetched with one bulk copy: the
+// element before / after the range belongs to the same array, except past its very last element (`last`).  Otherwise the
+// unaligned head / tail elements are fetched by scalar loads — which stall thread 0 for a DRAM latency before it can start
+// the bulk copy (measured: the exposed part of every sample in the round-1 version of these kernels).
+__device__ __forceinline__ uint32_t row_tx_bytes(const double* g, int len, bool sup, bool last) {
+  if (len <= 0) return 0u;
+  const int mis = static_cast<int>((reinterpret_cast<uintptr_t>(g) >> 3) & 1);
+  if (sup) {
+    int cnt = (mis + len + 1) & ~1;
+    if (last && ((mis + len) & 1)) cnt -= 2;
+    return 8u * static_cast<uint32_t>(cnt);
+  }
+  return 8u * static_cast<uint32_t>(make_seg(g, len).body);
+}
+__device__ __forceinline__ void row_scalars(double* sbuf, const double* g, int len, bool sup, bool last) {
+  if (len <= 0) return;
+  const int mis = static_cast<int>((reinterpret_cast<uintptr_t>(g) >> 3) & 1);
+  if (sup) {
+    if (last && ((mis + len) & 1)) sbuf[mis + len - 1] = g[len - 1];
+  } else {
+    const Seg q = make_seg(g, len);
+    if (q.head) sbuf[q.mis] = g[0];
+    if (q.tail) sbuf[q.mis + len - 1] = g[len - 1];
+  }
+}
+__device__ __forceinline__ void row_bulk(double* sbuf, const double* g, int len, bool sup, bool last, uint64_t* bar) {
+  if (len <= 0) return;
+  const int mis = static_cast<int>((reinterpret_cast<uintptr_t>(g) >> 3) & 1);
+  if (sup) {
+    int cnt = (mis + len + 1) & ~1;
+    if (last && ((mis + len) & 1)) cnt -= 2;
+    if (cnt > 0) bulk_g2s(sbuf, g - mis, 8u * cnt, bar);
+  } else {
+    const Seg q = make_seg(g, len);
+    if (q.body) bulk_g2s(sbuf + q.mis + q.head, g + q.head, 8u * q.body, bar);
+  }
 }
 
 // CTA-level exclusive prefix of per-thread triples.  Two-level: warp shuffle scan, then every warp scans
@@ -503,8 +543,9 @@ __global__ void __launch_bounds__(ST, 2) k1d_pass2(const PS p) {
 
 // ================================================================================================ per-element kappa
 // Same two passes with kappa_e read per element: k_e = fl(kappa_e/h_e) (solver.py:88 with kappa -> kappa[e]),
-// w_e = h_e/kappa_e.  R = 9 nodes per thread so that the extra row buffers (kappa, and u in the backward
-// pass 2) still allow two CTAs per SM; no prefetch.  dL/dkappa_e = -(q0_e + q1_e)(u_{e+1}-u_e)/kappa_e with
+// w_e = h_e/kappa_e.  R = 9 nodes per thread; the row buffers (input, kappa, and u in the backward pass 2) are DOUBLE
+// buffered: the rows of the next sample are in flight while the current one is processed (round 1 had no prefetch and
+// ran at two exposed DRAM latencies per sample).  dL/dkappa_e = -(q0_e + q1_e)(u_{e+1}-u_e)/kappa_e with
 // q_e = beta - s_e the flux of lambda in element e (s_e: chunk-local inclusive prefix of the rhs).
 constexpr int PR = 9;
 constexpr int PCH = PR * ST;   // 2304 nodes per chunk
@@ -542,7 +583,8 @@ __device__ __forceinline__ void load_mesh_chunk_pe(const PS& p, const ChunkP& k,
 // CTA scan for the PE kernels (same as cta_excl_scan; separate name only for readability of the call sites)
 #define cta_excl_scan_pe cta_excl_scan
 
-constexpr size_t smem_pe(int nrows) { return 2048 + sizeof(double) * (2 * (PCH + 2) + nrows * (PCH + 8)); }
+constexpr int PBUF = PCH + 8;   // doubles per row buffer
+constexpr size_t smem_pe(int nrows) { return 2048 + sizeof(double) * (2 * (PCH + 2) + 2 * nrows * PBUF); }
 
 template <bool BWD>
 __global__ void __launch_bounds__(ST, 2) k1d_pe_pass1(const PS p) {
@@ -552,32 +594,48 @@ __global__ void __launch_bounds__(ST, 2) k1d_pe_pass1(const PS p) {
   double* red = reinterpret_cast<double*>(smem_raw + 64 + SNW * 24);
   double* hsS = reinterpret_cast<double*>(smem_raw + 2048);
   double* rhS = hsS + (PCH + 2);
-  double* rin = rhS + (PCH + 2);        // f / gbar row chunk
-  double* kS = rin + (PCH + 8);         // kappa row chunk
+  double* rin = rhS + (PCH + 2);        // [2] f / gbar row chunk
+  double* kS = rin + 2 * PBUF;          // [2] kappa row chunk
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c = blockIdx.x % p.G, col = blockIdx.x / p.G;
   const ChunkP ck = make_chunk_pe(p, c, tid);
   load_mesh_chunk_pe(p, ck, hsS, rhS, tid);
-  for (int j = tid; j < PCH + 8; j += ST) kS[j] = 1.0;   // slots of elements that do not exist stay finite
-  if (tid == 0) mbar_init(bar, 1);
+  for (int j = tid; j < 2 * PBUF; j += ST) kS[j] = 1.0;   // slots of elements that do not exist stay finite
+  if (tid == 0) {
+    mbar_init_raw(bar, 1);
+    mbar_init_raw(bar + 1, 1);
+    fence_mbar_init();
+  }
+  fence_async_smem();
   __syncthreads();
   const double* hsT = hsS + ck.tb;
   const double* rhT = rhS + ck.tb;
-
-  int it = 0;
-  for (long long s = p.s_begin + col; s < p.s_end; s += p.NG, ++it) {
+  auto issue = [&](long long s, int b) {   // thread 0: rows of sample s -> buffer set b
     const double* g0 = p.in0 + s * p.ld0 + ck.n0;
     const double* gk = p.kap_row + s * p.ldk + ck.eA;
-    if (tid == 0) {
-      const Seg qk = make_seg(gk, ck.ecnt);
-      if (qk.head) kS[2 + qk.mis] = gk[0];
-      if (qk.tail) kS[2 + qk.mis + ck.ecnt - 1] = gk[ck.ecnt - 1];
-      issue_row(rin, g0, ck.len, bar, 8u * qk.body);
-      if (qk.body) bulk_g2s(kS + 2 + qk.mis + qk.head, gk + qk.head, 8u * qk.body, bar);
-    }
-    const double* r0 = rin + mis_of(g0) + ck.tb;
-    const double* kT = kS + 2 + mis_of(gk) + ck.tb + ck.koff;   // kT[j] = kappa of element n0-1+tb+j
-    mbar_wait(bar, it & 1);
+    const bool l0 = s == p.B - 1 && c == p.G - 1;
+    const bool lk = (p.ldk == 0 || s == p.B - 1) && ck.eA + ck.ecnt == p.nn - 1;
+    double* rb = rin + b * PBUF;
+    double* kb = kS + b * PBUF + 2;
+    row_scalars(rb, g0, ck.len, p.sup0, l0);
+    row_scalars(kb, gk, ck.ecnt, p.supk, lk);
+    mbar_arrive_expect_tx(bar + b, row_tx_bytes(g0, ck.len, p.sup0, l0) + row_tx_bytes(gk, ck.ecnt, p.supk, lk));
+    row_bulk(rb, g0, ck.len, p.sup0, l0, bar + b);
+    row_bulk(kb, gk, ck.ecnt, p.supk, lk, bar + b);
+  };
+
+  int it = 0;
+  long long s = p.s_begin + col;
+  if (tid == 0 && s < p.s_end) issue(s, 0);
+  for (; s < p.s_end; s += p.NG, ++it) {
+    const int b = it & 1;
+    // the other buffer set was last read in iteration it - 1, which ended with a CTA barrier
+    if (tid == 0 && s + p.NG < p.s_end) issue(s + p.NG, b ^ 1);
+    const double* g0 = p.in0 + s * p.ld0 + ck.n0;
+    const double* gk = p.kap_row + s * p.ldk + ck.eA;
+    const double* r0 = rin + b * PBUF + mis_of(g0) + ck.tb;
+    const double* kT = kS + b * PBUF + 2 + mis_of(gk) + ck.tb + ck.koff;   // kT[j] = kappa of element n0-1+tb+j
+    mbar_wait(bar + b, (it >> 1) & 1);
 
     double v[PR], wv[PR];
     Tri t = tri_id();
@@ -590,7 +648,7 @@ __global__ void __launch_bounds__(ST, 2) k1d_pe_pass1(const PS p) {
         double v0 = BWD ? in : __dadd_rn(__dmul_rn(hp, in), __dmul_rn(hi, in));
         if (j == 0 && ck.ownsL) v0 = 0.0;
         v[j] = v0;
-        const double w = hi * (2.0 / kT[j + 1]);   // w_e = h_e/kappa_e (hs = h/2)
+        const double w = hi * (2.0 * __drcp_rn(kT[j + 1]));   // w_e = h_e/kappa_e (hs = h/2); 2 RN(1/k) == RN(2/k)
         wv[j] = w;
         t.s += v0;
         t.w = fma(w, t.s, t.w);
@@ -666,15 +724,20 @@ __global__ void __launch_bounds__(ST, 2) k1d_pe_pass2(const PS p) {
   Tri* wt = reinterpret_cast<Tri*>(smem_raw + 64);               // [2][SNW]
   double* hsS = reinterpret_cast<double*>(smem_raw + 2048);
   double* rhS = hsS + (PCH + 2);
-  double* rin = rhS + (PCH + 2);        // f / gbar row chunk -> x0 -> output staging
-  double* kS = rin + (PCH + 8);         // kappa row chunk -> (backward) dL/dkappa_e staging
-  double* uS = kS + (PCH + 8);          // backward: u row chunk with one halo node
+  double* rinB = rhS + (PCH + 2);       // [2] f / gbar row chunk -> x0 -> output staging
+  double* kSB = rinB + 2 * PBUF;        // [2] kappa row chunk -> (backward) dL/dkappa_e staging
+  double* uSB = kSB + 2 * PBUF;         // [2] backward: u row chunk with one halo node
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c = blockIdx.x % p.G, col = blockIdx.x / p.G;
   const ChunkP ck = make_chunk_pe(p, c, tid);
   load_mesh_chunk_pe(p, ck, hsS, rhS, tid);
-  for (int j = tid; j < PCH + 8; j += ST) kS[j] = 1.0;
-  if (tid == 0) mbar_init(bar, 1);
+  for (int j = tid; j < 2 * PBUF; j += ST) kSB[j] = 1.0;
+  if (tid == 0) {
+    mbar_init_raw(bar, 1);
+    mbar_init_raw(bar + 1, 1);
+    fence_mbar_init();
+  }
+  fence_async_smem();
   __syncthreads();
   const double* hsT = hsS + ck.tb;
   const double* rhT = rhS + ck.tb;
@@ -683,29 +746,37 @@ __global__ void __launch_bounds__(ST, 2) k1d_pe_pass2(const PS p) {
   double gacc[PR];
 #pragma unroll
   for (int j = 0; j < PR; ++j) gacc[j] = 0.0;
-
-  int it = 0;
-  for (long long s = p.s_begin + col; s < p.s_end; s += p.NG, ++it) {
+  auto issue = [&](long long s, int b) {   // thread 0: rows of sample s -> buffer set b
     const double* g0 = p.in0 + s * p.ld0 + ck.n0;
     const double* gk = p.kap_row + s * p.ldk + ck.eA;
     const double* gu = BWD ? p.in1 + s * p.ld1 + ck.n0 : nullptr;
-    if (tid == 0) {
-      bulk_wait_read0();   // stores of the previous sample have read rin / kS
-      const Seg qk = make_seg(gk, ck.ecnt);
-      if (qk.head) kS[2 + qk.mis] = gk[0];
-      if (qk.tail) kS[2 + qk.mis + ck.ecnt - 1] = gk[ck.ecnt - 1];
-      uint32_t extra = 8u * qk.body;
-      Seg qu{0, 0, 0, 0};
-      if (BWD) {
-        qu = make_seg(gu, ulen);
-        if (qu.head) uS[qu.mis] = gu[0];
-        if (qu.tail) uS[qu.mis + ulen - 1] = gu[ulen - 1];
-        extra += 8u * qu.body;
-      }
-      issue_row(rin, g0, ck.len, bar, extra);
-      if (qk.body) bulk_g2s(kS + 2 + qk.mis + qk.head, gk + qk.head, 8u * qk.body, bar);
-      if (BWD && qu.body) bulk_g2s(uS + qu.mis + qu.head, gu + qu.head, 8u * qu.body, bar);
-    }
+    const bool l0 = s == p.B - 1 && c == p.G - 1;
+    const bool lk = (p.ldk == 0 || s == p.B - 1) && ck.eA + ck.ecnt == p.nn - 1;
+    const bool lu = s == p.B - 1 && ck.n0 + ulen == p.nn;
+    double* rb = rinB + b * PBUF;
+    double* kb = kSB + b * PBUF + 2;
+    double* ub = uSB + b * PBUF;
+    row_scalars(rb, g0, ck.len, p.sup0, l0);
+    row_scalars(kb, gk, ck.ecnt, p.supk, lk);
+    if (BWD) row_scalars(ub, gu, ulen, p.sup1, lu);
+    mbar_arrive_expect_tx(bar + b, row_tx_bytes(g0, ck.len, p.sup0, l0) + row_tx_bytes(gk, ck.ecnt, p.supk, lk) +
+                                       (BWD ? row_tx_bytes(gu, ulen, p.sup1, lu) : 0u));
+    row_bulk(rb, g0, ck.len, p.sup0, l0, bar + b);
+    row_bulk(kb, gk, ck.ecnt, p.supk, lk, bar + b);
+    if (BWD) row_bulk(ub, gu, ulen, p.sup1, lu, bar + b);
+  };
+
+  int it = 0;
+  long long s = p.s_begin + col;
+  if (tid == 0 && s < p.s_end) issue(s, 0);
+  for (; s < p.s_end; s += p.NG, ++it) {
+    const int bsel = it & 1;
+    double* rin = rinB + bsel * PBUF;
+    double* kS = kSB + bsel * PBUF;
+    const double* uS = uSB + bsel * PBUF;
+    const double* g0 = p.in0 + s * p.ld0 + ck.n0;
+    const double* gk = p.kap_row + s * p.ldk + ck.eA;
+    const double* gu = BWD ? p.in1 + s * p.ld1 + ck.n0 : nullptr;
     const double* cf = p.coef + (s * p.G + c) * NP2;
     const double alpha = cf[0], beta = cf[1], alpha1 = cf[2], beta1 = cf[3];
     const int mi = mis_of(g0);
@@ -714,7 +785,7 @@ __global__ void __launch_bounds__(ST, 2) k1d_pe_pass2(const PS p) {
     const int mo = have_out ? mis_of(go) : 0;
     const double* kT = kS + 2 + mis_of(gk) + ck.tb + ck.koff;
     const double* uT = BWD ? uS + mis_of(gu) + ck.tb : nullptr;
-    mbar_wait(bar, it & 1);
+    mbar_wait(bar + bsel, (it >> 1) & 1);
 
     double v[PR], ikv[PR], ge[PR];   // ikv = 2/kappa_e
     Tri t = tri_id();
@@ -727,7 +798,7 @@ __global__ void __launch_bounds__(ST, 2) k1d_pe_pass2(const PS p) {
         double v0 = BWD ? in : __dadd_rn(__dmul_rn(hp, in), __dmul_rn(hi, in));
         if (j == 0 && ck.ownsL) v0 = 0.0;
         v[j] = v0;
-        const double ik = 2.0 / kT[j + 1];
+        const double ik = 2.0 * __drcp_rn(kT[j + 1]);   // == RN(2 / kappa_e)
         ikv[j] = ik;
         const double w = hi * ik;   // w_e = h_e/kappa_e (hs = h/2)
         t.s += v0;
@@ -738,6 +809,12 @@ __global__ void __launch_bounds__(ST, 2) k1d_pe_pass2(const PS p) {
     }
     Tri tot;
     const Tri ex = cta_excl_scan_pe(t, wt, lane, warp, tot);
+    // prefetch the next sample into the other buffer set — here, not at the top of the iteration, so that the bulk stores of
+    // the previous sample (which read that set) have had half an iteration to drain
+    if (tid == 0 && s + p.NG < p.s_end) {
+      bulk_wait_read0();
+      issue(s + p.NG, bsel ^ 1);
+    }
     Tri t1 = tri_id();
     {
       double S = ex.s, X = ex.x, W = ex.w;
@@ -819,10 +896,8 @@ __global__ void __launch_bounds__(ST, 2) k1d_pe_pass2(const PS p) {
         if (qg.tail) gko[nel_chunk - 1] = kS[qg.mis + nel_chunk - 1];
         if (qg.body) bulk_s2g(gko + qg.head, kS + qg.mis + qg.head, 8u * qg.body);
       }
-      bulk_commit();
-      bulk_wait_read0();   // kS is refilled with 1.0-padding semantics below / by the next load
+      bulk_commit();   // (drained before this buffer set is refilled: see the prefetch above)
     }
-    __syncthreads();
   }
   if (BWD && shared_field) {
     double* o = p.gk_cols + static_cast<long long>(col) * (p.nn - 1) + ck.n0 + ck.tb;
@@ -902,10 +977,12 @@ int split1d_run(const dfe_mesh* m, long long B, bool bwd, const double* in0, lon
     p.ldk = kappa_mode == DFE_KAPPA_PER_SAMPLE_ELEMENT ? p.nn - 1 : 0;
     p.gke_out = gkappa;
     p.gk = nullptr;   // the fold kernel does not produce a scalar gradient in these modes
+    p.sup0 = (reinterpret_cast<uintptr_t>(in0) & 15) == 0;
+    p.sup1 = in1 && (reinterpret_cast<uintptr_t>(in1) & 15) == 0;
+    p.supk = (reinterpret_cast<uintptr_t>(kappa) & 15) == 0;
   }
 
-  static bool attr_done = false;
-  if (!attr_done) {
+  {   // per device / context, so set on every call (a process may drive several GPUs); a host-side table update
     DFE_CUDA_OK(cudaFuncSetAttribute(k1d_pass1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p1(false)));
     DFE_CUDA_OK(cudaFuncSetAttribute(k1d_pass1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p1(true)));
     DFE_CUDA_OK(cudaFuncSetAttribute(k1d_pass2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p2()));
@@ -914,7 +991,6 @@ int split1d_run(const dfe_mesh* m, long long B, bool bwd, const double* in0, lon
     DFE_CUDA_OK(cudaFuncSetAttribute(k1d_pe_pass1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pe(2)));
     DFE_CUDA_OK(cudaFuncSetAttribute(k1d_pe_pass2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pe(2)));
     DFE_CUDA_OK(cudaFuncSetAttribute(k1d_pe_pass2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pe(3)));
-    attr_done = true;
   }
   // Slabs: the batch is walked in groups of samples whose rows fit the L2, so that pass 2's re-read of
   // the row is an L2 hit.  DFE_1D_SLAB_MB overrides the slab size (0 = whole batch in one slab).
