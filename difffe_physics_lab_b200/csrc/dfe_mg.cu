@@ -24,6 +24,7 @@
 // the cycle (smooth / residual / restrict / prolong) and of CG (q = A p, vector updates) are separated by the
 // fixed-order grid reduction of dfe_gridsync.cuh, which doubles as the barrier: dot products are bit-reproducible,
 // no float atomics.  Stops at recursive ||r|| <= tol ||rhs||.
+#include <cmath>
 #include <cstdlib>
 #include <vector>
 
@@ -37,7 +38,18 @@ constexpr int MT = 768;            // threads per CTA, one CTA per SM
 constexpr int MW = MT / 32;
 constexpr int MG_MAXL = 12;
 constexpr int MG_COARSEST = 32;    // unknowns of the coarsest grid (explicit inverse)
-constexpr double OMEGA = 0.8;
+constexpr double OMEGA1 = 0.8;   // one sweep: optimal single damping for the high-frequency range [1/2, 2] of D^-1 A
+// Damping of sweep k = 1 .. nu.  One sweep: 0.8.  More: the reciprocals of the roots of the Chebyshev polynomial of degree nu
+// on [1/2, 2] — the eigenvalue range of D^-1 A that standard coarsening leaves to the smoother (lambda_max <= 2 by
+// Gershgorin for these M-matrices).  Two sweeps then damp the range by 1 / T_2(5/3) = 0.22 instead of 0.6^2 = 0.36; the
+// smoother is still a polynomial in D^-1 A, so the V-cycle stays symmetric positive definite.  DFE_MG_CHEB=0: constant 0.8.
+inline void mg_omegas(int nu, double* om) {
+  static const bool cheb = [] { const char* e = getenv("DFE_MG_CHEB"); return !(e && e[0] == '0'); }();
+  for (int k = 0; k < 8; ++k) om[k] = OMEGA1;
+  if (!cheb || nu < 2) return;
+  const double theta = 1.25, delta = 0.75, pi = 3.14159265358979323846;
+  for (int k = 1; k <= nu && k <= 8; ++k) om[k - 1] = 1.0 / (theta + delta * cos((2 * k - 1) * pi / (2.0 * nu)));
+}
 
 struct MgMat {   // one level; pointers into the hierarchy buffer
   int my, mx, n, nine;
@@ -257,6 +269,7 @@ struct MgArgs {
   double tol;
   long long maxit;
   int nu, backoff;
+  double omega[8];      // damping of smoothing sweep 1 .. nu (Chebyshev weights, see mg_omegas)
 };
 
 // contiguous range of the n nodes of a level owned by this CTA
@@ -293,16 +306,18 @@ struct CtaPhase {
 // (nullptr: the implicit x1).
 template <class Ph>
 __device__ __forceinline__ const double* mg_down(const MgMat& M, const MgVec& V, const MgMat& Mc, double* bc, int nu,
-                                                 const Ph& ph) {
+                                                 const double* om, const Ph& ph) {
   const int tid = threadIdx.x;
   int lo, hi;
   ph.range(M.n, lo, hi);
   const double* b = V.b;
   const double* dinv = M.dinv;
-  auto x1 = [&](int k) { return OMEGA * dinv[k] * b[k]; };
+  const double om1 = om[0];
+  auto x1 = [&](int k) { return om1 * dinv[k] * b[k]; };
   const double* src = nullptr;
   for (int s = 2; s <= nu; ++s) {
     double* dst = (src == V.xa) ? V.xb : V.xa;
+    const double OMEGA = om[s - 1];
     for (int k = lo + tid; k < hi; k += MT) {
       const int i = k / M.mx, j = k - i * M.mx;
       double xo, off;
@@ -345,7 +360,7 @@ __device__ __forceinline__ const double* mg_down(const MgMat& M, const MgVec& V,
 // forms sum_k b_k x_k and the closing barrier reduces it over the grid.  Returns the final iterate.
 template <class Ph>
 __device__ __forceinline__ const double* mg_up(const MgMat& M, const MgVec& V, const double* src, const double* e,
-                                               int nu, double* rz, const Ph& ph) {
+                                               int nu, const double* om, double* rz, const Ph& ph) {
   const int tid = threadIdx.x;
   int lo, hi;
   ph.range(M.n, lo, hi);
@@ -374,13 +389,14 @@ __device__ __forceinline__ const double* mg_up(const MgMat& M, const MgVec& V, c
       if (IN < cy && JW >= 0) c = fma(M.pw[2 * n + k], e[IN * cx + JW], c);
       if (IN < cy && JE < cx) c = fma(M.pw[3 * n + k], e[IN * cx + JE], c);
     }
-    dst[k] = (src ? src[k] : OMEGA * dinv[k] * b[k]) + c;
+    dst[k] = (src ? src[k] : om[0] * dinv[k] * b[k]) + c;
   }
   ph.sync();
   src = dst;
   for (int s = 1; s <= nu; ++s) {
     dst = (src == V.xa) ? V.xb : V.xa;
     const bool last = (rz != nullptr && s == nu);
+    const double OMEGA = om[nu - s];   // the pre-smoother's weights in reverse order: the cycle stays symmetric
     double acc = 0.0;
     for (int k = lo + tid; k < hi; k += MT) {
       const int i = k / M.mx, j = k - i * M.mx;
@@ -484,9 +500,9 @@ __global__ void __launch_bounds__(MT, 1) k_mgpcg(const __grid_constant__ MgArgs 
       // ======================================================= z = M^{-1} r : one V(nu, nu) cycle
       const double* xsrc[MG_MAXL];    // pre-smoothed iterate of every level (nullptr: the implicit first sweep)
       double rz_new = 0.0;
-      for (int l = 0; l < lc; ++l) xsrc[l] = mg_down(A.H.lev[l], A.v[l], A.H.lev[l + 1], A.v[l + 1].b, nu, gph);
+      for (int l = 0; l < lc; ++l) xsrc[l] = mg_down(A.H.lev[l], A.v[l], A.H.lev[l + 1], A.v[l + 1].b, nu, A.omega, gph);
       if (blockIdx.x == 0) {          // the tail: levels lc .. L-1, CTA 0 alone
-        for (int l = lc; l + 1 < L; ++l) xsrc[l] = mg_down(tm[l], tv[l], tm[l + 1], tv[l + 1].b, nu, cph);
+        for (int l = lc; l + 1 < L; ++l) xsrc[l] = mg_down(tm[l], tv[l], tm[l + 1], tv[l + 1].b, nu, A.omega, cph);
         const int nc = A.H.nc;
         if (tid < nc) {               // coarsest level: x = Ainv b
           const double* b = tv[L - 1].b;
@@ -496,7 +512,7 @@ __global__ void __launch_bounds__(MT, 1) k_mgpcg(const __grid_constant__ MgArgs 
         }
         __syncthreads();
         const double* e = tv[L - 1].xa;
-        for (int l = L - 2; l >= lc; --l) e = mg_up(tm[l], tv[l], xsrc[l], e, nu, nullptr, cph);
+        for (int l = L - 2; l >= lc; --l) e = mg_up(tm[l], tv[l], xsrc[l], e, nu, A.omega, nullptr, cph);
         // (for lc == L-1 the coarsest solution itself sits in the global xa of that level)
       }
       grid_barrier<MW>(gs, epoch, sh);
@@ -511,7 +527,7 @@ __global__ void __launch_bounds__(MT, 1) k_mgpcg(const __grid_constant__ MgArgs 
         for (int s = 1; s <= nu; ++s) cur = (cur == A.v[lc].xa) ? A.v[lc].xb : A.v[lc].xa;
         e = cur;
       }
-      for (int l = lc - 1; l >= 0; --l) e = mg_up(A.H.lev[l], A.v[l], xsrc[l], e, nu, l == 0 ? &rz_new : nullptr, gph);
+      for (int l = lc - 1; l >= 0; --l) e = mg_up(A.H.lev[l], A.v[l], xsrc[l], e, nu, A.omega, l == 0 ? &rz_new : nullptr, gph);
       if (grid_aborted(gs)) { status = 7.0; break; }
       const double* z = e;
       if (!(rz_new > 0.0) || !isfinite(rz_new)) { status = 5.0; break; }
@@ -770,6 +786,7 @@ extern "C" int dfe_mg_pcg(const dfe_mesh* m, const void* hier, const double* rhs
     R.tol = tol;
     R.maxit = maxit;
     R.nu = nu;
+    mg_omegas(nu, R.omega);
     static const int backoff = [] { const char* e = getenv("DFE_PCG_BACKOFF"); return e ? atoi(e) : 250; }();
     R.backoff = backoff;
     int per_sm = 0;
