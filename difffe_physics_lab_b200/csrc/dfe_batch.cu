@@ -916,14 +916,20 @@ __global__ void __launch_bounds__(512) k_band_rhs_fwd3(const MeshDev M, long lon
   cp_async_wait<0>();
 }
 
-__global__ void __launch_bounds__(SBT_MAX) k_band_grad3(const MeshDev M, long long B, int npad, int nnp,
+// GF: dL/df = M_F lambda (streams the lambda rows);  GK: per-warp partials of lambda^T K^0 u (streams u and lambda rows).
+// Both in one kernel cost 96 registers at 576 threads (one CTA per SM, 0.86 ms at config 5b); as two kernels each half keeps
+// the weights of ONE stencil in registers and two CTAs fit an SM, but the lambda rows are streamed twice (0.54 + 0.39 ms):
+// the fused form is the default, an adjoint without dL/df launches the GK half only.
+template <bool GF, bool GK>
+__global__ void __launch_bounds__(SBT_MAX, (GF && GK) ? 1 : 2) k_band_grad3(const MeshDev M, long long B, int npad, int nnp,
                                                         const double* __restrict__ X, const double* __restrict__ ufull,
                                                         long long ldu, const double* __restrict__ ellK,
                                                         const double* __restrict__ ellMr, const unsigned* __restrict__ ellc,
                                                         double* __restrict__ gkpart, double* __restrict__ gf, long long ldgf) {
-  extern __shared__ __align__(16) double sg[];   // [NST_G][nnp + 2 + npad]: u row, lambda row (free numbering)
+  extern __shared__ __align__(16) double sg[];   // [NST_G][(nnp + 2) + npad]: u row (GK only), lambda row (free numbering)
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
-  const int pitch = nnp + 2 + npad;        // u row (with room for its 16-byte phase) | lambda row
+  const int uoff = GK ? nnp + 2 : 0;       // u row (with room for its 16-byte phase) | lambda row
+  const int pitch = uoff + npad;
   double wk[SR][SW], wm[SR][SW];
   unsigned c[SR][SW];
   int rk[SR];
@@ -934,8 +940,8 @@ __global__ void __launch_bounds__(SBT_MAX) k_band_grad3(const MeshDev M, long lo
     rk[k] = ex ? M.free_rank[p] : -1;
 #pragma unroll
     for (int j = 0; j < SW; ++j) {
-      wk[k][j] = ex ? ellK[static_cast<size_t>(j) * nnp + p] : 0.0;
-      wm[k][j] = ex ? ellMr[static_cast<size_t>(j) * nnp + p] : 0.0;
+      wk[k][j] = (GK && ex) ? ellK[static_cast<size_t>(j) * nnp + p] : 0.0;
+      wm[k][j] = (GF && ex) ? ellMr[static_cast<size_t>(j) * nnp + p] : 0.0;
       c[k][j] = ex ? ellc[static_cast<size_t>(j) * nnp + p] : 0u;
     }
   }
@@ -946,9 +952,9 @@ __global__ void __launch_bounds__(SBT_MAX) k_band_grad3(const MeshDev M, long lo
   auto issue = [&]() {
     if (b_in < B) {
       const uint32_t du = sg32 + 8u * (st_in * pitch);
-      row_to_smem(du, ufull + b_in * ldu, M.n_nodes, tid, nt);
+      if (GK) row_to_smem(du, ufull + b_in * ldu, M.n_nodes, tid, nt);
       const double* sl = X + b_in * npad;      // 16-byte aligned rows (npad is a multiple of 32)
-      for (int q = tid; q < (npad >> 1); q += nt) cp_async16_u32(du + 8u * (nnp + 2) + 16u * q, sl + 2 * q);
+      for (int q = tid; q < (npad >> 1); q += nt) cp_async16_u32(du + 8u * uoff + 16u * q, sl + 2 * q);
     }
     cp_async_commit();
     b_in += bs;
@@ -960,31 +966,37 @@ __global__ void __launch_bounds__(SBT_MAX) k_band_grad3(const MeshDev M, long lo
     cp_async_wait<NST_G - 2>();
     __syncthreads();
     issue();
-    const double* ub = sg + st * pitch + ((reinterpret_cast<uintptr_t>(ufull + b * ldu) >> 3) & 1);
-    const double* lb = sg + st * pitch + nnp + 2;
+    const double* ub = sg + st * pitch + (GK ? ((reinterpret_cast<uintptr_t>(ufull + b * ldu) >> 3) & 1) : 0);
+    const double* lb = sg + st * pitch + uoff;
     double part = 0.0;
 #pragma unroll
     for (int k = 0; k < SR; ++k) {
       const int p = tid + k * nt;
-      double uv[SW], lv[SW];
+      if (GK) {
+        double uv[SW];
 #pragma unroll
-      for (int j = 0; j < SW; ++j) {
-        uv[j] = ub[c[k][j] & 0xffffu];
-        lv[j] = lb[c[k][j] >> 16];
-      }
-      const double lam = rk[k] >= 0 ? lb[rk[k]] : 0.0;
-      double ku = 0.0, ml = 0.0;
+        for (int j = 0; j < SW; ++j) uv[j] = ub[c[k][j] & 0xffffu];
+        const double lam = rk[k] >= 0 ? lb[rk[k]] : 0.0;
+        double ku = 0.0;
 #pragma unroll
-      for (int j = 0; j < SW; ++j) {
-        ku = fma(wk[k][j], uv[j], ku);
-        ml = fma(wm[k][j], lv[j], ml);
+        for (int j = 0; j < SW; ++j) ku = fma(wk[k][j], uv[j], ku);
+        part = fma(lam, ku, part);
       }
-      part = fma(lam, ku, part);
-      if (gf && p < M.n_nodes) gf[b * ldgf + p] = ml;
+      if (GF) {
+        double lv[SW];
+#pragma unroll
+        for (int j = 0; j < SW; ++j) lv[j] = lb[c[k][j] >> 16];
+        double ml = 0.0;
+#pragma unroll
+        for (int j = 0; j < SW; ++j) ml = fma(wm[k][j], lv[j], ml);
+        if (p < M.n_nodes) gf[b * ldgf + p] = ml;
+      }
     }
+    if (GK) {
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
-    if (lane == 0) gkpart[b * nw + warp] = part;
+      for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+      if (lane == 0) gkpart[b * nw + warp] = part;
+    }
     st = st + 1 == NST_G ? 0 : st + 1;
   }
   cp_async_wait<0>();
@@ -1748,14 +1760,23 @@ extern "C" int dfe_band_bwd(const dfe_mesh* m, int64_t B, const double* gbar, in
     if (kappa_mode == DFE_KAPPA_SCALAR && band_stencil_fits(m) && !old_kernels && !reg_kernels) {
       const int nt = ((m->dev.n_nodes + SR - 1) / SR + 31) & ~31;
       double* gkpart = X + static_cast<size_t>(B) * np;
-      const size_t sm3 = static_cast<size_t>(NST_G) * (p.nnp + 2 + np) * sizeof(double);
-      cudaFuncSetAttribute(k_band_grad3, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm3));
-      int occ = 1;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_band_grad3, nt, sm3);
-      long long grid = static_cast<long long>(occ > 0 ? occ : 1) * m->sm_count;
-      if (grid > B) grid = B;
-      k_band_grad3<<<static_cast<unsigned>(grid), nt, sm3, st>>>(m->dev, B, np, p.nnp, X, u, ldu, p.ellK, p.ellMr, p.ellc, gkpart,
-                                                                  gf, ldgf);
+      auto launch_half = [&](auto kern, size_t sm3, double* gfp) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm3));
+        int occ = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nt, sm3);
+        long long grid = static_cast<long long>(occ > 0 ? occ : 1) * m->sm_count;   // persistent: one wave
+        if (grid > B) grid = B;
+        kern<<<static_cast<unsigned>(grid), nt, sm3, st>>>(m->dev, B, np, p.nnp, X, u, ldu, p.ellK, p.ellMr, p.ellc, gkpart, gfp, ldgf);
+      };
+      // both halves in one kernel when dL/df is wanted (measured: 0.86 ms vs 0.54 + 0.39 ms as two kernels — the second
+      // pass over the lambda rows costs more than the lower occupancy); DFE_BAND_GRAD_SPLIT=1 is the A/B switch
+      static const bool split = getenv("DFE_BAND_GRAD_SPLIT") != nullptr;
+      if (gf && !split) {
+        launch_half(k_band_grad3<true, true>, static_cast<size_t>(NST_G) * (p.nnp + 2 + np) * sizeof(double), gf);
+      } else {
+        launch_half(k_band_grad3<false, true>, static_cast<size_t>(NST_G) * (p.nnp + 2 + np) * sizeof(double), nullptr);
+        if (gf) launch_half(k_band_grad3<true, false>, static_cast<size_t>(NST_G) * np * sizeof(double), gf);
+      }
       k_band_gksum<<<nblk(B, 256), 256, 0, st>>>(B, nt / 32, gkpart, gkappa);
     } else if (band_reg_fits(m) && !old_kernels) {
       const int nnp = (m->dev.n_nodes + 1) & ~1;
