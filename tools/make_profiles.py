@@ -91,7 +91,7 @@ for name, rep, pat, src, key in SETS.get(TAG, SETS["r02"]):
 (P / f"{TAG}_traffic.json").write_text(json.dumps(traffic, indent=1) + "\n")
 lines = []
 for f in ("bench", "bench_ref", "bench_c5a", "bench_c3", "bench_c4", "bench_c4_jacobi", "bench_c5b", "bench_c2e", "bench_n2", "bench_n4", "bench_n8",
-          "bench_ref_n2", "bench_ref_n8", "bench_c5a_n2", "bench_c5a_n8", "bench_c5b_n2", "bench_c5b_n8"):
+          "bench_ref_n2", "bench_ref_n4", "bench_ref_n8", "bench_c5b_n2", "bench_c5b_n4", "bench_c5b_n8"):
     fp = G / f"{f}.json"
     if fp.exists():
         for ln in fp.read_text().splitlines():
