@@ -22,7 +22,7 @@ LIB_PATH = PKG / "libdfe_b200.so"
 SOURCES = ["dfe_mesh.cu", "dfe_1d.cu", "dfe_1d_split.cu", "dfe_1d_pipe.cu", "dfe_general.cu", "dfe_pcg.cu", "dfe_mg.cu",
            "dfe_batch.cu"]
 HEADERS = [PKG / "csrc" / "dfe_internal.h", PKG / "csrc" / "dfe_1d_common.cuh", PKG / "csrc" / "dfe_gridsync.cuh", PKG / "csrc" / "dfe_exact.cuh",
-           ROOT / "include" / "dfe.h"]
+           PKG / "csrc" / "dfe_p2.cuh", ROOT / "include" / "dfe.h"]
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOT_CONVERGED, ERR_BREAKDOWN, ERR_WORKSPACE = range(7)
 KAPPA_SCALAR, KAPPA_PER_SAMPLE, KAPPA_PER_ELEMENT, KAPPA_PER_SAMPLE_ELEMENT = range(4)
@@ -30,7 +30,7 @@ KAPPA_SCALAR, KAPPA_PER_SAMPLE, KAPPA_PER_ELEMENT, KAPPA_PER_SAMPLE_ELEMENT = ra
 # every symbol include/dfe.h declares (tests check the library exports exactly these)
 SYMBOLS = [
     "dfe_last_error", "dfe_abi_version", "dfe_device_count",
-    "dfe_mesh_create", "dfe_mesh_destroy", "dfe_mesh_get_info", "dfe_mesh_csr_host", "dfe_mesh_free_nodes_host",
+    "dfe_mesh_create", "dfe_mesh_create_p", "dfe_mesh_destroy", "dfe_mesh_get_info", "dfe_mesh_csr_host", "dfe_mesh_free_nodes_host",
     "dfe_solve1d_workspace_bytes", "dfe_solve1d_fwd", "dfe_solve1d_bwd", "dfe_solve1d_bwd_misfit",
     "dfe_solve1d_supported", "dfe_mesh_fault",
     "dfe_assemble", "dfe_eliminate", "dfe_pcg_workspace_bytes", "dfe_pcg", "dfe_scatter", "dfe_gather_free",
@@ -141,6 +141,8 @@ def lib() -> C.CDLL:
     L.dfe_device_count.restype = ci
     L.dfe_mesh_create.restype = ci
     L.dfe_mesh_create.argtypes = [ci, i64, i64, vp, vp, i64, vp, vp, ci, C.POINTER(vp)]
+    L.dfe_mesh_create_p.restype = ci
+    L.dfe_mesh_create_p.argtypes = [ci, ci, i64, i64, vp, vp, i64, vp, vp, ci, C.POINTER(vp)]
     L.dfe_mesh_destroy.restype = None
     L.dfe_mesh_destroy.argtypes = [vp]
     L.dfe_mesh_get_info.restype = ci

@@ -1429,7 +1429,7 @@ int band_width(const dfe_mesh* m) {   // max |row - col| over the pattern of K_f
   return static_cast<int>(w);
 }
 bool band_fits(const dfe_mesh* m) {
-  if (!m || m->info.device < 0 || m->dev.n_free < 1) return false;
+  if (!m || m->info.device < 0 || m->dev.n_free < 1 || m->dev.npe != m->dev.dim + 1) return false;   // P1 load / gradient kernels
   // the gradient kernel keeps lambda (all nodes) and one sum per element in shared memory
   if ((2 * static_cast<size_t>(m->dev.n_nodes) + m->dev.n_el + 2 * BNW) * sizeof(double) > 200 * 1024) return false;
   return band_width(m) <= BW;
@@ -1443,7 +1443,7 @@ size_t batch_smem(const dfe_mesh* m, bool bwd) {
 }
 
 bool batch_fits(const dfe_mesh* m) {
-  if (!m || m->info.device < 0 || m->dev.n_free < 1) return false;
+  if (!m || m->info.device < 0 || m->dev.n_free < 1 || m->dev.npe != m->dev.dim + 1) return false;   // P1 load / gradient kernels
   if (m->dev.n_slices > BNW * RPT_MAX) return false;
   return batch_smem(m, true) <= 200 * 1024;
 }

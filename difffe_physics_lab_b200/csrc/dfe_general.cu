@@ -20,6 +20,17 @@ namespace {
 using dfe::MeshDev;
 constexpr double AREA_EPS = 1e-15;  // solver.py:120
 
+#include "dfe_p2.cuh"   // closed-form P2 element matrices (roadmap extension, no upstream arithmetic)
+
+// vertices of P2 triangle e (the first three of its six nodes)
+__device__ __forceinline__ P2Tri p2_tri_of(const MeshDev& M, int e, int (&n)[6]) {
+#pragma unroll
+  for (int q = 0; q < 6; ++q) n[q] = M.elems[6 * e + q];
+  const double x[3] = {M.nodes[2 * n[0]], M.nodes[2 * n[1]], M.nodes[2 * n[2]]};
+  const double y[3] = {M.nodes[2 * n[0] + 1], M.nodes[2 * n[1] + 1], M.nodes[2 * n[2] + 1]};
+  return p2_tri_geom(x, y);
+}
+
 struct Elem2D {
   double area, b[3], c[3];
 };
@@ -70,7 +81,34 @@ __device__ __forceinline__ void assemble_row(const MeshDev& M, int p, const doub
     const int e = M.adj_elem[a];
     const int loc = M.adj_loc[a];
     const double kap = kappa[per_elem ? e : 0];
-    if (M.dim == 1) {
+    if (M.npe != M.dim + 1) {                               // P2 (dfe_p2.cuh); F = M f with the consistent mass matrix
+      if (M.dim == 1) {
+        const int n[3] = {M.elems[3 * e], M.elems[3 * e + 1], M.elems[3 * e + 2]};
+        const double h = M.nodes[n[1]] - M.nodes[n[0]];
+        const double ks = kap / (3.0 * h), ms = h / 30.0;
+        double fl = 0.0;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          add(M.adj_slot[3 * a + q], ks * p2_line_k0(loc, q));
+          fl = fma(p2_line_m(loc, q), f[n[q]], fl);
+        }
+        Fp = fma(ms, fl, Fp);
+      } else {
+        int n[6];
+        const P2Tri T = p2_tri_of(M, e, n);
+        if (!T.keep) continue;
+        double kr[6], mr[6];
+        p2_tri_k0_row(T, loc, kr);
+        p2_tri_m_row(loc, mr);
+        double fl = 0.0;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          add(M.adj_slot[6 * a + q], kap * kr[q]);
+          fl = fma(mr[q], f[n[q]], fl);
+        }
+        Fp = fma(T.area * (1.0 / 180.0), fl, Fp);
+      }
+    } else if (M.dim == 1) {
       const int i = M.elems[2 * e], j = M.elems[2 * e + 1];
       const double h = __dsub_rn(M.nodes[j], M.nodes[i]);   // solver.py:84-85
       const double ke = __ddiv_rn(kap, h);                  // :88
@@ -228,14 +266,24 @@ __device__ __forceinline__ double div_m(double a, double b, double y) {
   return fma(fma(-b, q1, a), y, q1);
 }
 
-// element matrix (k00 k01 k02 k11 k12 k22) and load term (area/3) * (f_i + f_j + f_k)/3 of one triangle, solver.py:119-145
+// kappa is exactly zero or in [2^-170, 2^170] (with dfe_mesh::topo_geo_mid: every numerator then is 0 or in [2^-463, 2^411])
+__device__ __forceinline__ bool kappa_zero_or_mid(double v) {
+  const unsigned hi = static_cast<unsigned>(__double2hiint(v)) & 0x7fffffffu;
+  return ((hi >> 20) - 853u) <= 340u || (hi | static_cast<unsigned>(__double2loint(v))) == 0u;
+}
+
+// element matrix (k00 k01 k02 k11 k12 k22) and load term (area/3) * (f_i + f_j + f_k)/3 of one triangle, solver.py:119-145.
+// GEO: the handle has verified the range of the geometry once (dfe_mesh::topo_geo_mid), so only kappa and the load sum are
+// range-checked per call; otherwise every numerator is.
+template <bool GEO>
 __device__ __forceinline__ void tri_full(const double (&x)[3], const double (&y)[3], double kap, const double (&fv)[3],
                                          double (&k)[6], double& fterm) {
-  const double t1 = __dmul_rn(__dsub_rn(x[1], x[0]), __dsub_rn(y[2], y[0]));
-  const double t2 = __dmul_rn(__dsub_rn(x[2], x[0]), __dsub_rn(y[1], y[0]));
-  const double area = __dmul_rn(0.5, fabs(__dsub_rn(t1, t2)));   // :119
   const double b[3] = {__dsub_rn(y[1], y[2]), __dsub_rn(y[2], y[0]), __dsub_rn(y[0], y[1])};
   const double c[3] = {__dsub_rn(x[2], x[1]), __dsub_rn(x[0], x[2]), __dsub_rn(x[1], x[0])};
+  // :119  (x_j - x_i)(y_k - y_i) - (x_k - x_i)(y_j - y_i) = c2 b1 - (-c1)(-b2): negation is exact, the products are the same bits
+  const double t1 = __dmul_rn(c[2], b[1]);
+  const double t2 = __dmul_rn(c[1], b[2]);
+  const double area = __dmul_rn(0.5, fabs(__dsub_rn(t1, t2)));
   const double den = __dmul_rn(4.0, area);
   double num[6];
   num[0] = __dmul_rn(kap, __dadd_rn(__dmul_rn(b[0], b[0]), __dmul_rn(c[0], c[0])));   // :139
@@ -245,9 +293,14 @@ __device__ __forceinline__ void tri_full(const double (&x)[3], const double (&y)
   num[4] = __dmul_rn(kap, __dadd_rn(__dmul_rn(b[1], b[2]), __dmul_rn(c[1], c[2])));
   num[5] = __dmul_rn(kap, __dadd_rn(__dmul_rn(b[2], b[2]), __dmul_rn(c[2], c[2])));
   const double fsum = __dadd_rn(__dadd_rn(fv[0], fv[1]), fv[2]);
-  bool ok = zero_or_mid(den) && den != 0.0 && zero_or_mid(fsum) && zero_or_mid(area);
+  bool ok;
+  if (GEO) {
+    ok = kappa_zero_or_mid(kap) && zero_or_mid(fsum);
+  } else {
+    ok = zero_or_mid(den) && den != 0.0 && zero_or_mid(fsum) && zero_or_mid(area);
 #pragma unroll
-  for (int i = 0; i < 6; ++i) ok = ok && zero_or_mid(num[i]);
+    for (int i = 0; i < 6; ++i) ok = ok && zero_or_mid(num[i]);
+  }
   if (area < AREA_EPS) {                                          // :120-121 — contributes nothing (adds +0)
 #pragma unroll
     for (int i = 0; i < 6; ++i) k[i] = 0.0;
@@ -265,6 +318,7 @@ __device__ __forceinline__ void tri_full(const double (&x)[3], const double (&y)
   }
 }
 
+template <bool GEO>
 __global__ void __launch_bounds__(AQ_T, 4) k_assemble_tile(const MeshDev M, int gx, int gy, const double* __restrict__ kappa,
                                                         int per_elem, const double* __restrict__ f,
                                                         double* __restrict__ vals, double* __restrict__ F) {
@@ -293,14 +347,14 @@ __global__ void __launch_bounds__(AQ_T, 4) k_assemble_tile(const MeshDev M, int 
       double k[6], ft;
       {   // triangle 0 = [a, b, d]
         const double x[3] = {pa.x, pb.x, pd.x}, y[3] = {pa.y, pb.y, pd.y}, fv[3] = {fa, fb, fd};
-        tri_full(x, y, k0, fv, k, ft);
+        tri_full<GEO>(x, y, k0, fv, k, ft);
 #pragma unroll
         for (int i = 0; i < 6; ++i) tri[0][i][tid] = k[i];
         tri[0][6][tid] = ft;
       }
       {   // triangle 1 = [b, c, d]
         const double x[3] = {pb.x, pc.x, pd.x}, y[3] = {pb.y, pc.y, pd.y}, fv[3] = {fb, fc, fd};
-        tri_full(x, y, k1, fv, k, ft);
+        tri_full<GEO>(x, y, k1, fv, k, ft);
 #pragma unroll
         for (int i = 0; i < 6; ++i) tri[1][i][tid] = k[i];
         tri[1][6][tid] = ft;
@@ -397,7 +451,35 @@ __global__ void k_grad_elem(const MeshDev M, const double* __restrict__ lam, con
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= M.n_el) return;
   double g = 0.0;
-  if (M.dim == 1) {
+  if (M.npe != M.dim + 1) {                                 // P2: -lam_e^T K_e^0 u_e with the closed-form K_e^0
+    if (M.dim == 1) {
+      const int n[3] = {M.elems[3 * e], M.elems[3 * e + 1], M.elems[3 * e + 2]};
+      const double h = M.nodes[n[1]] - M.nodes[n[0]];
+      double acc = 0.0;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc = fma(lam[n[i]] * p2_line_k0(i, j), u[n[j]], acc);
+      g = -acc / (3.0 * h);
+    } else {
+      int n[6];
+      const P2Tri T = p2_tri_of(M, e, n);
+      if (T.keep) {
+        double ue[6], acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) ue[j] = u[n[j]];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          double kr[6], ri = 0.0;
+          p2_tri_k0_row(T, i, kr);
+#pragma unroll
+          for (int j = 0; j < 6; ++j) ri = fma(kr[j], ue[j], ri);
+          acc = fma(lam[n[i]], ri, acc);
+        }
+        g = -acc;
+      }
+    }
+  } else if (M.dim == 1) {
     const int i = M.elems[2 * e], j = M.elems[2 * e + 1];
     const double h = M.nodes[j] - M.nodes[i];
     g = -(lam[j] - lam[i]) * (u[j] - u[i]) / h;
@@ -427,7 +509,25 @@ __global__ void k_grad_f(const MeshDev M, const double* __restrict__ lam, double
   double g = 0.0;
   for (int a = M.adj_ptr[p]; a < M.adj_ptr[p + 1]; ++a) {
     const int e = M.adj_elem[a];
-    if (M.dim == 1) {
+    if (M.npe != M.dim + 1) {                               // P2: dL/df = M lam (consistent mass, symmetric)
+      const int loc = M.adj_loc[a];
+      if (M.dim == 1) {
+        const int n[3] = {M.elems[3 * e], M.elems[3 * e + 1], M.elems[3 * e + 2]};
+        double r = 0.0;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) r = fma(p2_line_m(loc, q), lam[n[q]], r);
+        g = fma((M.nodes[n[1]] - M.nodes[n[0]]) / 30.0, r, g);
+      } else {
+        int n[6];
+        const P2Tri T = p2_tri_of(M, e, n);
+        if (!T.keep) continue;
+        double mr[6], r = 0.0;
+        p2_tri_m_row(loc, mr);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) r = fma(mr[q], lam[n[q]], r);
+        g = fma(T.area * (1.0 / 180.0), r, g);
+      }
+    } else if (M.dim == 1) {
       const int i = M.elems[2 * e], j = M.elems[2 * e + 1];
       g = fma((M.nodes[j] - M.nodes[i]) * 0.5, lam[p], g);
     } else {
@@ -499,9 +599,16 @@ extern "C" int dfe_assemble(const dfe_mesh* m, const double* kappa, int kappa_mo
     const bool row_grid = getenv("DFE_ASSEMBLE_ROWS") != nullptr;     // row-owner structured kernel
     const bool k16 = (reinterpret_cast<uintptr_t>(kappa) & 15) == 0;         // per-element kappa is read as pairs
     if (m->topo_nx > 0 && !no_grid && !row_grid && k16) {
-      cudaFuncSetAttribute(k_assemble_tile, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      k_assemble_tile<<<dim3(blocks(m->topo_nx + 1, AN_C), blocks(m->topo_ny + 1, AN_R)), AQ_T, 0, static_cast<cudaStream_t>(stream)>>>(
-          m->dev, m->topo_nx, m->topo_ny, kappa, kappa_mode == DFE_KAPPA_PER_ELEMENT, f, vals_full, F);
+      const dim3 grid(blocks(m->topo_nx + 1, AN_C), blocks(m->topo_ny + 1, AN_R));
+      const int pe = kappa_mode == DFE_KAPPA_PER_ELEMENT;
+      cudaStream_t st = static_cast<cudaStream_t>(stream);
+      if (m->topo_geo_mid) {   // geometry range verified at handle creation: only kappa and the load sum are checked per call
+        cudaFuncSetAttribute(k_assemble_tile<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        k_assemble_tile<true><<<grid, AQ_T, 0, st>>>(m->dev, m->topo_nx, m->topo_ny, kappa, pe, f, vals_full, F);
+      } else {
+        cudaFuncSetAttribute(k_assemble_tile<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        k_assemble_tile<false><<<grid, AQ_T, 0, st>>>(m->dev, m->topo_nx, m->topo_ny, kappa, pe, f, vals_full, F);
+      }
     } else if (m->topo_nx > 0 && !no_grid)
       k_assemble_grid<<<blocks(m->dev.n_nodes, AG_T), AG_T, 0, static_cast<cudaStream_t>(stream)>>>(
           m->dev, m->topo_nx, m->topo_ny, kappa, kappa_mode == DFE_KAPPA_PER_ELEMENT, f, vals_full, F);

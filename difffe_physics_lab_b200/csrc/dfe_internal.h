@@ -82,6 +82,10 @@ struct dfe_mesh {
   int grid_nx = 0, grid_ny = 0;
   // element pattern of FEMesh.rectangle(topo_nx, topo_ny) alone (any Dirichlet set): enables the structured assembly kernel
   int topo_nx = 0, topo_ny = 0;
+  // rectangle() pattern only: every coordinate difference of every triangle is 0 or in [2^-120, 2^120] and every area in
+  // [2^-250, 2^250] — the geometric part of an element-matrix numerator then is 0 or in [2^-293, 2^241], and the structured
+  // assembly kernel checks only kappa and the load sum per call before it uses division-free quotients (dfe_exact.cuh)
+  bool topo_geo_mid = false;
   // ---- 1-D chain description
   bool chain = false;
   bool bc_left = false, bc_right = false, lift_left_first = true;

@@ -94,6 +94,12 @@ extern "C" int dfe_mesh_free_nodes_host(const dfe_mesh* m, const int64_t** free_
 extern "C" int dfe_mesh_create(int dim, int64_t n_nodes, int64_t n_el, const double* nodes,
                                const int64_t* elems, int64_t n_dir, const int64_t* dir_idx,
                                const double* dir_val, int device, dfe_mesh** out) {
+  return dfe_mesh_create_p(dim, dim + 1, n_nodes, n_el, nodes, elems, n_dir, dir_idx, dir_val, device, out);
+}
+
+extern "C" int dfe_mesh_create_p(int dim, int nodes_per_element, int64_t n_nodes, int64_t n_el, const double* nodes,
+                                 const int64_t* elems, int64_t n_dir, const int64_t* dir_idx,
+                                 const double* dir_val, int device, dfe_mesh** out) {
   DFE_REQUIRE(out, "dfe_mesh_create: out is null");
   *out = nullptr;
   if (dim != 1 && dim != 2) {
@@ -104,7 +110,10 @@ extern "C" int dfe_mesh_create(int dim, int64_t n_nodes, int64_t n_el, const dou
   DFE_REQUIRE(n_nodes >= 1 && n_el >= 0 && n_dir >= 0, "dfe_mesh_create: negative size");
   DFE_REQUIRE(nodes && (elems || n_el == 0) && ((dir_idx && dir_val) || n_dir == 0),
               "dfe_mesh_create: null array");
-  const int npe = dim + 1;
+  const int npe = nodes_per_element;
+  DFE_REQUIRE(npe == dim + 1 || npe == (dim + 1) * (dim + 2) / 2,
+              "dfe_mesh_create: %d nodes per element in %dD (P1 elements have %d, P2 elements %d)", npe, dim, dim + 1,
+              (dim + 1) * (dim + 2) / 2);
   const int64_t lim = std::numeric_limits<int32_t>::max() / 4;
   DFE_REQUIRE(n_nodes < lim && n_el * npe * npe < lim, "dfe_mesh_create: mesh too large for int32 indices");
   for (int64_t i = 0; i < n_el * npe; ++i)
@@ -236,7 +245,7 @@ extern "C" int dfe_mesh_create(int dim, int64_t n_nodes, int64_t n_el, const dou
   }
 
   // ---- 1-D chain detection (fused path): elements (e,e+1), h>0, Dirichlet ⊆ {0, n-1}, >=1 of them
-  bool chain = (dim == 1 && ne >= 1 && n == ne + 1 && nd >= 1 && nd <= 2 && nfree >= 1);
+  bool chain = (dim == 1 && npe == 2 && ne >= 1 && n == ne + 1 && nd >= 1 && nd <= 2 && nfree >= 1);
   if (chain)
     for (int e = 0; e < ne && chain; ++e)
       chain = h_elems[2 * e] == e && h_elems[2 * e + 1] == e + 1 && nodes[e + 1] > nodes[e] &&
@@ -254,7 +263,7 @@ extern "C" int dfe_mesh_create(int dim, int64_t n_nodes, int64_t n_el, const dou
 
   // ---- rectangle() topology (mesh.py:79-121): node id = row*(gx+1)+col, quad (r,c) -> [a,b,d], [b,c,d] with
   // a = r(gx+1)+c, b = a+1, c = a+gx+2, d = a+gx+1, and exactly the boundary nodes Dirichlet
-  if (dim == 2 && ne >= 2 && h_elems[0] == 0 && h_elems[1] == 1 && h_elems[2] >= 2) {
+  if (dim == 2 && npe == 3 && ne >= 2 && h_elems[0] == 0 && h_elems[1] == 1 && h_elems[2] >= 2) {
     const long long gx = h_elems[2] - 1;
     const long long gy = (n % (gx + 1) == 0) ? n / (gx + 1) - 1 : 0;
     bool ok = gx >= 2 && gy >= 2 && static_cast<long long>(ne) == 2 * gx * gy;
@@ -266,6 +275,28 @@ extern "C" int dfe_mesh_create(int dim, int64_t n_nodes, int64_t n_el, const dou
     if (ok) {
       m->topo_nx = static_cast<int>(gx);
       m->topo_ny = static_cast<int>(gy);
+      // range of the geometry (see dfe_mesh::topo_geo_mid); margins are wide enough for any host rounding mode / contraction
+      auto mid = [](double v, int lo, int hi) {
+        if (v == 0.0) return true;
+        int e;
+        std::frexp(v, &e);
+        return std::isfinite(v) && e > lo && e < hi;
+      };
+      bool geo = true;
+      for (long long q = 0; geo && q < gx * gy; ++q) {
+        const long long a = (q / gx) * (gx + 1) + q % gx;
+        const long long tri[2][3] = {{a, a + 1, a + gx + 1}, {a + 1, a + gx + 2, a + gx + 1}};
+        for (int t = 0; t < 2 && geo; ++t) {
+          const double* P0 = nodes + 2 * tri[t][0];
+          const double* P1 = nodes + 2 * tri[t][1];
+          const double* P2 = nodes + 2 * tri[t][2];
+          const double d[6] = {P1[0] - P0[0], P2[0] - P1[0], P0[0] - P2[0], P1[1] - P0[1], P2[1] - P1[1], P0[1] - P2[1]};
+          for (int i = 0; i < 6; ++i) geo = geo && mid(d[i], -120, 120);
+          const double area = 0.5 * std::fabs(d[0] * (-d[5]) - (-d[2]) * d[3]);
+          geo = geo && area != 0.0 && mid(area, -250, 250);
+        }
+      }
+      m->topo_geo_mid = geo;
     }
     ok = ok && nd == 2 * (gx + gy);
     for (long long p = 0; ok && p < n; ++p) {

@@ -1,7 +1,7 @@
 """``FEMesh`` — the input type of the hot path (mirror of reference ``diffhe/mesh.py``).
 
 Same public surface as the reference (``diffhe/mesh.py:14-143``): a mutable dataclass with
-``nodes`` (n_nodes, dim) float64, ``elements`` (n_el, dim+1) int64 and the insertion-ordered
+``nodes`` (n_nodes, dim) float64, ``elements`` (n_el, dim+1) int64 (``to_p2()``: 3 / 6 columns) and the insertion-ordered
 ``dirichlet_nodes`` dict, the ``line`` / ``rectangle`` factories, ``free_nodes()``, ``h()`` and the
 same ``repr``.  The tensors the factories produce are bit-identical to the reference's
 (tests/test_host_api.py checks them against golden copies), but ``rectangle`` is vectorised:
@@ -33,13 +33,13 @@ class NativeMesh:
         if n.ndim != 2 or e.ndim != 2:
             raise ValueError("FEMesh.nodes must be (n_nodes, dim) and FEMesh.elements (n_el, dim+1)")
         dim = n.shape[1]
-        if dim in (1, 2) and e.shape[1] != dim + 1:
-            raise ValueError(f"P1 elements in {dim}D have {dim + 1} nodes, got {e.shape[1]}")
+        if dim in (1, 2) and e.shape[1] not in (dim + 1, (dim + 1) * (dim + 2) // 2):
+            raise ValueError(f"elements in {dim}D have {dim + 1} (P1) or {(dim + 1) * (dim + 2) // 2} (P2) nodes, got {e.shape[1]}")
         di = np.fromiter(bc.keys(), dtype=np.int64, count=len(bc))
         dv = np.fromiter((float(v) for v in bc.values()), dtype=np.float64, count=len(bc))
         h = C.c_void_p()
-        _native.check(L.dfe_mesh_create(dim, n.shape[0], e.shape[0], n.ctypes.data, e.ctypes.data, len(bc),
-                                        di.ctypes.data, dv.ctypes.data, device, C.byref(h)))
+        _native.check(L.dfe_mesh_create_p(dim, e.shape[1], n.shape[0], e.shape[0], n.ctypes.data, e.ctypes.data, len(bc),
+                                          di.ctypes.data, dv.ctypes.data, device, C.byref(h)))
         self._h = h
         self._L = L
         info = _native.MeshInfo()
@@ -110,6 +110,11 @@ class FEMesh:
     def dim(self) -> int:
         return self.nodes.shape[1]
 
+    @property
+    def order(self) -> int:
+        """Polynomial degree of the elements: 1 (the reference's P1) or 2 (``to_p2``)."""
+        return 1 if self.elements.shape[1] == self.dim + 1 else 2
+
     # -------------------------------------------------------------- factories
     @classmethod
     def line(cls, n_elements: int = 10, x_left: float = 0.0, x_right: float = 1.0,
@@ -147,6 +152,37 @@ class FEMesh:
                     | np.isclose(y, y_range[0]) | np.isclose(y, y_range[1]))
         bc = dict.fromkeys(np.flatnonzero(boundary).tolist(), bc_value)
         return cls(nodes=torch.from_numpy(coords), elements=torch.from_numpy(tris), dirichlet_nodes=bc)
+
+    def to_p2(self) -> "FEMesh":
+        """The same mesh with quadratic (P2) elements — an item of the reference's roadmap (README.md:139-143), absent
+        from its code.  The vertices keep their ids; one node per edge (1-D: per element) is appended at the midpoint:
+        1-D elements become ``[left, right, mid]``, triangles ``[v0, v1, v2, m01, m12, m20]``.  A midpoint is a Dirichlet
+        node when its edge lies on the boundary (belongs to one triangle; in 1-D never) and both end points are Dirichlet
+        nodes; its value is the mean of theirs.  The solver then assembles the P2 stiffness matrix and the consistent
+        load ``F = M f`` (``f`` given at all P2 nodes)."""
+        if self.order != 1:
+            raise ValueError("to_p2() expects a P1 mesh")
+        x = self.nodes.detach().cpu().numpy()
+        el = self.elements.detach().cpu().numpy().astype(np.int64)
+        n = x.shape[0]
+        bc = dict(self.dirichlet_nodes)
+        if self.dim == 1:
+            mids = 0.5 * (x[el[:, 0]] + x[el[:, 1]])
+            new_el = np.concatenate((el, n + np.arange(el.shape[0], dtype=np.int64)[:, None]), axis=1)
+        else:
+            pairs = np.stack((el[:, [0, 1]], el[:, [1, 2]], el[:, [2, 0]]), axis=1).reshape(-1, 2)   # (3 n_el, 2)
+            key = np.sort(pairs, axis=1)
+            uniq, inv, cnt = np.unique(key, axis=0, return_inverse=True, return_counts=True)
+            inv = inv.reshape(-1)
+            mids = 0.5 * (x[uniq[:, 0]] + x[uniq[:, 1]])
+            new_el = np.concatenate((el, n + inv.reshape(-1, 3)), axis=1)
+            if bc:
+                isd = np.zeros(n, dtype=bool)
+                isd[np.fromiter(bc.keys(), dtype=np.int64, count=len(bc))] = True
+                for k in np.flatnonzero((cnt == 1) & isd[uniq[:, 0]] & isd[uniq[:, 1]]).tolist():
+                    bc[n + k] = 0.5 * (float(bc[int(uniq[k, 0])]) + float(bc[int(uniq[k, 1])]))
+        nodes = torch.from_numpy(np.concatenate((x, mids), axis=0))
+        return FEMesh(nodes=nodes, elements=torch.from_numpy(new_el), dirichlet_nodes=bc)
 
     # ------------------------------------------------------------ convenience
     def free_nodes(self) -> List[int]:

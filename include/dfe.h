@@ -84,6 +84,14 @@ int dfe_device_count(void);
 int dfe_mesh_create(int dim, int64_t n_nodes, int64_t n_el, const double* nodes_host,
                     const int64_t* elems_host, int64_t n_dir, const int64_t* dir_idx_host,
                     const double* dir_val_host, int device, dfe_mesh** out);
+/* Same, with an explicit number of nodes per element: dim + 1 (P1, what dfe_mesh_create passes) or (dim + 1)(dim + 2) / 2
+ * (P2: 1-D [left, right, mid], 2-D [v0, v1, v2, m01, m12, m20]; geometry is read from the vertices).  P2 elements are an
+ * item of the reference's roadmap (reference README.md:139-143), not of its code: there is no upstream arithmetic to match,
+ * the load is F = M f with the consistent mass matrix, and the mesh takes the general CSR + PCG route only (the fused 1-D,
+ * banded, shared-memory-batch and multigrid routes report "unsupported"). */
+int dfe_mesh_create_p(int dim, int nodes_per_element, int64_t n_nodes, int64_t n_el, const double* nodes_host,
+                      const int64_t* elems_host, int64_t n_dir, const int64_t* dir_idx_host,
+                      const double* dir_val_host, int device, dfe_mesh** out);
 void dfe_mesh_destroy(dfe_mesh* m);
 int dfe_mesh_get_info(const dfe_mesh* m, dfe_mesh_info* info);
 /* Host copies of the patterns (int64, owned by the handle).  which = 0: K (n_nodes rows),

@@ -343,13 +343,20 @@ def test_assembly_bit_exact_large_per_element_kappa():
     assert np.array_equal(np.sort(vals), np.sort(ovals))
 
 
-@pytest.mark.parametrize("nx,ny,scalar", [(300, 70, False), (31, 7, True), (32, 8, False), (1, 1, False), (95, 130, True)])
-def test_assembly_three_kernels_same_bits(monkeypatch, nx, ny, scalar):
+ASM_ENVS = ("DFE_ASSEMBLE_ROWS", "DFE_ASSEMBLE_GENERAL")
+
+
+@pytest.mark.parametrize("nx,ny,scalar,scale", [(300, 70, False, 1.0), (31, 7, True, 1.0), (32, 8, False, 1.0), (1, 1, False, 1.0),
+                                                (95, 130, True, 1.0), (64, 200, False, 1.0), (40, 33, False, 1e130),
+                                                (33, 21, False, 1e-9)])
+def test_assembly_three_kernels_same_bits(monkeypatch, nx, ny, scalar, scale):
     """The element-parallel tile kernel (default on rectangle() patterns), the row-owner structured kernel and the general
-    adjacency-list kernel produce the same K and F bit for bit — tile edges, mesh edges, partial Dirichlet sets, and (on the
-    small cases) the oracle's reference-order accumulation."""
+    adjacency-list kernel produce the same K and F bit for bit — tile edges, mesh edges, partial Dirichlet sets, coordinates
+    outside the range in which the handle lets the tile kernel skip its per-numerator range checks (scale 1e130), a mesh
+    whose triangles are all below the reference's degenerate-area threshold (scale 1e-9) — and, on the small cases, the
+    oracle's reference-order accumulation."""
     rng = np.random.default_rng(nx * 1000 + ny)
-    m = FEMesh.rectangle(nx, ny, x_range=(-0.7, 1.9), y_range=(0.1, 0.9), bc_value=0.25)
+    m = FEMesh.rectangle(nx, ny, x_range=(-0.7 * scale, 1.9 * scale), y_range=(0.1 * scale, 0.9 * scale), bc_value=0.25)
     if nx > 4:                                   # a partial Dirichlet set keeps the structured pattern
         for k in list(m.dirichlet_nodes)[::3]:
             del m.dirichlet_nodes[k]
@@ -357,8 +364,8 @@ def test_assembly_three_kernels_same_bits(monkeypatch, nx, ny, scalar):
     f = rng.uniform(-1, 1, m.n_nodes)
     out = {}
     for name, env in (("tile", None), ("rows", "DFE_ASSEMBLE_ROWS"), ("general", "DFE_ASSEMBLE_GENERAL")):
-        monkeypatch.delenv("DFE_ASSEMBLE_ROWS", raising=False)
-        monkeypatch.delenv("DFE_ASSEMBLE_GENERAL", raising=False)
+        for e in ASM_ENVS:
+            monkeypatch.delenv(e, raising=False)
         if env:
             monkeypatch.setenv(env, "1")
         _, vals, F, vf, Ff, dinv = abi_assemble(m, kap, f)
