@@ -862,11 +862,15 @@ __device__ __forceinline__ int row_to_smem(uint32_t dst16, const double* src, in
   return mis;
 }
 
+// SPI samples per CTA barrier: with one sample per barrier the loop ran at ~3800 cycles per sample and SM against ~500 issue
+// cycles of work (barrier + cp.async issue + shared-memory latency + the dependent fma chain, all exposed); SPI independent
+// samples share one barrier and interleave their chains.  The ring holds NG groups of SPI rows.
+template <int SPI, int NG>
 __global__ void __launch_bounds__(512) k_band_rhs_fwd3(const MeshDev M, long long B, int npad, int nnp,
                                                        const double* __restrict__ f, long long ldf,
                                                        const double* __restrict__ ellM, const unsigned* __restrict__ ellc,
                                                        const double* __restrict__ liftc, double* __restrict__ X) {
-  extern __shared__ __align__(16) double sg[];   // [NST_F][nnp + 2]
+  extern __shared__ __align__(16) double sg[];   // [NG][SPI][nnp + 2]
   const int tid = threadIdx.x, nt = blockDim.x;
   double w[SR][SW], lc[SR];
   int c[SR][SW];
@@ -884,34 +888,42 @@ __global__ void __launch_bounds__(512) k_band_rhs_fwd3(const MeshDev M, long lon
   const long long b0 = blockIdx.x, bs = gridDim.x;
   const int pitch = nnp + 2;                          // (room for the 16-byte phase of a row)
   const uint32_t sg32 = smem_u32(sg);
-  int st_in = 0;                                      // stage the next row goes to
-  long long b_in = b0;                                // ... and its sample
+  int st_in = 0;                                      // group slot the next rows go to
+  long long b_in = b0;                                // ... and the first sample of that group
   auto issue = [&]() {
-    if (b_in < B) row_to_smem(sg32 + 8u * (st_in * pitch), f + b_in * ldf, M.n_nodes, tid, nt);
+#pragma unroll
+    for (int s = 0; s < SPI; ++s)
+      if (b_in + s * bs < B) row_to_smem(sg32 + 8u * ((st_in * SPI + s) * pitch), f + (b_in + s * bs) * ldf, M.n_nodes, tid, nt);
     cp_async_commit();
-    b_in += bs;
-    st_in = st_in + 1 == NST_F ? 0 : st_in + 1;
+    b_in += SPI * bs;
+    st_in = st_in + 1 == NG ? 0 : st_in + 1;
   };
-  for (int i = 0; i < NST_F - 1; ++i) issue();
+  for (int i = 0; i < NG - 1; ++i) issue();
   int st = 0;
-  for (long long b = b0; b < B; b += bs) {
-    cp_async_wait<NST_F - 2>();
-    __syncthreads();               // every thread's part of this row has landed, and everybody is done with the previous one
+  for (long long b = b0; b < B; b += SPI * bs) {
+    cp_async_wait<NG - 2>();
+    __syncthreads();               // every thread's part of this group has landed, and everybody is done with the previous one
     issue();
-    const double* fb = sg + st * pitch + ((reinterpret_cast<uintptr_t>(f + b * ldf) >> 3) & 1);
-    double* xb = X + b * npad;
 #pragma unroll
     for (int k = 0; k < SR; ++k) {
       const int r = tid + k * nt;
-      double v[SW];
+      double a[SPI];
 #pragma unroll
-      for (int j = 0; j < SW; ++j) v[j] = fb[c[k][j]];
-      double a = -lc[k];
+      for (int s = 0; s < SPI; ++s) {
+        const long long bb = b + s * bs;
+        const double* fb = sg + (st * SPI + s) * pitch + ((reinterpret_cast<uintptr_t>(f + bb * ldf) >> 3) & 1);
+        double v[SW];
 #pragma unroll
-      for (int j = 0; j < SW; ++j) a = fma(w[k][j], v[j], a);
-      if (r < npad) xb[r] = a;
+        for (int j = 0; j < SW; ++j) v[j] = fb[c[k][j]];
+        a[s] = -lc[k];
+#pragma unroll
+        for (int j = 0; j < SW; ++j) a[s] = fma(w[k][j], v[j], a[s]);
+      }
+#pragma unroll
+      for (int s = 0; s < SPI; ++s)
+        if (r < npad && b + s * bs < B) X[(b + s * bs) * npad + r] = a[s];
     }
-    st = st + 1 == NST_F ? 0 : st + 1;
+    st = st + 1 == NG ? 0 : st + 1;
   }
   cp_async_wait<0>();
 }
@@ -920,13 +932,13 @@ __global__ void __launch_bounds__(512) k_band_rhs_fwd3(const MeshDev M, long lon
 // Both in one kernel cost 96 registers at 576 threads (one CTA per SM, 0.86 ms at config 5b); as two kernels each half keeps
 // the weights of ONE stencil in registers and two CTAs fit an SM, but the lambda rows are streamed twice (0.54 + 0.39 ms):
 // the fused form is the default, an adjoint without dL/df launches the GK half only.
-template <bool GF, bool GK>
+template <bool GF, bool GK, int SPI, int NG>
 __global__ void __launch_bounds__(SBT_MAX, (GF && GK) ? 1 : 2) k_band_grad3(const MeshDev M, long long B, int npad, int nnp,
                                                         const double* __restrict__ X, const double* __restrict__ ufull,
                                                         long long ldu, const double* __restrict__ ellK,
                                                         const double* __restrict__ ellMr, const unsigned* __restrict__ ellc,
                                                         double* __restrict__ gkpart, double* __restrict__ gf, long long ldgf) {
-  extern __shared__ __align__(16) double sg[];   // [NST_G][(nnp + 2) + npad]: u row (GK only), lambda row (free numbering)
+  extern __shared__ __align__(16) double sg[];   // [NG][SPI][(nnp + 2) + npad]: u row (GK only), lambda row (free numbering)
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
   const int uoff = GK ? nnp + 2 : 0;       // u row (with room for its 16-byte phase) | lambda row
   const int pitch = uoff + npad;
@@ -950,54 +962,69 @@ __global__ void __launch_bounds__(SBT_MAX, (GF && GK) ? 1 : 2) k_band_grad3(cons
   int st_in = 0;
   long long b_in = b0;
   auto issue = [&]() {
-    if (b_in < B) {
-      const uint32_t du = sg32 + 8u * (st_in * pitch);
-      if (GK) row_to_smem(du, ufull + b_in * ldu, M.n_nodes, tid, nt);
-      const double* sl = X + b_in * npad;      // 16-byte aligned rows (npad is a multiple of 32)
-      for (int q = tid; q < (npad >> 1); q += nt) cp_async16_u32(du + 8u * uoff + 16u * q, sl + 2 * q);
+#pragma unroll
+    for (int s = 0; s < SPI; ++s) {
+      const long long bb = b_in + s * bs;
+      if (bb < B) {
+        const uint32_t du = sg32 + 8u * ((st_in * SPI + s) * pitch);
+        if (GK) row_to_smem(du, ufull + bb * ldu, M.n_nodes, tid, nt);
+        const double* sl = X + bb * npad;      // 16-byte aligned rows (npad is a multiple of 32)
+        for (int q = tid; q < (npad >> 1); q += nt) cp_async16_u32(du + 8u * uoff + 16u * q, sl + 2 * q);
+      }
     }
     cp_async_commit();
-    b_in += bs;
-    st_in = st_in + 1 == NST_G ? 0 : st_in + 1;
+    b_in += SPI * bs;
+    st_in = st_in + 1 == NG ? 0 : st_in + 1;
   };
-  for (int i = 0; i < NST_G - 1; ++i) issue();
+  for (int i = 0; i < NG - 1; ++i) issue();
   int st = 0;
-  for (long long b = b0; b < B; b += bs) {
-    cp_async_wait<NST_G - 2>();
+  for (long long b = b0; b < B; b += SPI * bs) {
+    cp_async_wait<NG - 2>();
     __syncthreads();
     issue();
-    const double* ub = sg + st * pitch + (GK ? ((reinterpret_cast<uintptr_t>(ufull + b * ldu) >> 3) & 1) : 0);
-    const double* lb = sg + st * pitch + uoff;
-    double part = 0.0;
+    double part[SPI];
+#pragma unroll
+    for (int s = 0; s < SPI; ++s) part[s] = 0.0;
 #pragma unroll
     for (int k = 0; k < SR; ++k) {
       const int p = tid + k * nt;
-      if (GK) {
-        double uv[SW];
 #pragma unroll
-        for (int j = 0; j < SW; ++j) uv[j] = ub[c[k][j] & 0xffffu];
-        const double lam = rk[k] >= 0 ? lb[rk[k]] : 0.0;
-        double ku = 0.0;
+      for (int s = 0; s < SPI; ++s) {
+        const long long bb = b + s * bs;
+        const double* ub = sg + (st * SPI + s) * pitch + (GK ? ((reinterpret_cast<uintptr_t>(ufull + bb * ldu) >> 3) & 1) : 0);
+        const double* lb = sg + (st * SPI + s) * pitch + uoff;
+        if (GK) {
+          double uv[SW];
 #pragma unroll
-        for (int j = 0; j < SW; ++j) ku = fma(wk[k][j], uv[j], ku);
-        part = fma(lam, ku, part);
-      }
-      if (GF) {
-        double lv[SW];
+          for (int j = 0; j < SW; ++j) uv[j] = ub[c[k][j] & 0xffffu];
+          const double lam = rk[k] >= 0 ? lb[rk[k]] : 0.0;
+          double ku = 0.0;
 #pragma unroll
-        for (int j = 0; j < SW; ++j) lv[j] = lb[c[k][j] >> 16];
-        double ml = 0.0;
+          for (int j = 0; j < SW; ++j) ku = fma(wk[k][j], uv[j], ku);
+          part[s] = fma(lam, ku, part[s]);
+        }
+        if (GF) {
+          double lv[SW];
 #pragma unroll
-        for (int j = 0; j < SW; ++j) ml = fma(wm[k][j], lv[j], ml);
-        if (p < M.n_nodes) gf[b * ldgf + p] = ml;
+          for (int j = 0; j < SW; ++j) lv[j] = lb[c[k][j] >> 16];
+          double ml = 0.0;
+#pragma unroll
+          for (int j = 0; j < SW; ++j) ml = fma(wm[k][j], lv[j], ml);
+          if (p < M.n_nodes && bb < B) gf[bb * ldgf + p] = ml;
+        }
       }
     }
     if (GK) {
 #pragma unroll
-      for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
-      if (lane == 0) gkpart[b * nw + warp] = part;
+      for (int d = 16; d > 0; d >>= 1)
+#pragma unroll
+        for (int s = 0; s < SPI; ++s) part[s] += __shfl_xor_sync(0xffffffffu, part[s], d);
+      if (lane == 0)
+#pragma unroll
+        for (int s = 0; s < SPI; ++s)
+          if (b + s * bs < B) gkpart[(b + s * bs) * nw + warp] = part[s];
     }
-    st = st + 1 == NST_G ? 0 : st + 1;
+    st = st + 1 == NG ? 0 : st + 1;
   }
   cp_async_wait<0>();
 }
@@ -1013,6 +1040,17 @@ __global__ void k_band_gksum(long long B, int nw, const double* __restrict__ gkp
 bool band_stencil_fits(const dfe_mesh* m) {
   return m->dev.dim == 2 && m->info.max_row_nnz <= SW && m->dev.n_nodes <= SR * SBT_MAX && m->dev.n_nodes < 65536 &&
          band_npad(m) <= SR * 512 && static_cast<size_t>(NST_G) * (2 * m->dev.n_nodes + 34) * sizeof(double) <= 200 * 1024;
+}
+
+// samples per CTA barrier of the stencil-form kernels: the largest of 4 / 2 / 1 whose ring (3 groups for 4, 4 for 2, the
+// round-1 depth for 1) fits `row_bytes * rows <= 216 KB`; DFE_BAND_SPI overrides (A/B switch)
+int band_spi(size_t row_bytes) {
+  const char* e = getenv("DFE_BAND_SPI");   // read per call: the tests compare the variants bit for bit in one process
+  const int forced = e ? atoi(e) : 0;
+  const size_t cap = 216 * 1024;
+  int spi = 12 * row_bytes <= cap ? 4 : 8 * row_bytes <= cap ? 2 : 1;
+  if ((forced == 1 || forced == 2 || forced == 4) && forced <= spi) spi = forced;
+  return spi;
 }
 
 bool band_reg_fits(const dfe_mesh* m) {
@@ -1651,10 +1689,13 @@ extern "C" int dfe_band_factor(const dfe_mesh* m, const double* vals_full, void*
     cudaError_t e = cudaMemsetAsync(p.invd, 0, (np + 2 * np * BW) * sizeof(double), st);
     if (e == cudaSuccess) e = cudaMemsetAsync(p.Ab, 0, (np + 40) * (BW + 1) * sizeof(double), st);
     k_band_gather<<<nblk(m->dev.n_free, 128), 128, 0, st>>>(m->dev, vals_full, p.Ab);
+    // (running the Cholesky chain on a second stream under the load-vector kernel of dfe_band_fwd was measured: no gain —
+    // the one-CTA factorisation is latency-bound and slows down under a bandwidth-bound neighbour as much as it overlaps)
     static const bool unblocked = getenv("DFE_BAND_FACTOR_ROWS") != nullptr;   // A/B switch: the row-by-row kernel
     if (unblocked) k_band_factor<<<1, 256, 0, st>>>(m->dev.n_free, band_npad(m), p.Ab, p.invd, p.Lc, p.Lr, p.status);
     else k_band_factor_blk<<<1, 256, 0, st>>>(m->dev.n_free, band_npad(m), p.Ab, p.invd, p.Lc, p.Lr, p.status);
     k_band_blocks<<<static_cast<unsigned>(np / 32), 256, 0, st>>>(band_npad(m), p.invd, p.Lr, p.Ff, p.Bf);
+    if (e == cudaSuccess && status_dev) e = cudaMemcpyAsync(status_dev, p.status, sizeof(int), cudaMemcpyDeviceToDevice, st);
     k_band_geom<<<nblk(m->dev.n_el, 128), 128, 0, st>>>(m->dev, p.geom);
     {
       const int nt = m->dev.n_el > m->n_lift ? m->dev.n_el : m->n_lift;
@@ -1665,7 +1706,6 @@ extern "C" int dfe_band_factor(const dfe_mesh* m, const double* vals_full, void*
       }
     }
     if (e == cudaSuccess) e = cudaGetLastError();
-    if (e == cudaSuccess && status_dev) e = cudaMemcpyAsync(status_dev, p.status, sizeof(int), cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) {
       dfe::set_error("dfe_band_factor: %s", cudaGetErrorString(e));
       rc = DFE_ERR_CUDA;
@@ -1695,13 +1735,21 @@ extern "C" int dfe_band_fwd(const dfe_mesh* m, int64_t B, const double* f, int64
     static const bool reg_kernels = getenv("DFE_BAND_REG") != nullptr;   // A/B switch: no stencil-form kernels
     if (band_stencil_fits(m) && !old_kernels && !reg_kernels) {
       const int nt = ((np + SR - 1) / SR + 31) & ~31;
-      const size_t sm3 = static_cast<size_t>(NST_F) * (p.nnp + 2) * sizeof(double);
-      cudaFuncSetAttribute(k_band_rhs_fwd3, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm3));
-      int occ = 1;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_band_rhs_fwd3, nt, sm3);
-      long long rgrid = static_cast<long long>(occ > 0 ? occ : 1) * m->sm_count;   // persistent: one wave
-      if (rgrid > B) rgrid = B;
-      k_band_rhs_fwd3<<<static_cast<unsigned>(rgrid), nt, sm3, st>>>(m->dev, B, np, p.nnp, f, ldf, p.ellM, p.ellc, p.liftc, X);
+      const size_t row = static_cast<size_t>(p.nnp + 2) * sizeof(double);
+      auto launch_rhs = [&](auto kern, int rows) {
+        const size_t sm3 = rows * row;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm3));
+        int occ = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nt, sm3);
+        long long rgrid = static_cast<long long>(occ > 0 ? occ : 1) * m->sm_count;   // persistent: one wave
+        if (rgrid > B) rgrid = B;
+        kern<<<static_cast<unsigned>(rgrid), nt, sm3, st>>>(m->dev, B, np, p.nnp, f, ldf, p.ellM, p.ellc, p.liftc, X);
+      };
+      switch (band_spi(row)) {
+        case 4: launch_rhs(k_band_rhs_fwd3<4, 3>, 12); break;
+        case 2: launch_rhs(k_band_rhs_fwd3<2, 4>, 8); break;
+        default: launch_rhs(k_band_rhs_fwd3<1, NST_F>, NST_F); break;
+      }
     } else {
       const size_t rsm = (static_cast<size_t>(m->dev.n_nodes) + m->dev.n_el) * sizeof(double);
       cudaFuncSetAttribute(k_band_rhs_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rsm));
@@ -1771,11 +1819,20 @@ extern "C" int dfe_band_bwd(const dfe_mesh* m, int64_t B, const double* gbar, in
       // both halves in one kernel when dL/df is wanted (measured: 0.86 ms vs 0.54 + 0.39 ms as two kernels — the second
       // pass over the lambda rows costs more than the lower occupancy); DFE_BAND_GRAD_SPLIT=1 is the A/B switch
       static const bool split = getenv("DFE_BAND_GRAD_SPLIT") != nullptr;
+      const size_t row2 = static_cast<size_t>(p.nnp + 2 + np) * sizeof(double), row1 = static_cast<size_t>(np) * sizeof(double);
       if (gf && !split) {
-        launch_half(k_band_grad3<true, true>, static_cast<size_t>(NST_G) * (p.nnp + 2 + np) * sizeof(double), gf);
+        switch (band_spi(row2)) {
+          case 4: launch_half(k_band_grad3<true, true, 4, 3>, 12 * row2, gf); break;
+          case 2: launch_half(k_band_grad3<true, true, 2, 4>, 8 * row2, gf); break;
+          default: launch_half(k_band_grad3<true, true, 1, NST_G>, NST_G * row2, gf); break;
+        }
       } else {
-        launch_half(k_band_grad3<false, true>, static_cast<size_t>(NST_G) * (p.nnp + 2 + np) * sizeof(double), nullptr);
-        if (gf) launch_half(k_band_grad3<true, false>, static_cast<size_t>(NST_G) * np * sizeof(double), gf);
+        switch (band_spi(2 * row2)) {   // two CTAs per SM for this half
+          case 4: launch_half(k_band_grad3<false, true, 4, 3>, 12 * row2, nullptr); break;
+          case 2: launch_half(k_band_grad3<false, true, 2, 4>, 8 * row2, nullptr); break;
+          default: launch_half(k_band_grad3<false, true, 1, NST_G>, NST_G * row2, nullptr); break;
+        }
+        if (gf) launch_half(k_band_grad3<true, false, 1, NST_G>, NST_G * row1, gf);
       }
       k_band_gksum<<<nblk(B, 256), 256, 0, st>>>(B, nt / 32, gkpart, gkappa);
     } else if (band_reg_fits(m) && !old_kernels) {

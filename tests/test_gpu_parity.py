@@ -502,6 +502,23 @@ def test_2d_batched_small_systems_kernel():
             u_band, gk_band = u, float(k.grad)
         else:
             assert relerr(u, u_band) <= 1e-11 and abs(float(k.grad) - gk_band) <= 1e-10 * abs(gk_band)
+    # (a') the stencil-form load / gradient kernels with 1, 2 and 4 samples per CTA barrier: same bits
+    import os
+    outs = []
+    for spi in ("1", "2", "4"):
+        os.environ["DFE_BAND_SPI"] = spi
+        try:
+            k = torch.tensor(0.8, dtype=torch.float64, device="cuda", requires_grad=True)
+            ft = torch.tensor(f, device="cuda", requires_grad=True)
+            s = DifferentiableFESolver(m, kappa=k)
+            ut = s(ft)
+            (ut * torch.tensor(gbar, device="cuda")).sum().backward()
+            outs.append((ut.detach().clone(), ft.grad.clone(), k.grad.clone()))
+        finally:
+            del os.environ["DFE_BAND_SPI"]
+    for o in outs[1:]:
+        assert all(torch.equal(a, b) for a, b in zip(outs[0], o))
+    assert torch.equal(outs[2][0], torch.tensor(u_band, device="cuda"))
     # (b) batched route == per-sample route (same arithmetic for F, lifting, SpMV; different reduction trees)
     B = 6
     k = torch.tensor(1.7, dtype=torch.float64, device="cuda", requires_grad=True)
