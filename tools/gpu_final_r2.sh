@@ -27,4 +27,7 @@ timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k re
 S5A="python bench.py --workload c5a --steps 2 --warmup 3 --no-cpu"
 timeout -s KILL 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_c5a.csv $S5A > gpurun_out/ncu_l5a.log 2>&1; echo "launches c5a rc=$?"
 timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k k1d_pipe -s 8 -c 2 -f -o gpurun_out/prof_c5a_r2 $S5A > gpurun_out/ncu_c5a_r2.log 2>&1; echo "full c5a rc=$?"
+SE="python bench.py --workload c2e --steps 1 --warmup 1 --no-e2e --no-cpu"
+timeout -s KILL 600 ncu --set full --clock-control none -k regex:k1d_pe -s 4 -c 4 -f -o gpurun_out/prof_c2e_r2 $SE > gpurun_out/ncu_c2e_r2.log 2>&1; echo "full c2e rc=$?"
+timeout -s KILL 300 python examples/convergence_2d.py > gpurun_out/convergence_2d.log 2>&1; echo "convergence example rc=$?"
 for f in bench bench_ref; do echo "--- $f"; head -c 1500 gpurun_out/$f.json; echo; done

@@ -62,7 +62,8 @@ SETS = {"r01": (("config 2 (1-D pipelined kernels)", "prof_pipe_final.ncu-rep", 
         "r02": (("config 2 (1-D pipelined kernels; default bench line)", "prof_pipe_r2.ncu-rep", "k1d_pipe<", "launches_c2.csv", "c2"),
                 ("config 5a (sweep: forward + fused misfit adjoint)", "prof_c5a_r2.ncu-rep", "k1d_pipe<", "launches_c5a.csv", "c5a"),
                 ("config 4 (multigrid-preconditioned CG, structured assembly)", "prof_c4_r2.ncu-rep", "k_", "launches_c4.csv", "c4"),
-                ("config 5b (banded batch: block TRSM on the FP64 tensor cores, stencil load / gradient kernels)", "prof_c5b_r2.ncu-rep", "k_band", "launches_c5b.csv", "c5b"))}
+                ("config 5b (banded batch: block TRSM on the FP64 tensor cores, stencil load / gradient kernels)", "prof_c5b_r2.ncu-rep", "k_band", "launches_c5b.csv", "c5b"),
+                ("config 2 variant c2e (per-sample per-element kappa, two-pass kernels)", "prof_c2e_r2.ncu-rep", "k1d_pe", "launches_c2e.csv", "c2e"))}
 for name, rep, pat, src, key in SETS.get(TAG, SETS["r02"]):
     summary.append(f"## {name}\n")
     if (G / src).exists():
