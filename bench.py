@@ -331,6 +331,50 @@ def parity_block(mesh, rows, f, kappa, gbar, u, gf, gk, shared_kappa, per_elem=F
             "note": "rows of the last timed step, chosen from the first, a middle and the last pipeline iteration"}
 
 
+def parity_block_2d(mesh, nm, kappa, f, u, gk):
+    """Proof that the timed 2-D solve did the work, without a CPU solve of the 1e6-unknown system: the TRUE relative residual
+    of the assembled system (dfe_assemble values on the handle's CSR pattern, sparse mat-vec in torch on the device) and the
+    Euler identity of the gradient (K is linear in kappa and the boundary values are zero, so for J = sum(u):
+    sum_e kappa_e dJ/dkappa_e = -J).  The oracle comparison at this size is tests/test_gpu_mg.py."""
+    import torch
+    import ctypes as C
+    from difffe_physics_lab_b200 import _native
+    L = _native.lib()
+    dev = u.device
+    I = nm.info
+    kf = kappa.detach().reshape(-1).contiguous()
+    mode = _native.KAPPA_SCALAR if kf.numel() == 1 else _native.KAPPA_PER_ELEMENT
+    vals = torch.empty(I.nnz_full, dtype=torch.float64, device=dev)
+    F = torch.empty(I.n_nodes, dtype=torch.float64, device=dev)
+    _native.check(L.dfe_assemble(nm.handle, kf.data_ptr(), mode, f.data_ptr(), vals.data_ptr(), F.data_ptr(),
+                                 torch.cuda.current_stream().cuda_stream))
+    rp, col = nm.csr(0)
+    K = torch.sparse_csr_tensor(torch.from_numpy(rp).to(dev), torch.from_numpy(col).to(dev), vals, size=(I.n_nodes, I.n_nodes))
+    free = torch.from_numpy(nm.free_nodes()).to(dev)
+    r = (F - K @ u.detach())[free]
+    res = float(r.norm() / F[free].norm())
+    J = float(u.detach().sum())
+    euler = abs(float((kappa.detach() * gk).sum()) + J) / abs(J)
+    return {"true_residual_rel": res, "euler_identity_rel": euler,
+            "what": "||F - K u||_free / ||F||_free with K, F from dfe_assemble (bit-exact with the reference's dense arrays) and the "
+                    "timed u; |sum_e kappa_e dJ/dkappa_e + J| / |J| for J = sum(u) with the timed gradient"}
+
+
+def parity_block_small2d(mesh, rows, f, kappa, gbar, u, gf):
+    """Rows of the timed config-5b output against the oracle (sparse LU + refinement): max relative error of u and dL/df."""
+    from oracle import oracle as O
+    nodes, el, bc = mesh.nodes.numpy(), mesh.elements.numpy(), mesh.dirichlet_nodes
+    worst_u = worst_gf = 0.0
+    for b in rows:
+        fb, gb = f[b].detach().cpu().numpy(), gbar[b].cpu().numpy()
+        uo = O.forward(nodes, el, bc, float(kappa), fb)
+        _, gfo, _ = O.adjoint_and_grads(nodes, el, bc, float(kappa), uo, gb)
+        worst_u = max(worst_u, float(np.abs(u[b].detach().cpu().numpy() - uo).max() / np.abs(uo).max()))
+        worst_gf = max(worst_gf, float(np.abs(gf[b].cpu().numpy() - gfo).max() / np.abs(gfo).max()))
+    return {"max_rel": max(worst_u, worst_gf), "u_max_rel": worst_u, "gf_max_rel": worst_gf, "rows": [int(b) for b in rows],
+            "tolerance": 1e-9, "oracle": "oracle/oracle.py (sparse LU + refinement of the same float64 system)"}
+
+
 def time_sweep(args, rank, world, dev, n_el, B_total, steps, warmup):
     """BASELINE config 5a as SURVEY §8(d) defines it: 65 536 samples on line(16384), shared kappa, sharded over the
     ranks (strong scaling); per step  forward -> fused misfit adjoint (gbar = 2 (u - u_data) / n formed in the kernel,
@@ -709,6 +753,7 @@ def run_b200_2d(args, w, rank, local_rank, world, dev):
         u.sum().backward()
         its["fwd"] = s.last_pcg[0][0]
         its["adj"] = s._opts["last_pcg_adjoint"][0][0]
+        its["u"], its["gk"] = u, kr.grad
         return kr.grad
 
     def barrier():
@@ -736,6 +781,14 @@ def run_b200_2d(args, w, rank, local_rank, world, dev):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t[0])
     ms_step = ms_total / args.steps
+    parity = None
+    if rank == 0 and not args.no_parity:
+        try:
+            parity = parity_block_2d(mesh, nm, kappa, f, its.pop("u"), its.pop("gk"))
+        except Exception as exc:
+            parity = {"true_residual_rel": None, "error": f"{type(exc).__name__}: {exc}"}
+    its.pop("u", None)
+    its.pop("gk", None)
     peak, peak_src = measured_peak()
     N, nnz = I.n_free, I.nnz_free
     bytes_iter = 12 * nnz + 104 * N + 4 * (N + 1)              # SURVEY §8d accounting convention
@@ -819,7 +872,8 @@ def run_b200_2d(args, w, rank, local_rank, world, dev):
                 "config": {"workload": w["desc"], "nx": nx, "n_free": int(N), "nnz_free": int(nnz), "pcg_tol": 1e-13,
                            "l2": "config 4 working set ~0.2 GB > L2; config 3 (3 MB) is L2/latency-bound by construction",
                            "mesh_setup_s": t_setup, "parallelism": f"replicas only x{world} (a single mesh stays on one GPU)"},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": kt.launches, "clocks": clocks}
+                "roofline": roofline, "parity": parity, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": kt.launches,
+                "clocks": clocks}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -854,6 +908,7 @@ def run_b200_small2d(args, w, rank, local_rank, world, dev):
         u.backward(gbar)
         its["fwd"] = s.last_pcg[0][0]
         its["adj"] = s._opts["last_pcg_adjoint"][0][0]
+        its["u"] = u
         if world > 1:
             red[0] = kr.grad
             dist.all_reduce(red)
@@ -885,6 +940,14 @@ def run_b200_small2d(args, w, rank, local_rank, world, dev):
         ms_total = float(t[0])
     ms_step = ms_total / args.steps
     value = B * world * args.steps / (ms_total * 1e-3)
+    parity = None
+    u_last = its.pop("u", None)
+    if rank == 0 and not args.no_parity and u_last is not None:
+        try:
+            parity = parity_block_small2d(mesh, sorted({0, B // 2 + 1, B - 1}), f, kappa, gbar, u_last, f.grad)
+        except Exception as exc:
+            parity = {"max_rel": None, "error": f"{type(exc).__name__}: {exc}"}
+    del u_last
     peak, peak_src = measured_peak()
     kern = {k: {"calls": c, "ms_per_launch": m / c} for k, (c, m) in ksum.items()}
     roofline = None
@@ -948,7 +1011,8 @@ def run_b200_small2d(args, w, rank, local_rank, world, dev):
                 "config": {"workload": w["desc"], "nx": nx, "n_free": int(I.n_free), "batch_per_gpu": B, "global_batch": B * world,
                            "kappa": "shared", "pcg_tol": 1e-13, "l2": "inputs 0.57 GB/array larger than L2; no flush",
                            "parallelism": f"batch-sharded x{world}, mesh replicated" + (", NCCL allreduce of [dL/dkappa, loss]" if world > 1 else "")},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": kt.launches, "clocks": clocks}
+                "roofline": roofline, "parity": parity, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": kt.launches,
+                "clocks": clocks}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

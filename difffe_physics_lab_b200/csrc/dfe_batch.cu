@@ -1233,7 +1233,9 @@ __global__ void __launch_bounds__(32 * MMA_W, 2) k_band_solve_mma(int npad, long
                                                                   const double* __restrict__ Bf, double* __restrict__ X,
                                                                   const int* __restrict__ fnode, int nfree,
                                                                   const double* __restrict__ gsrc, long long ldg,
-                                                                  double* __restrict__ uout, long long ldu) {
+                                                                  double* __restrict__ uout, long long ldu,
+                                                                  const int* __restrict__ dir_idx,
+                                                                  const double* __restrict__ dir_val, int n_dir) {
   __shared__ __align__(16) double stg[2][FRAGD];
   __shared__ uint64_t bar[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1372,6 +1374,15 @@ __global__ void __launch_bounds__(32 * MMA_W, 2) k_band_solve_mma(int npad, long
           *reinterpret_cast<double2*>(row[mt] + 32 * k + 8 * nt) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
         }
       }
+  }
+  if (SOUT && n_dir > 0) {   // u[d] = g on the Dirichlet nodes of the warp's samples (solver.py:177-179): scattered 8-byte
+    // stores that hide behind the other warps' MMAs here; as a kernel of their own they cost 68 us at config 5b
+    for (int d = lane; d < n_dir; d += 32) {
+      const int node = dir_idx[d];
+      const double gv = dir_val[d];
+      for (int sidx = 0; sidx < MMA_S; ++sidx)
+        if (s0 + sidx < B) uout[(s0 + sidx) * ldu + node] = gv;
+    }
   }
 }
 
@@ -1654,20 +1665,12 @@ inline unsigned nblk(long long n, int t) { return static_cast<unsigned>((n + t -
 void band_solve(int np, long long B, const BandPtrs& p, double* X, cudaStream_t st) {
   static const bool scalar = getenv("DFE_BAND_SCALAR") != nullptr;
   if (scalar) k_band_solve<<<nblk((B + BS - 1) / BS, 4), 128, 0, st>>>(np, B, p.invd, p.Lc, p.Lr, X);
-  else k_band_solve_mma<false, false><<<nblk(B, MMA_W * MMA_S), 32 * MMA_W, 0, st>>>(np, B, p.Ff, p.Bf, X, nullptr, 0, nullptr, 0, nullptr, 0);
+  else k_band_solve_mma<false, false><<<nblk(B, MMA_W * MMA_S), 32 * MMA_W, 0, st>>>(np, B, p.Ff, p.Bf, X, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, nullptr, 0);
 }
 // the fused variants exist for the tensor-core kernel only
 bool band_fused_io() {
   static const bool off = getenv("DFE_BAND_SCALAR") != nullptr || getenv("DFE_BAND_NOFUSE") != nullptr;
   return !off;
-}
-// u[d] = g on the Dirichlet nodes of every sample (solver.py:177-179) when the solve scatters the free rows itself
-__global__ void k_band_dirichlet(const MeshDev M, long long B, double* __restrict__ u, long long ldu) {
-  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (idx >= B * M.n_dir) return;
-  const long long b = idx / M.n_dir;
-  const int d = static_cast<int>(idx - b * M.n_dir);
-  u[b * ldu + M.dir_idx[d]] = M.dir_val[d];
 }
 }  // namespace
 
@@ -1758,9 +1761,9 @@ extern "C" int dfe_band_fwd(const dfe_mesh* m, int64_t B, const double* f, int64
       k_band_rhs_fwd<<<static_cast<unsigned>(rgrid), BT, rsm, st>>>(m->dev, B, np, f, ldf, vals_full, p.geom, X);
     }
     if (band_fused_io()) {
-      if (m->dev.n_dir > 0) k_band_dirichlet<<<nblk(B * m->dev.n_dir, 256), 256, 0, st>>>(m->dev, B, u, ldu);
       k_band_solve_mma<false, true><<<nblk(B, MMA_W * MMA_S), 32 * MMA_W, 0, st>>>(np, B, p.Ff, p.Bf, X, m->dev.free_nodes,
-                                                                                   m->dev.n_free, nullptr, 0, u, ldu);
+                                                                                   m->dev.n_free, nullptr, 0, u, ldu,
+                                                                                   m->dev.dir_idx, m->dev.dir_val, m->dev.n_dir);
     } else {
       band_solve(np, B, p, X, st);
       k_band_scatter<<<nblk(B * (m->dev.n_free + m->dev.n_dir), 256), 256, 0, st>>>(m->dev, B, np, X, u, ldu);
@@ -1797,7 +1800,7 @@ extern "C" int dfe_band_bwd(const dfe_mesh* m, int64_t B, const double* gbar, in
     double* X = static_cast<double*>(ws);
     if (band_fused_io()) {
       k_band_solve_mma<true, false><<<nblk(B, MMA_W * MMA_S), 32 * MMA_W, 0, st>>>(np, B, p.Ff, p.Bf, X, m->dev.free_nodes,
-                                                                                   m->dev.n_free, gbar, ldg, nullptr, 0);
+                                                                                   m->dev.n_free, gbar, ldg, nullptr, 0, nullptr, nullptr, 0);
     } else {
       k_band_rhs_bwd<<<nblk(B * np, 256), 256, 0, st>>>(m->dev, B, np, gbar, ldg, X);
       band_solve(np, B, p, X, st);
