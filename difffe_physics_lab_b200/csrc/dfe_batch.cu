@@ -1140,28 +1140,29 @@ __global__ void __launch_bounds__(128) k_band_solve(int npad, long long B, const
 // ---------------------------------------------------------------------------------------------------------------------
 // The same two triangular solves as a BLOCK-banded TRSM on the FP64 tensor cores (DMMA m8n8k4).
 //
-// With 32 x 32 blocks the band of L is block-bidiagonal: L y = b reads  y_k = H_k b_k + G_k y_{k-1}  with
-// H_k = L_kk^{-1} and G_k = -H_k L_{k,k-1}, and L^T x = y reads  x_k = H_k^T y_k + G'_k x_{k+1}  with
-// G'_k = -H_k^T L_{k+1,k}^T — two 32 x 32 products per block row and right-hand side instead of 32 dependent
-// shuffle / fma steps, i.e. a contraction: the one place of this library where tensor cores apply (the scalar kernel
-// above runs at ~2 TFLOP/s because every step waits for the previous one).  k_band_blocks builds H, G, G' once per
-// factorisation (one CTA per block row) and stores them in the register layout of the DMMA B operand.
+// With 32 x 32 blocks the band of L is block-bidiagonal: L y = b reads  y_k = H_k (b_k - S_k y_{k-1})  with
+// H_k = L_kk^{-1} (lower triangular) and S_k = L_{k,k-1} (UPPER triangular: the band is 32 wide), and L^T x = y reads
+// x_k = H_k^T (y_k - S_{k+1}^T x_{k+1}) — two TRIANGULAR 32 x 32 products per block row and right-hand side instead of 32
+// dependent shuffle / fma steps, i.e. a contraction: the one place of this library where tensor cores apply (the scalar
+// kernel above runs at ~2 TFLOP/s because every step waits for the previous one).  k_band_blocks builds H once per
+// factorisation (one CTA per block row) and stores H, -S and their transposes in the register layout of the DMMA B
+// operand.  (Round 2 first used y_k = H_k b_k + G_k y_{k-1} with the full block G_k = -H_k S_k: 26 non-zero 8 x 8 tiles per
+// block row; the two triangular factors have 20, and the kernel is bound by the FP64 MMA pipe.)
 //
-// The solve works on the transposed problem (samples x rows), Y_k^T = B_k^T H_k^T + Y_{k-1}^T G_k^T, so that a warp's
+// The solve works on the transposed problem (samples x rows), Y_k^T = (B_k^T - Y_{k-1}^T S_k^T) H_k^T, so that a warp's
 // 16 samples are the M dimension (two 8-row tiles) and the previous block's result is the A operand of the next
 // product.  The accumulator layout of m8n8k4 (thread t holds row t/4, columns 2(t%4), 2(t%4)+1 of an 8 x 8 tile) differs
 // from the A layout (row t/4, column t%4) — but a contraction may enumerate its k index in any order as long as both
 // operands agree: k-step (tile nt', half j) is DEFINED to cover the columns 8nt' + 2(t%4) + j, which are exactly the
 // accumulator registers the thread already holds.  The B fragments are stored with the matching permutation, and the
 // result of one block row feeds the next one without a single shuffle or shared-memory round trip.
-constexpr int FRAGD = 2048;   // doubles per block row and direction: H fragments (1024), then G fragments (1024)
+constexpr int FRAGD = 2048;   // doubles per block row and direction: H fragments (1024), then -S fragments (1024)
 constexpr int MMA_W = 8;      // warps per CTA of the solve kernel
 constexpr int MMA_S = 16;     // samples per warp (two m8 tiles)
 
 __global__ void __launch_bounds__(256) k_band_blocks(int npad, const double* __restrict__ invd, const double* __restrict__ Lr,
                                                      double* __restrict__ Ff, double* __restrict__ Bf) {
-  __shared__ double D[32][33], S[32][33], U[32][33], H[32][33], G2[32][33];
-  double (*G)[33] = D;   // L_kk is dead once H exists: G takes its place
+  __shared__ double D[32][33], S[32][33], U[32][33], H[32][33];
   const int k = blockIdx.x, nb = npad >> 5, tid = threadIdx.x;
   for (int q = tid; q < 1024; q += 256) {
     const int a = q >> 5, b = q & 31;
@@ -1193,28 +1194,16 @@ __global__ void __launch_bounds__(256) k_band_blocks(int npad, const double* __r
     for (int r = 0; r < 32; ++r) H[r][c] = h[r];
   }
   __syncthreads();
-  for (int q = tid; q < 1024; q += 256) {
-    const int r = q >> 5, c = q & 31;
-    double g = 0.0, g2 = 0.0;
-#pragma unroll 8
-    for (int a = 0; a < 32; ++a) {
-      g = fma(H[r][a], S[a][c], g);
-      g2 = fma(H[a][r], U[c][a], g2);
-    }
-    G[r][c] = -g;
-    G2[r][c] = -g2;
-  }
-  __syncthreads();
   double* ff = Ff + static_cast<size_t>(k) * FRAGD;
   double* bf = Bf + static_cast<size_t>(k) * FRAGD;
   for (int q = tid; q < 1024; q += 256) {
     const int f = q >> 5, t = q & 31;
     const int nt = f & 3, j = (f >> 2) & 1, ntp = f >> 3;
     const int cc = 8 * ntp + 2 * (t & 3) + j, rr = 8 * nt + (t >> 2);
-    ff[q] = H[rr][cc];            // forward:  out[s][r] += in[s][c] H[r][c]
-    ff[1024 + q] = G[rr][cc];
-    bf[q] = H[cc][rr];            // backward: out[s][r] += in[s][c] H[c][r]
-    bf[1024 + q] = G2[rr][cc];
+    ff[q] = H[rr][cc];            // forward:  out[s][r] += in[s][c] H[r][c]          (zero for c > r)
+    ff[1024 + q] = -S[rr][cc];    //           t[s][r]   += y_prev[s][c] (-S[r][c])    (zero for c < r)
+    bf[q] = H[cc][rr];            // backward: out[s][r] += in[s][c] H[c][r]          (zero for c < r)
+    bf[1024 + q] = -U[cc][rr];    //           t[s][r]   += x_next[s][c] (-U[c][r])    (zero for c > r)
   }
 }
 
@@ -1301,37 +1290,17 @@ __global__ void __launch_bounds__(32 * MMA_W, 2) k_band_solve_mma(int npad, long
     mbar_wait(&bar[step & 1], (step >> 1) & 1);
     const double* sH = stg[step & 1];
     const double* sG = sH + 1024;
+    // ---- stage 1: t = rhs of this block - S y_prev (forward) / - S_next^T x_next (backward).  The right-hand side is already
+    // in the accumulator layout; S is triangular: 10 of its 16 8 x 8 tiles are non-zero.
+    double t[2][4][2];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
-    // ---- H_k applied to this block's right-hand side.  H_k = L_kk^{-1} is lower triangular (its transpose, used on the
-    // way back, upper triangular): 6 of the 16 8 x 8 tiles are zero and are skipped (the kernel is bound by the FP64 MMA
-    // pipe: ncu `math` 43 % of the stall samples)
-    if (step < nb) {
-#pragma unroll
-      for (int ntp = 0; ntp < 4; ++ntp)
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-#pragma unroll
-          for (int nt = ntp; nt < 4; ++nt) {      // out[s][r] += in[s][c] H[r][c], zero for c > r
-            const double b = sH[((ntp * 2 + j) * 4 + nt) * 32 + lane];
-            dmma884(acc[0][nt][0], acc[0][nt][1], R[0][ntp][j], b);
-            dmma884(acc[1][nt][0], acc[1][nt][1], R[1][ntp][j], b);
-          }
-    } else {
-#pragma unroll
-      for (int ntp = 0; ntp < 4; ++ntp)
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-#pragma unroll
-          for (int nt = 0; nt <= ntp; ++nt) {     // out[s][r] += in[s][c] H[c][r], zero for c < r
-            const double b = sH[((ntp * 2 + j) * 4 + nt) * 32 + lane];
-            dmma884(acc[0][nt][0], acc[0][nt][1], R[0][ntp][j], b);
-            dmma884(acc[1][nt][0], acc[1][nt][1], R[1][ntp][j], b);
-          }
-    }
-    // ---- the right-hand side of the next step is in flight while G_k is applied to the previous block's result
+      for (int nt = 0; nt < 4; ++nt) {
+        t[mt][nt][0] = R[mt][nt][0];
+        t[mt][nt][1] = R[mt][nt][1];
+      }
+    // ---- the right-hand side of the next step is in flight while the two products run
     const int knext = step + 1 < nb ? step + 1 : nsteps - 2 - step;   // block of step + 1 (== k at the turn-around)
     if (step + 1 < nsteps && knext != k) {
       if (GIN && step + 1 < nb) {
@@ -1348,15 +1317,57 @@ __global__ void __launch_bounds__(32 * MMA_W, 2) k_band_solve_mma(int npad, long
       }
     }
     if (step != 0 && step != nb) {   // first block of a pass: nothing above / below it
+      if (step < nb) {
+#pragma unroll
+        for (int ntp = 0; ntp < 4; ++ntp)
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int nt = 0; nt <= ntp; ++nt) {     // t[s][r] += y_prev[s][c] (-S[r][c]), zero for c < r
+              const double b = sG[((ntp * 2 + j) * 4 + nt) * 32 + lane];
+              dmma884(t[0][nt][0], t[0][nt][1], P[0][ntp][j], b);
+              dmma884(t[1][nt][0], t[1][nt][1], P[1][ntp][j], b);
+            }
+      } else {
+#pragma unroll
+        for (int ntp = 0; ntp < 4; ++ntp)
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int nt = ntp; nt < 4; ++nt) {      // t[s][r] += x_next[s][c] (-U[c][r]), zero for c > r
+              const double b = sG[((ntp * 2 + j) * 4 + nt) * 32 + lane];
+              dmma884(t[0][nt][0], t[0][nt][1], P[0][ntp][j], b);
+              dmma884(t[1][nt][0], t[1][nt][1], P[1][ntp][j], b);
+            }
+      }
+    }
+    // ---- stage 2: H_k (forward; lower triangular) or H_k^T (backward; upper triangular) applied to t — the accumulators of
+    // stage 1 are the A operand (see above); 10 non-zero tiles
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+    if (step < nb) {
 #pragma unroll
       for (int ntp = 0; ntp < 4; ++ntp)
 #pragma unroll
         for (int j = 0; j < 2; ++j)
 #pragma unroll
-          for (int nt = 0; nt < 4; ++nt) {
-            const double b = sG[((ntp * 2 + j) * 4 + nt) * 32 + lane];
-            dmma884(acc[0][nt][0], acc[0][nt][1], P[0][ntp][j], b);
-            dmma884(acc[1][nt][0], acc[1][nt][1], P[1][ntp][j], b);
+          for (int nt = ntp; nt < 4; ++nt) {      // out[s][r] += t[s][c] H[r][c], zero for c > r
+            const double b = sH[((ntp * 2 + j) * 4 + nt) * 32 + lane];
+            dmma884(acc[0][nt][0], acc[0][nt][1], t[0][ntp][j], b);
+            dmma884(acc[1][nt][0], acc[1][nt][1], t[1][ntp][j], b);
+          }
+    } else {
+#pragma unroll
+      for (int ntp = 0; ntp < 4; ++ntp)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int nt = 0; nt <= ntp; ++nt) {     // out[s][r] += t[s][c] H[c][r], zero for c < r
+            const double b = sH[((ntp * 2 + j) * 4 + nt) * 32 + lane];
+            dmma884(acc[0][nt][0], acc[0][nt][1], t[0][ntp][j], b);
+            dmma884(acc[1][nt][0], acc[1][nt][1], t[1][ntp][j], b);
           }
     }
 #pragma unroll
