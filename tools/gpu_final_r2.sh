@@ -30,6 +30,7 @@ timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k k1
 SE="python bench.py --workload c2e --steps 1 --warmup 1 --no-e2e --no-cpu"
 timeout -s KILL 600 ncu --set full --clock-control none -k regex:k1d_pe -s 4 -c 4 -f -o gpurun_out/prof_c2e_r2 $SE > gpurun_out/ncu_c2e_r2.log 2>&1; echo "full c2e rc=$?"
 timeout -s KILL 300 python examples/convergence_2d.py > gpurun_out/convergence_2d.log 2>&1; echo "convergence example rc=$?"
+timeout -s KILL 300 python examples/topopt_heat.py > gpurun_out/topopt_heat.log 2>&1; echo "topology optimisation example rc=$?"
 # the summaries are generated HERE as well (gpurun merges at most 64 MiB back: if the captures are larger, the largest
 # .ncu-rep files are dropped after their summaries exist)
 python tools/make_profiles.py r02 > gpurun_out/make_profiles.log 2>&1; echo "make_profiles rc=$?"
