@@ -6,9 +6,9 @@ dL/dkappa, as hand-written sm_100a CUDA behind the C ABI of ``include/dfe.h``.  
 (the reference's package name) resolves to thin aliases of these modules.
 """
 from .mesh import FEMesh
-from .solver import DifferentiableFESolver
+from .solver import DifferentiableFESolver, assemble_sparse
 from .loss import PhysicsLoss
 from .neural import NeuralPDE
 
 __version__ = "0.1.0"
-__all__ = ["FEMesh", "DifferentiableFESolver", "PhysicsLoss", "NeuralPDE"]
+__all__ = ["FEMesh", "DifferentiableFESolver", "PhysicsLoss", "NeuralPDE", "assemble_sparse"]

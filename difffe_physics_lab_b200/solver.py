@@ -699,6 +699,39 @@ def _general_backward(L, nm, gbar, u, kappa, mode, mats, gf, gk, opts):
         gk.copy_(gk_b.reshape(gk.shape))
 
 
+def assemble_sparse(mesh: FEMesh, kappa, f: torch.Tensor, device=None):
+    """``(K, F)``: the stiffness matrix of ``mesh`` as a ``torch.sparse_csr_tensor`` on the GPU and the load vector, BEFORE
+    the Dirichlet elimination — the arrays the reference builds densely in ``solver.py:82-96`` / ``:112-145`` (its roadmap
+    item "sparse matrix assembly", README.md:139-143 upstream).  For P1 meshes the values and the pattern are bit-identical
+    to the reference's dense ``K`` / ``F`` (rows and columns ascending; structural entries that happen to be 0 are kept);
+    ``kappa`` is a number, a 0-dim / 1-element tensor or an ``(n_elements,)`` field.  No gradients flow through this call."""
+    if mesh.dim not in (1, 2):
+        raise NotImplementedError("Only 1D and 2D supported")
+    if not torch.cuda.is_available():
+        raise RuntimeError("assemble_sparse (difffe_physics_lab_b200) runs on CUDA only; there is deliberately no CPU fallback")
+    dev = torch.device(device) if device is not None else (f.device if f.is_cuda else torch.device("cuda", torch.cuda.current_device()))
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    L = _native.lib()
+    nm = mesh._native(dev.index)
+    I = nm.info
+    kap = torch.as_tensor(kappa, dtype=torch.float64).detach().reshape(-1).to(dev).contiguous()
+    if kap.numel() not in (1, mesh.n_elements):
+        raise ValueError(f"kappa must have 1 or n_elements={mesh.n_elements} entries, got {kap.numel()}")
+    mode = _native.KAPPA_SCALAR if kap.numel() == 1 else _native.KAPPA_PER_ELEMENT
+    if f.shape != (mesh.n_nodes,):
+        raise ValueError(f"f must have shape ({mesh.n_nodes},), got {tuple(f.shape)}")
+    fd = f.detach().to(device=dev, dtype=torch.float64).contiguous()
+    with torch.cuda.device(dev):
+        vals = torch.empty(max(I.nnz_full, 1), dtype=torch.float64, device=dev)
+        F = torch.empty(I.n_nodes, dtype=torch.float64, device=dev)
+        _native.check(L.dfe_assemble(nm.handle, kap.data_ptr(), mode, fd.data_ptr(), vals.data_ptr(), F.data_ptr(), _stream(dev)))
+        rp, col = nm.csr(0)
+        K = torch.sparse_csr_tensor(torch.from_numpy(rp).to(dev), torch.from_numpy(col).to(dev), vals[:I.nnz_full],
+                                    size=(I.n_nodes, I.n_nodes))
+    return K, F
+
+
 # ----------------------------------------------------------------------------- module
 class DifferentiableFESolver(nn.Module):
     """Assemble and solve the P1 FEM system for ``mesh`` and a nodal forcing ``f``.

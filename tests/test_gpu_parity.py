@@ -378,6 +378,23 @@ def test_assembly_three_kernels_same_bits(monkeypatch, nx, ny, scalar, scale):
         assert np.array_equal(out["tile"][0], ovals) and np.array_equal(out["tile"][1], oF)
 
 
+@pytest.mark.parametrize("name", ["rect7x5_rand", "rect5x4_partial_bc", "line40_rand"])
+def test_assemble_sparse_public_api(golden, name):
+    """``assemble_sparse`` (the reference roadmap's sparse assembly): the torch CSR matrix densifies to the reference's K bit for
+    bit, F likewise; the matrix applies like the dense one."""
+    import warnings
+    from difffe_physics_lab_b200 import assemble_sparse
+    c = golden.case(name)
+    m = mesh_from_case(c)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        K, F = assemble_sparse(m, float(c["kappa"]), torch.as_tensor(c["f"]))
+        assert K.is_cuda and K.layout == torch.sparse_csr
+        assert np.array_equal(K.to_dense().cpu().numpy(), c["K"]) and np.array_equal(F.cpu().numpy(), c["F"])
+        x = torch.linspace(0, 1, m.n_nodes, dtype=torch.float64, device="cuda")
+        assert np.allclose((K @ x).cpu().numpy(), c["K"] @ x.cpu().numpy(), rtol=0, atol=1e-12 * np.abs(c["K"]).max())
+
+
 @pytest.mark.parametrize("name", CASES_2D)
 def test_2d_golden(golden, name):
     c = golden.case(name)
