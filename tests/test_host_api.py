@@ -42,6 +42,11 @@ def test_compute_calls_fail_loudly_without_a_device():
     m = FEMesh.line(10)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         DifferentiableFESolver(m)(torch.ones(11))
+    from difffe_physics_lab_b200 import assemble_sparse
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        assemble_sparse(m, 1.0, torch.ones(11))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        DifferentiableFESolver(m.to_p2())(torch.ones(21))
     with pytest.raises(_native.DfeError):
         m._native(0)   # asking for a device that is not there
     # host-only handle: compute entry points refuse
